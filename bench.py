@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of exact cosine top-k over a row-sharded synthetic corpus (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one batch of `--batch` queries scanned against the whole corpus (each rank scans its
+row shard, one allgather of the per-rank top-k lists, k-way merge).  Total corpus size is fixed as
+N grows (strong scaling: the metric is quoted on ONE 10M x 768 corpus at 1/2/4/8 GPUs).
+
+Prints ONE JSON line: value = whole-job QPS with inputs resident in HBM (CUDA events, max over
+ranks); e2e = the same through the host-buffer API (pinned host queries in, host results out);
+roofline = the scan kernel against the measured HBM peak; cpu_baseline = the CPU oracle
+(restatement of the reference's pgvector path) timed on this box's cores on a bounded sample.
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "QPS exact cosine top-10, 10Mx768 corpus"
+DEFAULT_BATCH = 4          # queries per step (see DESIGN.md "Measurement")
+CHUNK = 1 << 18            # rows generated per chunk; shard cuts fall on chunk boundaries
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--batch", type=int, default=DEFAULT_BATCH)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--sweep", default="1,64", help="extra batch sizes measured briefly at N=1 ('' = none)")
+    ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--cpu-queries", type=int, default=8, help="queries of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's pgvector path) on this box's cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_qps(args, steps: int, warmup: int) -> dict:
+    """Times oracle.search (C restatement of pgvector cosine_distance + ORDER BY/LIMIT, all host
+    threads) on a bounded sample: `cpu_rows` rows x `cpu_queries` queries per step, and scales the
+    per-query time linearly in the row count to the full corpus (the scan is linear in rows)."""
+    from oracle import oracle
+    from mrag_b200 import synth
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)
+    n_s, nq_s = min(args.cpu_rows, args.rows), args.cpu_queries
+    X, valid = synth.make_corpus(n_s, args.dim, seed=1234)
+    if args.dtype == "bf16":
+        X = oracle.round_bf16(X)
+    Q = synth.make_queries(X, nq_s, seed=4321)
+    mask = valid.astype(bool)
+    for _ in range(max(1, min(warmup, 1))):
+        oracle.search(X, Q[:1], args.k, mask)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.search(X, Q, args.k, mask)
+    dt = time.perf_counter() - t0
+    per_query_sample = dt / (steps * nq_s)
+    per_query_full = per_query_sample * (args.rows / n_s)
+    return {
+        "value": 1.0 / per_query_full, "unit": "queries/s", "cores": cores, "kind": "port",
+        "sample": f"{n_s} rows x {args.dim} ({args.dtype} rows upcast to fp32, as pgvector stores float4) x {nq_s} queries x "
+                  f"{steps} steps, {cores} scan threads; per-query time scaled x{args.rows / n_s:.0f} to {args.rows} rows",
+        "seconds": dt, "ms_per_query_sample": per_query_sample * 1e3,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    base = cpu_reference_qps(args, steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["seconds"] / steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.cpu_queries),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = Postgres+pgvector, not runnable here (no Postgres, extension not vendored): this arm "
+                "is the CPU oracle port of its exact-scan plan, all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {
+        "workload": f"{args.rows}x{args.dim} {args.dtype} corpus, top-{args.k}, query batch {batch}, row-sharded",
+        "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "k": args.k, "batch": batch,
+        "filter": "embedding_vec IS NOT NULL only", "l2": "inputs larger than L2 (no flush needed)",
+        "parallelism": f"rowshard{args.gpus}",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mrag_b200
+    from mrag_b200 import index as mi
+    from mrag_b200 import sharded, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the scan has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    # ---- build this rank's shard (chunk-aligned contiguous row block; 64 rows per document)
+    n_chunks = (args.rows + CHUNK - 1) // CHUNK
+    c_lo, c_hi = (n_chunks * rank) // world, (n_chunks * (rank + 1)) // world
+    lo, hi = min(c_lo * CHUNK, args.rows), min(c_hi * CHUNK, args.rows)
+    n_local = hi - lo
+    idx = mi.Index(args.dim, args.dtype, local_rank, max(n_local, 1))
+    idx.set_row_base(lo)
+    t_build = time.perf_counter()
+    plant = None
+    for first, X in synth.cuda_corpus_chunks(args.rows, args.dim, dev, seed=1234, chunk=CHUNK):
+        if first == 0:
+            plant = X[:4096].clone()                      # queries are planted near rows of chunk 0 on every rank
+        if first < lo:
+            if rank == 0 or first > 0:
+                pass
+            continue
+        if first >= hi:
+            break
+        m = X.shape[0]
+        meta = mi.make_meta(m, doc_idx=(np.arange(first, first + m) // 64).astype(np.uint32))
+        idx.append_device(X, meta)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    assert len(idx) == n_local
+
+    elem = 2 if args.dtype == "bf16" else 4
+    hbm_peak, peak_src = load_peaks()
+
+    def make_searcher():
+        if world > 1:
+            return sharded.ShardedSearcher(index=idx)
+        return None
+    ss = make_searcher()
+
+    def one_step(qd, k, out=None):
+        if ss is not None:
+            return ss.search(qd, k)
+        return idx.search_device(qd, k, out=out, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(batch: int, steps: int, warmup: int, sample_clocks: bool):
+        Q = synth.cuda_queries(plant, batch, args.dim, dev, seed=4321)
+        out = None
+        if ss is None:
+            out = (torch.empty((batch, args.k), dtype=torch.float32, device=dev),
+                   torch.empty((batch, args.k), dtype=torch.int64, device=dev),
+                   torch.empty((batch,), dtype=torch.int32, device=dev))
+        for _ in range(max(warmup, 3)):
+            res = one_step(Q, args.k, out)
+        barrier()
+        clocks = ClockSampler(local_rank) if sample_clocks else None
+        if clocks:
+            clocks.start()
+        mi.profile_begin(steps)
+        launches0 = mi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            res = one_step(Q, args.k, out)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = mi.launch_count() - launches0
+        scan_ms = [x for x in mi.profile_read(1, steps) if x >= 0]
+        prep_ms = [x for x in mi.profile_read(0, steps) if x >= 0]
+        merge_ms = [x for x in mi.profile_read(2, steps) if x >= 0]
+        mi.profile_begin(0)
+        clk = clocks.stop() if clocks else None
+        return {"batch": batch, "ms": ms, "steps": steps, "launches": launches, "scan_ms": scan_ms, "prep_ms": prep_ms,
+                "merge_ms": merge_ms, "clocks": clk, "result": res, "Q": Q}
+
+    def roofline_of(m, batch):
+        scan_launches = (batch + 3) // 4 if idx.last_scan_kind() == "gemv" else 1
+        if not m["scan_ms"]:
+            return None
+        per_launch_ms = float(np.mean(m["scan_ms"])) / scan_launches
+        q_per_launch = min(batch, 4) if idx.last_scan_kind() == "gemv" else batch
+        bytes_launch = n_local * args.dim * elem + (n_local + 7) // 8 + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12
+        ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "kernel": f"scan_{idx.last_scan_kind()}", "launches_per_step": scan_launches,
+                "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src}
+
+    # ---- headline
+    m = measure(args.batch, args.steps, args.warmup, sample_clocks=True)
+    qps = args.batch * args.steps / (m["ms"] * 1e-3)
+    roof = roofline_of(m, args.batch)
+
+    # ---- end to end through the host-buffer API: pinned host queries in, host results out, every step
+    Qh = m["Q"].cpu().pin_memory()
+    hs = torch.empty((args.batch, args.k), dtype=torch.float32).pin_memory()
+    hr = torch.empty((args.batch, args.k), dtype=torch.int64).pin_memory()
+    hc = torch.empty((args.batch,), dtype=torch.int32).pin_memory()
+    qd = torch.empty_like(m["Q"])
+
+    def e2e_step():
+        if ss is None:
+            idx.search_pinned(Qh, args.k, hs, hr, hc)          # H2D + scan + select + D2H + sync inside the C ABI
+        else:
+            qd.copy_(Qh, non_blocking=True)
+            s, r, c = ss.search(qd, args.k)
+            hs.copy_(s, non_blocking=True); hr.copy_(r, non_blocking=True); hc.copy_(c, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_qps = args.batch * args.steps / e2e_s
+    # the e2e path must return what the device path returned
+    if ss is None:
+        assert torch.equal(hr, m["result"][1].cpu()), "e2e result differs from device-resident result"
+
+    # ---- brief sweep over other batch sizes (N=1 only, not the headline)
+    sweep = []
+    if world == 1 and args.sweep:
+        for b in [int(x) for x in args.sweep.split(",") if x.strip()]:
+            if b == args.batch:
+                continue
+            mm = measure(b, 5, 3, sample_clocks=False)
+            rr = roofline_of(mm, b)
+            sweep.append({"batch": b, "qps": b * mm["steps"] / (mm["ms"] * 1e-3), "ms_per_step": mm["ms"] / mm["steps"],
+                          "scan_frac_of_hbm_peak": rr["frac"] if rr else None,
+                          "kernel": f"scan_{idx.last_scan_kind()}"})
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            b = cpu_reference_qps(args, steps=3, warmup=1)
+            cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:   # the GPU number stands even if the checker cannot be built here
+            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, args.batch),
+            "e2e": {"value": e2e_qps, "unit": "queries/s",
+                    "h2d_bytes_per_step": args.batch * args.dim * 4,
+                    "d2h_bytes_per_step": args.batch * args.k * 12 + args.batch * 4},
+            "gpu_launches": int(m["launches"]),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": m["clocks"],
+            "phases_ms": {"prepare": float(np.mean(m["prep_ms"])) if m["prep_ms"] else None,
+                          "scan": float(np.mean(m["scan_ms"])) if m["scan_ms"] else None,
+                          "merge": float(np.mean(m["merge_ms"])) if m["merge_ms"] else None},
+            "rows_per_gpu": n_local, "build_s": t_build, "sweep": sweep,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    idx.close()
+
+
+if __name__ == "__main__":
+    main()

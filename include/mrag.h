@@ -1,0 +1,224 @@
+/*
+ * mrag.h -- C ABI of the B200-native exact cosine top-k scan ("mrag").
+ *
+ * This is the drop-in boundary for ONE path of ananthlk/Mobius-RAG: the SQL shape
+ *
+ *     SELECT ..., 1 - (embedding_vec <=> :q) AS similarity
+ *     FROM rag_published_embeddings WHERE <filters> AND embedding_vec IS NOT NULL
+ *     ORDER BY embedding_vec <=> :q LIMIT :k
+ *
+ * issued by  app/services/vector_store.py:274-287  (PgVectorStore._search_async)
+ * and by     app/services/corpus_search.py:1525-1536 (_vector_arm).
+ * The reference has no FFI of its own for this path (it sends SQL to pgvector), so
+ * each entry point below names the reference statement it stands in for.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (streams travel as void*).
+ *   - every function returns 0 on success, a negative mrag_status otherwise;
+ *     mrag_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns every input buffer; the library copies what it keeps before
+ *     returning.  The index handle owns all device memory.
+ *   - "row" is a position in the index (0-based, append order); the host shim keeps the
+ *     row -> UUID / text hydration table (the reference hydrates in the same SELECT,
+ *     corpus_search.py:621-640).
+ *   - mrag_search* are re-entrant on one handle from several host threads (the reference
+ *     runs up to 5 narrow searches concurrently, corpus_search_agent.py:794-797);
+ *     append / tombstone take the writer side of the same lock.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with MRAG_ERR_CUDA.
+ */
+#ifndef MRAG_H_
+#define MRAG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRAG_VERSION_MAJOR 0
+#define MRAG_VERSION_MINOR 1
+
+typedef enum mrag_status {
+    MRAG_OK = 0,
+    MRAG_ERR_ARG = -1,      /* bad argument (null, dim mismatch, k out of range ...) */
+    MRAG_ERR_CUDA = -2,     /* CUDA runtime / driver failure, or no device */
+    MRAG_ERR_OOM = -3,      /* device or host allocation failed / capacity exceeded */
+    MRAG_ERR_STATE = -4     /* call not valid in this state */
+} mrag_status;
+
+/* storage type of the corpus in HBM */
+typedef enum mrag_dtype {
+    MRAG_F32 = 0,  /* float4 rows, as pgvector stores them (add_pgvector_columns.py:49) */
+    MRAG_BF16 = 1  /* bf16 rows (round-to-nearest-even of the fp32 input); 1e-2 score mode */
+} mrag_dtype;
+
+/* largest k the fused scan+select handles in one pass; callers may ask for up to
+ * MRAG_MAX_K (vector arm LIMIT = k*2*over_fetch <= 1600, corpus_search.py:1458,3297),
+ * larger k go through the multi-round path inside mrag_search. */
+#define MRAG_FUSED_K 128
+#define MRAG_MAX_K 2048
+
+/* code-space limits of the denormalised metadata columns */
+#define MRAG_PAYER_WORDS 16   /* payer codes < 1024  */
+#define MRAG_SMALL_WORDS 4    /* state / program / authority / source_type codes < 256 */
+#define MRAG_TAG_WORDS 8      /* document d: and p: tag codes, one bit each, < 512 (lexicon has ~231 codes, corpus_search_lexicon.py:4) */
+#define MRAG_CODE_NONE 0xFFFF /* "column is empty string" code for payer; 0xFF for the u8 columns */
+
+/*
+ * One row of rag_published_embeddings as the scan sees it (app/models.py:242-280):
+ * the document-level columns are denormalised on every row, exactly like the table.
+ * Strings are dictionary-coded by the host shim (mrag/vocab.py); equality on codes is
+ * equality on strings.
+ */
+typedef struct mrag_rowmeta {
+    uint32_t doc_idx;     /* dense index of document_id                        */
+    uint16_t payer;       /* code of document_payer                            */
+    uint8_t  state;       /* code of document_state                            */
+    uint8_t  program;     /* code of document_program                          */
+    uint8_t  authority;   /* code of document_authority_level                  */
+    uint8_t  source_type; /* code of source_type                               */
+    uint8_t  valid;       /* 0 <=> embedding_vec IS NULL (vector_store.py:263-266) */
+    uint8_t  reserved;
+} mrag_rowmeta;
+
+/* which clauses of mrag_filter are active */
+enum {
+    MRAG_F_PAYER       = 1u << 0,  /* payer IN payer_any  OR (payer IN payer_alt_any AND state = alt_state)
+                                      -- corpus_search.py:524-535 incl. the FL-Medicaid MCO union      */
+    MRAG_F_STATE       = 1u << 1,  /* document_state = state_eq            corpus_search.py:536-538  */
+    MRAG_F_PROGRAM     = 1u << 2,  /* document_program = program_eq        corpus_search.py:539-541  */
+    MRAG_F_AUTHORITY   = 1u << 3,  /* document_authority_level = ..        corpus_search.py:542-544  */
+    MRAG_F_SOURCE_TYPE = 1u << 4,  /* source_type = ..                     vector_store.py:156       */
+    MRAG_F_DOC_EQ      = 1u << 5,  /* document_id = :document_id           vector_store.py:247-249   */
+    MRAG_F_DOC_POOL    = 1u << 6,  /* document_id = ANY(:inc_ids)          corpus_search.py:546-558  */
+    MRAG_F_TAG_STRICT  = 1u << 7,  /* OR(state IN, program IN, payer IN)   corpus_search.py:1478-1496 */
+    MRAG_F_TAG_RELAXED = 1u << 8   /* doc d/p tag bitset & tag_any != 0    corpus_search.py:1497-1510 */
+};
+
+typedef struct mrag_filter {
+    uint32_t flags;
+    /* MRAG_F_PAYER */
+    uint64_t payer_any[MRAG_PAYER_WORDS];
+    uint64_t payer_alt_any[MRAG_PAYER_WORDS];
+    uint16_t alt_state;                /* state code required with payer_alt_any */
+    /* equality clauses (codes); a code that exists nowhere in the corpus matches no row */
+    uint16_t state_eq;
+    uint16_t program_eq;
+    uint16_t authority_eq;
+    uint16_t source_type_eq;
+    uint16_t reserved0;
+    uint32_t doc_eq;
+    /* MRAG_F_DOC_POOL: host array of doc_idx values (copied by the call) */
+    const uint32_t* doc_pool;
+    int64_t n_doc_pool;
+    /* MRAG_F_TAG_STRICT: one OR group over three code sets */
+    uint64_t tag_state_any[MRAG_SMALL_WORDS];
+    uint64_t tag_program_any[MRAG_SMALL_WORDS];
+    uint64_t tag_payer_any[MRAG_PAYER_WORDS];
+    /* MRAG_F_TAG_RELAXED: document tag bits, any-of */
+    uint64_t tag_any[MRAG_TAG_WORDS];
+} mrag_filter;
+
+typedef struct mrag_index mrag_index;
+
+/* --- lifecycle ---------------------------------------------------------------------- */
+
+/* CREATE TABLE .. embedding_vec vector(dim)   (add_pgvector_columns.py:56-65).
+ * capacity = maximum number of rows this shard will ever hold (device memory is
+ * reserved up front: capacity * round_up(dim,64) * sizeof(elem)). */
+int mrag_create(mrag_index** out, int dim, int dtype, int device, int64_t capacity);
+int mrag_destroy(mrag_index* idx);
+
+/* --- write side --------------------------------------------------------------------- */
+
+/* UPDATE .. SET embedding_vec = CAST('[..]' AS vector)  (embedding_worker.py:65-94,
+ * publish.py:327-362).  rows = n*dim float32, HOST memory, row-major; meta = n entries.
+ * Elements must be finite (pgvector rejects NaN/Inf on input). Returns the first new row
+ * index through *first_row (may be NULL). */
+int mrag_append(mrag_index* idx, const float* rows, int64_t n, const mrag_rowmeta* meta,
+                int64_t* first_row);
+/* same, rows already resident on the index's device (fp32, row-major, pitch = dim).
+ * `stream` is a cudaStream_t or NULL. */
+int mrag_append_device(mrag_index* idx, const void* d_rows_f32, int64_t n,
+                       const mrag_rowmeta* meta, int64_t* first_row, void* stream);
+
+/* document_tags.d_tags / p_tags key sets as bitsets (app/models.py:525-543):
+ * bits = n_docs * MRAG_TAG_WORDS u64, doc-major; replaces docs [first_doc, first_doc+n_docs). */
+int mrag_set_doc_tags(mrag_index* idx, int64_t first_doc, const uint64_t* bits, int64_t n_docs);
+
+/* DELETE FROM .. WHERE document_id = :id  (publish.py:310-313, vector_store.py:101-104):
+ * clears the valid bit of every row whose doc_idx matches. *n_rows (may be NULL) gets the count. */
+int mrag_tombstone_doc(mrag_index* idx, uint32_t doc_idx, int64_t* n_rows);
+
+int64_t mrag_size(const mrag_index* idx);      /* rows appended so far (incl. tombstoned) */
+int64_t mrag_capacity(const mrag_index* idx);
+int mrag_dim(const mrag_index* idx);
+int mrag_index_dtype(const mrag_index* idx);
+int mrag_device(const mrag_index* idx);
+
+/* --- read side ---------------------------------------------------------------------- */
+
+/* search options */
+enum {
+    MRAG_OPT_DEVICE_IO   = 1u << 0, /* q / scores / rows / counts are DEVICE pointers on the index's device */
+    MRAG_OPT_FORCE_GEMV  = 1u << 1, /* pin the CUDA-core streaming kernel (testing / tuning) */
+    MRAG_OPT_FORCE_MMA   = 1u << 2, /* pin the tcgen05 kernel (testing / tuning)             */
+    MRAG_OPT_NO_SYNC     = 1u << 3  /* with DEVICE_IO: enqueue only, do not synchronise the stream */
+};
+
+/*
+ * The scan: for each of nq queries, ORDER BY embedding_vec <=> q LIMIT k over the rows that
+ * pass `filter` (NULL = only "embedding_vec IS NOT NULL").
+ *   q       nq*dim float32 (query vectors are float4 server side, vector_store.py:272)
+ *   scores  nq*k  float32   similarity = 1 - cosine_distance, descending; NaN for zero-norm rows
+ *   rows    nq*k  int64     row index + row_base; -1 beyond counts[i]
+ *   counts  nq    int32     rows returned (< k when fewer rows pass the filter)
+ * Ordering: similarity descending, NaN last, ties by ascending row (pgvector leaves ties
+ * unspecified; this library fixes them so results do not depend on sharding).
+ * `stream`: cudaStream_t to run on, or NULL for an internal per-call stream.
+ */
+int mrag_search(mrag_index* idx, const float* q, int nq, int k, const mrag_filter* filter,
+                float* scores, int64_t* rows, int32_t* counts, uint32_t options, void* stream);
+
+/* Global row id offset added to every returned row (shard base for row-sharded corpora). */
+int mrag_set_row_base(mrag_index* idx, int64_t row_base);
+
+/* K4: k-way merge of `n_lists` per-shard results into one nq*k result on `device`.
+ * This is the step that follows the allgather across row shards.  List l lives at
+ * (d_scores_in + l*stride_scores)[nq*k], (d_rows_in + l*stride_rows)[nq*k],
+ * (d_counts_in + l*stride_counts)[nq]  (strides in ELEMENTS of each array, so the three arrays
+ * of one shard may sit in one packed allgather slot).  DEVICE pointers.  n_lists*k <= 16384. */
+int mrag_merge_topk(int device, int n_lists, int nq, int k,
+                    const float* d_scores_in, const int64_t* d_rows_in, const int32_t* d_counts_in,
+                    int64_t stride_scores, int64_t stride_rows, int64_t stride_counts,
+                    float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream);
+
+/* K2 alone: evaluate `filter` into a row bitmap (bit r of word r/32), DEVICE pointer,
+ * ceil(size/32) words; *n_pass (HOST, may be NULL) gets the popcount. */
+int mrag_filter_mask(mrag_index* idx, const mrag_filter* filter, uint32_t* d_mask_out,
+                     int64_t* n_pass, void* stream);
+
+/* per-kernel device time of the LAST mrag_search on this thread, CUDA events, ms.
+ * what: 0 = prepare (query prep + filter-mask), 1 = scan (score + per-producer select),
+ *       2 = merge/finalize (+ NaN tail), 3 = whole call on the device.
+ * Synchronises on the call's end event. Returns a negative value if there is none. */
+float mrag_last_kernel_ms(int what);
+/* Profiling ring for benchmarks: after mrag_profile_begin(n) the next n searches ON THIS THREAD
+ * record their own event set (no synchronisation is added to the search). mrag_profile_read
+ * waits for them and writes up to `max` durations (ms) of phase `what` (as above) in call
+ * order; returns how many were written. mrag_profile_begin(0) releases the ring. */
+int mrag_profile_begin(int n);
+int mrag_profile_read(int what, float* out_ms, int max);
+/* number of kernels this library has launched in this process so far */
+int64_t mrag_launch_count(void);
+/* name of the scan kernel variant the last search on this thread used ("gemv", "mma") */
+const char* mrag_last_scan_kind(void);
+
+const char* mrag_last_error(void);
+const char* mrag_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRAG_H_ */

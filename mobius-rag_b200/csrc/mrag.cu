@@ -1,0 +1,783 @@
+// mrag.cu -- the C ABI of include/mrag.h: index lifecycle, write side, and the search driver
+// that strings the kernels together on one CUDA stream:
+//
+//   query_prep_kernel -> [pool_bitmap_kernel] -> [filter_mask_kernel]      (prepare)
+//   -> scan_gemv_kernel x ceil(nq / NQ)                                    (scan + fused select)
+//   -> merge_kernel -> nan_tail_kernel                                     (ORDER BY .. LIMIT k)
+//
+// Stands in for the SQL statement of app/services/vector_store.py:274-287 and
+// app/services/corpus_search.py:1525-1536 (see include/mrag.h for the clause-by-clause map).
+// There is no CPU path in this file: without a device every compute entry point fails.
+#include "../../include/mrag.h"
+#include "common.cuh"
+#include "prep.cuh"
+#include "scan_gemv.cuh"
+#include "select.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+using namespace mrag;
+
+// ------------------------------------------------------------------------------------------
+// errors / counters
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            int c_ = (e_ == cudaErrorMemoryAllocation) ? MRAG_ERR_OOM : MRAG_ERR_CUDA;        \
+            return fail(c_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define LAUNCHED()                                                                         \
+    do {                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(MRAG_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                 \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int host_next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------
+// per-call workspace (one per concurrent search; pooled on the index)
+// ------------------------------------------------------------------------------------------
+struct EventSet {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};   // start, prepared, scanned, end
+    bool recorded = false;
+    int create() {
+        for (auto& x : e) CU(cudaEventCreate(&x));
+        return 0;
+    }
+    void destroy() {
+        for (auto& x : e) if (x) { cudaEventDestroy(x); x = nullptr; }
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 4 + 64;
+        CU(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Workspace {
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the last (possibly still running) use
+    bool in_use = false;
+    EventSet ev;
+    DevBuf<float> qraw, qpad, qinv, scores;
+    DevBuf<__nv_bfloat16> qbf;
+    DevBuf<uint32_t> mask, pool, pool_bits;
+    DevBuf<uint64_t> part, ub;
+    DevBuf<int64_t> rows;
+    DevBuf<int32_t> counts;
+    DevBuf<int> flags;              // [0] need_tail
+    DevBuf<unsigned long long> npass;
+    void release() {
+        qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
+        mask.release(); pool.release(); pool_bits.release(); part.release(); ub.release();
+        rows.release(); counts.release(); flags.release(); npass.release();
+        ev.destroy();
+        if (own_stream) cudaStreamDestroy(own_stream);
+        own_stream = nullptr;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// the index
+// ------------------------------------------------------------------------------------------
+struct mrag_index {
+    int dim = 0, ld = 0, dtype = 0, device = 0, num_sms = 0;
+    int64_t capacity = 0, size = 0, row_base = 0;
+    int64_t n_docs = 0;                 // max doc_idx seen + 1
+    void* rows = nullptr;               // [capacity][ld] storage dtype
+    float* inv_norm = nullptr;          // [capacity] 1/|x| of the stored row (+inf: zero norm)
+    MetaCols cols{};
+    uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
+    int64_t n_tag_docs = 0, tag_docs_cap = 0;
+    cudaStream_t wstream = nullptr;     // write-side stream
+    std::shared_mutex lock;             // searches share, writers exclude
+    std::mutex ws_lock;
+    std::vector<Workspace*> pool;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static size_t elem_size(int dtype) { return dtype == MRAG_BF16 ? 2 : 4; }
+
+// thread-local record of the last search (for mrag_last_kernel_ms / mrag_last_scan_kind)
+static thread_local EventSet t_last_ev;          // borrowed handles (owned by a workspace / ring)
+static thread_local bool t_last_valid = false;
+static thread_local const char* t_last_kind = "none";
+static thread_local std::vector<EventSet> t_ring;
+static thread_local int t_ring_used = 0;
+static thread_local int t_ring_device = -1;
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int64_t capacity) {
+    if (!out) return fail(MRAG_ERR_ARG, "mrag_create: out is null");
+    *out = nullptr;
+    if (dim < 1 || dim > 16384) return fail(MRAG_ERR_ARG, "mrag_create: dim %d out of range [1,16384]", dim);
+    if (dtype != MRAG_F32 && dtype != MRAG_BF16) return fail(MRAG_ERR_ARG, "mrag_create: unknown dtype %d", dtype);
+    if (capacity < 1 || capacity > (int64_t(1) << 31) - 64)
+        return fail(MRAG_ERR_ARG, "mrag_create: capacity %lld out of range [1, 2^31-64]", (long long)capacity);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(MRAG_ERR_CUDA, "mrag_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(MRAG_ERR_ARG, "mrag_create: device %d not in [0,%d)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_create: cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(MRAG_ERR_CUDA, "mrag_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    mrag_index* x = new (std::nothrow) mrag_index();
+    if (!x) return fail(MRAG_ERR_OOM, "mrag_create: host allocation failed");
+    x->dim = dim;
+    x->ld = int(ceil_div(dim, 64) * 64);
+    x->dtype = dtype;
+    x->device = device;
+    x->num_sms = prop.multiProcessorCount;
+    x->capacity = capacity;
+    const int64_t cap32 = ceil_div(capacity, 32) * 32;
+    const size_t row_bytes = size_t(x->ld) * elem_size(dtype);
+    cudaError_t e = cudaSuccess;
+    // 2 MB of slack after the last row: the TMA / vector paths may touch a whole tile past `size`
+    if (e == cudaSuccess) e = cudaMalloc(&x->rows, size_t(cap32) * row_bytes + (2u << 20));
+    if (e == cudaSuccess) e = cudaMalloc(&x->inv_norm, size_t(cap32) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.doc_idx, size_t(cap32) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.payer, size_t(cap32) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.state, size_t(cap32));
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.program, size_t(cap32));
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.authority, size_t(cap32));
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.source_type, size_t(cap32));
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.valid, size_t(cap32 / 32 + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemset(x->cols.valid, 0, size_t(cap32 / 32 + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32) * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->wstream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        int code = (e == cudaErrorMemoryAllocation) ? MRAG_ERR_OOM : MRAG_ERR_CUDA;
+        fail(code, "mrag_create: %s (capacity %lld x ld %d x %zu B)", cudaGetErrorString(e),
+             (long long)capacity, x->ld, elem_size(dtype));
+        cudaGetLastError();
+        mrag_destroy(x);
+        t_err = std::string("mrag_create: ") + cudaGetErrorString(e);
+        return code;
+    }
+    *out = x;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_destroy(mrag_index* x) {
+    if (!x) return MRAG_OK;
+    DeviceGuard g(x->device);
+    cudaDeviceSynchronize();
+    for (Workspace* w : x->pool) { w->release(); delete w; }
+    x->pool.clear();
+    if (x->rows) cudaFree(x->rows);
+    if (x->inv_norm) cudaFree(x->inv_norm);
+    if (x->cols.doc_idx) cudaFree(x->cols.doc_idx);
+    if (x->cols.payer) cudaFree(x->cols.payer);
+    if (x->cols.state) cudaFree(x->cols.state);
+    if (x->cols.program) cudaFree(x->cols.program);
+    if (x->cols.authority) cudaFree(x->cols.authority);
+    if (x->cols.source_type) cudaFree(x->cols.source_type);
+    if (x->cols.valid) cudaFree(x->cols.valid);
+    if (x->doc_tags) cudaFree(x->doc_tags);
+    if (x->wstream) cudaStreamDestroy(x->wstream);
+    t_last_valid = false;
+    delete x;
+    return MRAG_OK;
+}
+
+extern "C" int64_t mrag_size(const mrag_index* x) { return x ? x->size : -1; }
+extern "C" int64_t mrag_capacity(const mrag_index* x) { return x ? x->capacity : -1; }
+extern "C" int mrag_dim(const mrag_index* x) { return x ? x->dim : -1; }
+extern "C" int mrag_index_dtype(const mrag_index* x) { return x ? x->dtype : -1; }
+extern "C" int mrag_device(const mrag_index* x) { return x ? x->device : -1; }
+
+extern "C" int mrag_set_row_base(mrag_index* x, int64_t row_base) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_row_base: null index");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    x->row_base = row_base;
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// write side
+// ------------------------------------------------------------------------------------------
+static int append_device_locked(mrag_index* x, const float* d_rows, int64_t n, const mrag_rowmeta* meta,
+                                int64_t first, cudaStream_t s, mrag_rowmeta* d_meta_scratch) {
+    const int wpb = 256 / 32;
+    if (x->dtype == MRAG_BF16)
+        store_rows_kernel<1><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm);
+    else
+        store_rows_kernel<0><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(d_meta_scratch, meta, size_t(n) * sizeof(mrag_rowmeta), cudaMemcpyHostToDevice, s));
+    scatter_meta_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, s>>>(d_meta_scratch, n, first, x->cols);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
+static int append_common(mrag_index* x, const float* rows, bool rows_on_device, int64_t n,
+                         const mrag_rowmeta* meta, int64_t* first_row, cudaStream_t user_stream) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_append: null index");
+    if (n < 0) return fail(MRAG_ERR_ARG, "mrag_append: n < 0");
+    if (n == 0) { if (first_row) *first_row = x->size; return MRAG_OK; }
+    if (!rows) return fail(MRAG_ERR_ARG, "mrag_append: rows is null");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    if (x->size + n > x->capacity)
+        return fail(MRAG_ERR_OOM, "mrag_append: %lld + %lld rows exceed capacity %lld", (long long)x->size,
+                    (long long)n, (long long)x->capacity);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_append: cudaSetDevice(%d) failed", x->device);
+    cudaStream_t s = x->wstream;
+    if (rows_on_device && user_stream) {
+        // order our stream after the producer of d_rows
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, user_stream));
+        CU(cudaStreamWaitEvent(s, ev, 0));
+        cudaEventDestroy(ev);
+    }
+    // default metadata: every row its own document, no codes, vector present
+    std::vector<mrag_rowmeta> defmeta;
+    const int64_t chunk = rows_on_device
+        ? std::min<int64_t>(n, int64_t(1) << 20)
+        : std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / (int64_t(x->dim) * 4)));
+    mrag_rowmeta* d_meta = nullptr;
+    float* d_stage = nullptr;
+    CU(cudaMalloc(&d_meta, size_t(chunk) * sizeof(mrag_rowmeta)));
+    if (!rows_on_device) {
+        cudaError_t e = cudaMalloc(&d_stage, size_t(chunk) * x->dim * 4);
+        if (e != cudaSuccess) { cudaFree(d_meta); return fail(MRAG_ERR_OOM, "mrag_append: staging alloc failed"); }
+    }
+    int rc = MRAG_OK;
+    int64_t max_doc = x->n_docs - 1;
+    for (int64_t off = 0; off < n && rc == MRAG_OK; off += chunk) {
+        const int64_t m = std::min(chunk, n - off);
+        const mrag_rowmeta* mp;
+        if (meta) {
+            mp = meta + off;
+        } else {
+            defmeta.resize(size_t(m));
+            for (int64_t i = 0; i < m; ++i) {
+                mrag_rowmeta r{};
+                r.doc_idx = uint32_t(x->size + off + i);
+                r.payer = MRAG_CODE_NONE; r.state = 0xFF; r.program = 0xFF; r.authority = 0xFF; r.source_type = 0xFF;
+                r.valid = 1;
+                defmeta[size_t(i)] = r;
+            }
+            mp = defmeta.data();
+        }
+        for (int64_t i = 0; i < m; ++i) max_doc = std::max<int64_t>(max_doc, mp[i].doc_idx);
+        const float* src = rows + off * x->dim;
+        if (!rows_on_device) {
+            cudaError_t e = cudaMemcpyAsync(d_stage, src, size_t(m) * x->dim * 4, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { rc = fail(MRAG_ERR_CUDA, "mrag_append: H2D failed: %s", cudaGetErrorString(e)); break; }
+            src = d_stage;
+        }
+        rc = append_device_locked(x, src, m, mp, x->size + off, s, d_meta);
+        // the host meta chunk / staging buffer are reused by the next iteration
+        if (rc == MRAG_OK) {
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_append: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(d_meta);
+    if (d_stage) cudaFree(d_stage);
+    if (rc != MRAG_OK) return rc;
+    if (first_row) *first_row = x->size;
+    x->size += n;
+    x->n_docs = max_doc + 1;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_append(mrag_index* x, const float* rows, int64_t n, const mrag_rowmeta* meta, int64_t* first_row) {
+    return append_common(x, rows, false, n, meta, first_row, nullptr);
+}
+
+extern "C" int mrag_append_device(mrag_index* x, const void* d_rows_f32, int64_t n, const mrag_rowmeta* meta,
+                                  int64_t* first_row, void* stream) {
+    return append_common(x, static_cast<const float*>(d_rows_f32), true, n, meta, first_row,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mrag_set_doc_tags(mrag_index* x, int64_t first_doc, const uint64_t* bits, int64_t n_docs) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_doc_tags: null index");
+    if (first_doc < 0 || n_docs < 0) return fail(MRAG_ERR_ARG, "mrag_set_doc_tags: negative range");
+    if (n_docs == 0) return MRAG_OK;
+    if (!bits) return fail(MRAG_ERR_ARG, "mrag_set_doc_tags: bits is null");
+    if (first_doc + n_docs > (int64_t(1) << 32)) return fail(MRAG_ERR_ARG, "mrag_set_doc_tags: doc index overflow");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_set_doc_tags: cudaSetDevice failed");
+    const int64_t need = first_doc + n_docs;
+    if (need > x->tag_docs_cap) {
+        int64_t cap = std::max<int64_t>(need + need / 2, 1024);
+        uint64_t* p = nullptr;
+        CU(cudaMalloc(&p, size_t(cap) * MRAG_TAG_WORDS * 8));
+        CU(cudaMemsetAsync(p, 0, size_t(cap) * MRAG_TAG_WORDS * 8, x->wstream));
+        if (x->doc_tags) {
+            CU(cudaMemcpyAsync(p, x->doc_tags, size_t(x->n_tag_docs) * MRAG_TAG_WORDS * 8, cudaMemcpyDeviceToDevice, x->wstream));
+            CU(cudaStreamSynchronize(x->wstream));
+            cudaFree(x->doc_tags);
+        }
+        x->doc_tags = p;
+        x->tag_docs_cap = cap;
+    }
+    CU(cudaMemcpyAsync(x->doc_tags + size_t(first_doc) * MRAG_TAG_WORDS, bits, size_t(n_docs) * MRAG_TAG_WORDS * 8,
+                       cudaMemcpyHostToDevice, x->wstream));
+    CU(cudaStreamSynchronize(x->wstream));
+    x->n_tag_docs = std::max(x->n_tag_docs, need);
+    return MRAG_OK;
+}
+
+extern "C" int mrag_tombstone_doc(mrag_index* x, uint32_t doc_idx, int64_t* n_rows) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_tombstone_doc: null index");
+    if (n_rows) *n_rows = 0;
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    if (x->size == 0) return MRAG_OK;
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_tombstone_doc: cudaSetDevice failed");
+    unsigned long long* d_hit = nullptr;
+    CU(cudaMalloc(&d_hit, 8));
+    CU(cudaMemsetAsync(d_hit, 0, 8, x->wstream));
+    tombstone_kernel<<<unsigned(ceil_div(x->size, 256)), 256, 0, x->wstream>>>(x->cols.doc_idx, x->size, doc_idx,
+                                                                              x->cols.valid, d_hit);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long hit = 0;
+    cudaError_t e = cudaMemcpyAsync(&hit, d_hit, 8, cudaMemcpyDeviceToHost, x->wstream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(x->wstream);
+    cudaFree(d_hit);
+    if (e != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_tombstone_doc: %s", cudaGetErrorString(e));
+    if (n_rows) *n_rows = int64_t(hit);
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspaces
+// ------------------------------------------------------------------------------------------
+static Workspace* acquire_ws(mrag_index* x, cudaStream_t want_stream) {
+    std::lock_guard<std::mutex> l(x->ws_lock);
+    Workspace* pick = nullptr;
+    for (Workspace* w : x->pool) {
+        if (w->in_use) continue;
+        // a workspace left running by a NO_SYNC call may be reused in stream order on the same
+        // stream, or by anyone once its end event has completed
+        if (w->last_stream == nullptr || (want_stream && w->last_stream == want_stream)) { pick = w; break; }
+        if (w->ev.recorded && cudaEventQuery(w->ev.e[3]) == cudaSuccess) { w->last_stream = nullptr; pick = w; break; }
+    }
+    if (!pick) {
+        pick = new (std::nothrow) Workspace();
+        if (!pick) return nullptr;
+        if (pick->ev.create() != 0 ||
+            cudaStreamCreateWithFlags(&pick->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            pick->release();
+            delete pick;
+            return nullptr;
+        }
+        x->pool.push_back(pick);
+    }
+    pick->in_use = true;
+    return pick;
+}
+
+static void release_ws(mrag_index* x, Workspace* w, cudaStream_t running_on) {
+    std::lock_guard<std::mutex> l(x->ws_lock);
+    w->last_stream = running_on;   // nullptr when the call synchronised
+    w->in_use = false;
+}
+
+// ------------------------------------------------------------------------------------------
+// filter -> device form
+// ------------------------------------------------------------------------------------------
+static void to_dev_filter(const mrag_filter* f, DevFilter* d) {
+    memset(d, 0, sizeof *d);
+    d->flags = f->flags;
+    memcpy(d->payer_any, f->payer_any, sizeof d->payer_any);
+    memcpy(d->payer_alt_any, f->payer_alt_any, sizeof d->payer_alt_any);
+    d->alt_state = f->alt_state; d->state_eq = f->state_eq; d->program_eq = f->program_eq;
+    d->authority_eq = f->authority_eq; d->source_type_eq = f->source_type_eq;
+    d->doc_eq = f->doc_eq;
+    memcpy(d->tag_state_any, f->tag_state_any, sizeof d->tag_state_any);
+    memcpy(d->tag_program_any, f->tag_program_any, sizeof d->tag_program_any);
+    memcpy(d->tag_payer_any, f->tag_payer_any, sizeof d->tag_payer_any);
+    memcpy(d->tag_any, f->tag_any, sizeof d->tag_any);
+}
+
+// builds the row bitmap for `f` into `mask_out` (ceil(n/32) words) on stream s
+static int build_mask(mrag_index* x, Workspace* w, const mrag_filter* f, int64_t n, uint32_t* mask_out,
+                      unsigned long long* d_npass, cudaStream_t s) {
+    DevFilter df;
+    to_dev_filter(f, &df);
+    const uint32_t* pool_bits = nullptr;
+    if (df.flags & MRAG_F_DOC_POOL) {
+        if (f->n_doc_pool < 0 || (f->n_doc_pool > 0 && !f->doc_pool))
+            return fail(MRAG_ERR_ARG, "mrag_filter: doc_pool is null or n_doc_pool < 0");
+        const int64_t words = ceil_div(std::max<int64_t>(x->n_docs, 1), 32);
+        if (w->pool_bits.reserve(size_t(words))) return MRAG_ERR_OOM;
+        CU(cudaMemsetAsync(w->pool_bits.p, 0, size_t(words) * 4, s));
+        if (f->n_doc_pool > 0) {
+            if (w->pool.reserve(size_t(f->n_doc_pool))) return MRAG_ERR_OOM;
+            CU(cudaMemcpyAsync(w->pool.p, f->doc_pool, size_t(f->n_doc_pool) * 4, cudaMemcpyHostToDevice, s));
+            pool_bitmap_kernel<<<unsigned(ceil_div(f->n_doc_pool, 256)), 256, 0, s>>>(w->pool.p, f->n_doc_pool,
+                                                                                     w->pool_bits.p, x->n_docs);
+            LAUNCHED();
+        }
+        pool_bits = w->pool_bits.p;
+    }
+    const int64_t n32 = ceil_div(n, 32) * 32;
+    filter_mask_kernel<<<unsigned(ceil_div(n32, 256)), 256, 0, s>>>(df, x->cols, n, pool_bits, x->doc_tags,
+                                                                   x->n_tag_docs, mask_out, d_npass);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scan dispatch
+// ------------------------------------------------------------------------------------------
+static const int kMaxSmem = 232448;   // 227 KB
+
+template <int DT, int NQ>
+static int launch_gemv(const ScanArgs& a, int grid, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = gemv_smem_bytes(NQ, a.ld, a.kp);
+    if (smem > size_t(kMaxSmem))
+        return fail(MRAG_ERR_ARG, "scan: %zu B of shared memory needed (dim too large for k)", smem);
+    if (dev < 64 && !attr_set[dev]) {
+        CU(cudaFuncSetAttribute(scan_gemv_kernel<DT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set[dev] = true;
+    }
+    scan_gemv_kernel<DT, NQ><<<grid, kGemvThreads, smem, s>>>(a);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
+static int gemv_nq_for(int nq, int ld, int kp) {
+    // widest query group whose buffers fit in shared memory
+    for (int g : {4, 2, 1})
+        if ((nq >= g || g == 1) && gemv_smem_bytes(g, ld, kp) <= size_t(kMaxSmem)) return g;
+    return 1;
+}
+
+static int run_scan_gemv(mrag_index* x, ScanArgs a, int nq, int grid, cudaStream_t s) {
+    int q0 = 0;
+    while (q0 < nq) {
+        const int left = nq - q0;
+        const int g = gemv_nq_for(left >= 3 ? 4 : left, a.ld, a.kp);
+        a.q0 = q0;
+        a.nq = std::min(g, left);
+        int rc;
+        if (x->dtype == MRAG_BF16) {
+            rc = g == 4 ? launch_gemv<1, 4>(a, grid, s) : g == 2 ? launch_gemv<1, 2>(a, grid, s) : launch_gemv<1, 1>(a, grid, s);
+        } else {
+            rc = g == 4 ? launch_gemv<0, 4>(a, grid, s) : g == 2 ? launch_gemv<0, 2>(a, grid, s) : launch_gemv<0, 1>(a, grid, s);
+        }
+        if (rc != MRAG_OK) return rc;
+        q0 += a.nq;
+    }
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------
+static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float* q, int nq, int k,
+                         const mrag_filter* filter, float* scores, int64_t* rows, int32_t* counts,
+                         uint32_t options, cudaStream_t s) {
+    const bool dev_io = options & MRAG_OPT_DEVICE_IO;
+    const int64_t n = x->size;
+    const int ld = x->ld;
+    const size_t nk = size_t(nq) * k;
+
+    CU(cudaEventRecord(ev.e[0], s));
+    // ---- queries
+    const float* d_q = q;
+    if (!dev_io) {
+        if (w->qraw.reserve(size_t(nq) * x->dim)) return MRAG_ERR_OOM;
+        CU(cudaMemcpyAsync(w->qraw.p, q, size_t(nq) * x->dim * 4, cudaMemcpyHostToDevice, s));
+        d_q = w->qraw.p;
+    }
+    if (w->qpad.reserve(size_t(nq) * ld) || w->qinv.reserve(size_t(nq)) || w->flags.reserve(4) ||
+        w->counts.reserve(size_t(nq)) || w->scores.reserve(nk) || w->rows.reserve(nk))
+        return MRAG_ERR_OOM;
+    query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(d_q, nq, x->dim, ld, w->qpad.p,
+                                                                               w->qinv.p, nullptr, nq);
+    LAUNCHED();
+    CU(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), s));
+
+    float* d_scores = dev_io ? scores : w->scores.p;
+    int64_t* d_rows = dev_io ? rows : w->rows.p;
+    int32_t* d_counts = dev_io ? counts : w->counts.p;
+
+    // ---- WHERE
+    const uint32_t* mask = x->cols.valid;     // embedding_vec IS NOT NULL
+    if (n > 0 && filter && filter->flags) {
+        if (w->mask.reserve(size_t(ceil_div(n, 32)) + 1)) return MRAG_ERR_OOM;
+        int rc = build_mask(x, w, filter, n, w->mask.p, nullptr, s);
+        if (rc != MRAG_OK) return rc;
+        mask = w->mask.p;
+    }
+    CU(cudaEventRecord(ev.e[1], s));
+
+    // ---- scan + select, MRAG_FUSED_K results per round
+    const int rounds = int(ceil_div(k, MRAG_FUSED_K));
+    const int64_t nwords = ceil_div(n, 32);
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
+    if (rounds > 1 && w->ub.reserve(size_t(nq))) return MRAG_ERR_OOM;
+    float scan_ms_dummy = 0; (void)scan_ms_dummy;
+    // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
+    // earlier rounds is attributed to the scan phase
+    for (int r = 0; r < rounds; ++r) {
+        const int k_off = r * MRAG_FUSED_K;
+        const int kr = std::min(MRAG_FUSED_K, k - k_off);
+        const int kp = std::max(8, host_next_pow2(kr));
+        if (w->part.reserve(size_t(nq) * grid * kp)) return MRAG_ERR_OOM;
+        if (n > 0) {
+            ScanArgs a{};
+            a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p;
+            a.ub = (r > 0) ? w->ub.p : nullptr;
+            a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid;
+            int rc = run_scan_gemv(x, a, nq, grid, s);
+            if (rc != MRAG_OK) return rc;
+            t_last_kind = "gemv";
+        } else {
+            CU(cudaMemsetAsync(w->part.p, 0, size_t(nq) * grid * kp * 8, s));
+        }
+        if (r == rounds - 1) CU(cudaEventRecord(ev.e[2], s));
+        MergeArgs m{};
+        m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = kr; m.k_total = k; m.k_off = k_off;
+        m.scores = d_scores; m.rows = d_rows; m.counts = d_counts; m.row_base = x->row_base;
+        m.ub_out = (rounds > 1) ? w->ub.p : nullptr;
+        m.need_tail = w->flags.p;
+        merge_kernel<<<nq, kMergeThreads, 0, s>>>(m);
+        LAUNCHED();
+    }
+    // ---- NaN tail (Postgres: NaN distances sort last)
+    if (n > 0) {
+        TailArgs t{};
+        t.inv_norm = x->inv_norm; t.mask = mask; t.n = n; t.qinv = w->qinv.p; t.nq = nq; t.k_total = k;
+        t.scores = d_scores; t.rows = d_rows; t.counts = d_counts; t.row_base = x->row_base;
+        t.need_tail = w->flags.p;
+        nan_tail_kernel<<<nq, 256, 0, s>>>(t);
+        LAUNCHED();
+    }
+    if (!dev_io) {
+        CU(cudaMemcpyAsync(scores, d_scores, nk * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(rows, d_rows, nk * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(counts, d_counts, size_t(nq) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaEventRecord(ev.e[3], s));
+    ev.recorded = true;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const mrag_filter* filter, float* scores,
+                           int64_t* rows, int32_t* counts, uint32_t options, void* stream) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_search: null index");
+    if (nq < 0) return fail(MRAG_ERR_ARG, "mrag_search: nq < 0");
+    if (nq == 0) return MRAG_OK;
+    if (nq > 65535) return fail(MRAG_ERR_ARG, "mrag_search: nq %d > 65535", nq);
+    if (k < 1 || k > MRAG_MAX_K) return fail(MRAG_ERR_ARG, "mrag_search: k %d not in [1,%d]", k, MRAG_MAX_K);
+    if (!q || !scores || !rows || !counts) return fail(MRAG_ERR_ARG, "mrag_search: null buffer");
+    const bool dev_io = options & MRAG_OPT_DEVICE_IO;
+    const bool no_sync = (options & MRAG_OPT_NO_SYNC) && dev_io;
+    if ((options & MRAG_OPT_NO_SYNC) && !dev_io)
+        return fail(MRAG_ERR_ARG, "mrag_search: MRAG_OPT_NO_SYNC needs MRAG_OPT_DEVICE_IO");
+    if (options & MRAG_OPT_FORCE_MMA)
+        return fail(MRAG_ERR_STATE, "mrag_search: the tcgen05 scan is not built into this version");
+
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_search: cudaSetDevice(%d) failed (no CPU path)", x->device);
+    Workspace* w = acquire_ws(x, static_cast<cudaStream_t>(stream));
+    if (!w) return fail(MRAG_ERR_OOM, "mrag_search: cannot create a workspace");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : w->own_stream;
+
+    EventSet* ev = &w->ev;
+    if (t_ring_used < int(t_ring.size()) && t_ring_device == x->device) ev = &t_ring[size_t(t_ring_used++)];
+    int rc = search_locked(x, w, *ev, q, nq, k, filter, scores, rows, counts, options, s);
+    if (ev != &w->ev) {
+        // keep the workspace's own end marker valid for reuse decisions
+        cudaEventRecord(w->ev.e[3], s);
+        w->ev.recorded = true;
+    }
+    if (rc == MRAG_OK && !no_sync) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_search: %s", cudaGetErrorString(e));
+    } else if (rc != MRAG_OK) {
+        cudaStreamSynchronize(s);
+        cudaGetLastError();
+    }
+    t_last_ev = *ev;
+    t_last_valid = (rc == MRAG_OK);
+    release_ws(x, w, (rc == MRAG_OK && no_sync) ? s : nullptr);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 alone, K4
+// ------------------------------------------------------------------------------------------
+extern "C" int mrag_filter_mask(mrag_index* x, const mrag_filter* filter, uint32_t* d_mask_out, int64_t* n_pass,
+                                void* stream) {
+    if (!x || !d_mask_out) return fail(MRAG_ERR_ARG, "mrag_filter_mask: null argument");
+    if (n_pass) *n_pass = 0;
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    const int64_t n = x->size;
+    if (n == 0) return MRAG_OK;
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_filter_mask: cudaSetDevice failed");
+    Workspace* w = acquire_ws(x, static_cast<cudaStream_t>(stream));
+    if (!w) return fail(MRAG_ERR_OOM, "mrag_filter_mask: cannot create a workspace");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : w->own_stream;
+    mrag_filter none;
+    memset(&none, 0, sizeof none);
+    int rc = MRAG_OK;
+    if (w->npass.reserve(1)) rc = MRAG_ERR_OOM;
+    if (rc == MRAG_OK && cudaMemsetAsync(w->npass.p, 0, 8, s) != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "memset failed");
+    if (rc == MRAG_OK) rc = build_mask(x, w, filter ? filter : &none, n, d_mask_out, w->npass.p, s);
+    unsigned long long np = 0;
+    if (rc == MRAG_OK) {
+        cudaError_t e = cudaMemcpyAsync(&np, w->npass.p, 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_filter_mask: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(s);
+    }
+    if (n_pass) *n_pass = int64_t(np);
+    release_ws(x, w, nullptr);
+    return rc;
+}
+
+extern "C" int mrag_merge_topk(int device, int n_lists, int nq, int k, const float* d_scores_in,
+                               const int64_t* d_rows_in, const int32_t* d_counts_in, int64_t stride_scores,
+                               int64_t stride_rows, int64_t stride_counts, float* d_scores_out,
+                               int64_t* d_rows_out, int32_t* d_counts_out, void* stream) {
+    if (n_lists < 1 || nq < 0 || k < 1) return fail(MRAG_ERR_ARG, "mrag_merge_topk: bad sizes");
+    if (nq == 0) return MRAG_OK;
+    if (int64_t(n_lists) * k > kXMergeMaxSlots)
+        return fail(MRAG_ERR_ARG, "mrag_merge_topk: n_lists*k = %lld > %d", (long long)n_lists * k, kXMergeMaxSlots);
+    if (!d_scores_in || !d_rows_in || !d_counts_in || !d_scores_out || !d_rows_out || !d_counts_out)
+        return fail(MRAG_ERR_ARG, "mrag_merge_topk: null buffer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_merge_topk: cudaSetDevice(%d) failed (no CPU path)", device);
+    static bool attr_set[64] = {};
+    if (device < 64 && !attr_set[device]) {
+        CU(cudaFuncSetAttribute(xmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXMergeMaxSlots * 12));
+        attr_set[device] = true;
+    }
+    XMergeArgs a{};
+    a.n_lists = n_lists; a.nq = nq; a.k = k;
+    a.scores_in = d_scores_in; a.rows_in = d_rows_in; a.counts_in = d_counts_in;
+    a.stride_scores = stride_scores; a.stride_rows = stride_rows; a.stride_counts = stride_counts;
+    a.scores_out = d_scores_out; a.rows_out = d_rows_out; a.counts_out = d_counts_out;
+    const int total = n_lists * k;
+    const size_t smem = size_t(host_next_pow2(total < 2 ? 2 : total)) * 12;
+    xmerge_kernel<<<nq, kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------
+static float phase_ms(const EventSet& ev, int what) {
+    if (!ev.recorded) return -1.0f;
+    if (cudaEventSynchronize(ev.e[3]) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    cudaError_t e;
+    switch (what) {
+        case 0: e = cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]); break;
+        case 1: e = cudaEventElapsedTime(&ms, ev.e[1], ev.e[2]); break;
+        case 2: e = cudaEventElapsedTime(&ms, ev.e[2], ev.e[3]); break;
+        case 3: e = cudaEventElapsedTime(&ms, ev.e[0], ev.e[3]); break;
+        default: return -1.0f;
+    }
+    return e == cudaSuccess ? ms : -1.0f;
+}
+
+extern "C" float mrag_last_kernel_ms(int what) {
+    if (!t_last_valid) return -1.0f;
+    return phase_ms(t_last_ev, what);
+}
+
+extern "C" int mrag_profile_begin(int n) {
+    for (auto& e : t_ring) e.destroy();
+    t_ring.clear();
+    t_ring_used = 0;
+    t_ring_device = -1;
+    t_last_valid = false;
+    if (n <= 0) return MRAG_OK;
+    if (n > 4096) return fail(MRAG_ERR_ARG, "mrag_profile_begin: n %d > 4096", n);
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    t_ring.resize(size_t(n));
+    for (auto& e : t_ring) {
+        int rc = e.create();
+        if (rc != 0) return MRAG_ERR_CUDA;
+    }
+    t_ring_device = dev;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_profile_read(int what, float* out_ms, int max) {
+    if (!out_ms || max < 0) return fail(MRAG_ERR_ARG, "mrag_profile_read: bad buffer");
+    int n = 0;
+    for (int i = 0; i < t_ring_used && n < max; ++i) out_ms[n++] = phase_ms(t_ring[size_t(i)], what);
+    return n;
+}
+
+extern "C" int64_t mrag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" const char* mrag_last_scan_kind(void) { return t_last_kind; }
+extern "C" const char* mrag_last_error(void) { return t_err.c_str(); }
+extern "C" const char* mrag_version(void) { return "mrag-b200 0.1 (sm_100a)"; }

@@ -1,0 +1,155 @@
+// prep.cuh -- write-side and per-call preparation kernels.
+//   store_rows_kernel   fp32 rows -> storage dtype (+ zero padding to ld) + 1/|x| of the STORED row
+//                       (embedding_worker.py:65-94 / publish.py:327-362 write float4 rows, un-normalised)
+//   scatter_meta_kernel mrag_rowmeta AoS -> SoA columns + valid bitmap
+//   filter_mask_kernel  K2: WHERE clauses -> row bitmap
+//                       (corpus_search.py:516-560, 1471-1523; vector_store.py:245-267)
+//   pool_bitmap_kernel  document_id = ANY(:inc_ids) -> document bitmap
+//   tombstone_kernel    DELETE .. WHERE document_id = :id
+//   query_prep_kernel   pad queries to ld, 1/|q|, bf16 copy for the tensor-core path
+#pragma once
+#include "common.cuh"
+#include "../../include/mrag.h"
+#include <math_constants.h>
+
+namespace mrag {
+
+// one warp per row
+template <int DT>
+__global__ void __launch_bounds__(256) store_rows_kernel(const float* __restrict__ src, int64_t n, int dim,
+                                                        void* __restrict__ dst, int ld, int64_t first_row,
+                                                        float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const float* s = src + r * dim;
+    float ss = 0.0f;
+    for (int e = lane; e < ld; e += 32) {
+        float v = (e < dim) ? s[e] : 0.0f;
+        if (DT == 1) {
+            __nv_bfloat16 b = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16*>(dst)[(first_row + r) * ld + e] = b;
+            v = __bfloat162float(b);
+        } else {
+            reinterpret_cast<float*>(dst)[(first_row + r) * ld + e] = v;
+        }
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv_norm[first_row + r] = (ss > 0.0f) ? 1.0f / sqrtf(ss) : CUDART_INF_F;
+}
+
+struct MetaCols {
+    uint32_t* doc_idx; uint16_t* payer; uint8_t* state; uint8_t* program; uint8_t* authority;
+    uint8_t* source_type; uint32_t* valid;
+};
+
+__global__ void __launch_bounds__(256) scatter_meta_kernel(const mrag_rowmeta* __restrict__ m, int64_t n,
+                                                          int64_t first_row, MetaCols c) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mrag_rowmeta x = m[i];
+    const int64_t r = first_row + i;
+    c.doc_idx[r] = x.doc_idx; c.payer[r] = x.payer; c.state[r] = x.state; c.program[r] = x.program;
+    c.authority[r] = x.authority; c.source_type[r] = x.source_type;
+    if (x.valid) atomicOr(&c.valid[r >> 5], 1u << (r & 31));
+}
+
+// device copy of mrag_filter without the host pointer
+struct DevFilter {
+    uint32_t flags;
+    uint64_t payer_any[MRAG_PAYER_WORDS];
+    uint64_t payer_alt_any[MRAG_PAYER_WORDS];
+    uint16_t alt_state, state_eq, program_eq, authority_eq, source_type_eq;
+    uint32_t doc_eq;
+    uint64_t tag_state_any[MRAG_SMALL_WORDS];
+    uint64_t tag_program_any[MRAG_SMALL_WORDS];
+    uint64_t tag_payer_any[MRAG_PAYER_WORDS];
+    uint64_t tag_any[MRAG_TAG_WORDS];
+};
+
+MRAG_DEVINL bool bit_in(const uint64_t* set, uint32_t code, uint32_t words) {
+    return (code >> 6) < words && ((set[code >> 6] >> (code & 63)) & 1ull);
+}
+
+// K2.  One thread per row, one warp per bitmap word (ballot).  Reads 10 B of metadata per row.
+__global__ void __launch_bounds__(256) filter_mask_kernel(const __grid_constant__ DevFilter f, MetaCols c, int64_t n,
+                                                         const uint32_t* __restrict__ pool_bits,
+                                                         const uint64_t* __restrict__ doc_tags, int64_t n_tag_docs,
+                                                         uint32_t* __restrict__ mask_out,
+                                                         unsigned long long* __restrict__ n_pass) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (r < n) {
+        ok = (c.valid[r >> 5] >> (r & 31)) & 1u;              // embedding_vec IS NOT NULL
+        if (ok && f.flags) {
+            const uint32_t payer = c.payer[r], state = c.state[r];
+            if (f.flags & MRAG_F_PAYER)
+                ok = bit_in(f.payer_any, payer, MRAG_PAYER_WORDS) ||
+                     (bit_in(f.payer_alt_any, payer, MRAG_PAYER_WORDS) && state == f.alt_state);
+            if (ok && (f.flags & MRAG_F_STATE)) ok = state == f.state_eq;
+            if (ok && (f.flags & MRAG_F_PROGRAM)) ok = c.program[r] == f.program_eq;
+            if (ok && (f.flags & MRAG_F_AUTHORITY)) ok = c.authority[r] == f.authority_eq;
+            if (ok && (f.flags & MRAG_F_SOURCE_TYPE)) ok = c.source_type[r] == f.source_type_eq;
+            if (ok && (f.flags & (MRAG_F_DOC_EQ | MRAG_F_DOC_POOL | MRAG_F_TAG_RELAXED))) {
+                const uint32_t d = c.doc_idx[r];
+                if (f.flags & MRAG_F_DOC_EQ) ok = d == f.doc_eq;
+                if (ok && (f.flags & MRAG_F_DOC_POOL)) ok = (pool_bits[d >> 5] >> (d & 31)) & 1u;
+                if (ok && (f.flags & MRAG_F_TAG_RELAXED)) {
+                    bool any = false;
+                    if (int64_t(d) < n_tag_docs) {
+#pragma unroll
+                        for (int w = 0; w < MRAG_TAG_WORDS; ++w) any |= (doc_tags[size_t(d) * MRAG_TAG_WORDS + w] & f.tag_any[w]) != 0;
+                    }
+                    ok = any;
+                }
+            }
+            if (ok && (f.flags & MRAG_F_TAG_STRICT))
+                ok = bit_in(f.tag_state_any, state, MRAG_SMALL_WORDS) ||
+                     bit_in(f.tag_program_any, c.program[r], MRAG_SMALL_WORDS) ||
+                     bit_in(f.tag_payer_any, payer, MRAG_PAYER_WORDS);
+        }
+    }
+    const uint32_t word = __ballot_sync(kFull, ok);
+    if ((threadIdx.x & 31) == 0) {
+        if (r < ((n + 31) & ~int64_t(31))) mask_out[r >> 5] = word;
+        if (n_pass && word) atomicAdd(n_pass, (unsigned long long)__popc(word));
+    }
+}
+
+__global__ void pool_bitmap_kernel(const uint32_t* __restrict__ pool, int64_t n_pool, uint32_t* bits, int64_t n_docs) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_pool) return;
+    const uint32_t d = pool[i];
+    if (int64_t(d) < n_docs) atomicOr(&bits[d >> 5], 1u << (d & 31));
+}
+
+__global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n, uint32_t doc, uint32_t* valid,
+                                 unsigned long long* n_hit) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (doc_idx[r] == doc) {
+        uint32_t old = atomicAnd(&valid[r >> 5], ~(1u << (r & 31)));
+        if ((old >> (r & 31)) & 1u) atomicAdd(n_hit, 1ull);
+    }
+}
+
+// one warp per query: zero-pad to ld, 1/|q| (float4 query, vector_store.py:272), bf16 copy
+__global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ q, int nq, int dim, int ld,
+                                                        float* __restrict__ qpad, float* __restrict__ qinv,
+                                                        __nv_bfloat16* __restrict__ qbf, int nq_pad) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq_pad) return;
+    float ss = 0.0f;
+    for (int e = lane; e < ld; e += 32) {
+        float v = (i < nq && e < dim) ? q[size_t(i) * dim + e] : 0.0f;
+        if (i < nq) qpad[size_t(i) * ld + e] = v;
+        if (qbf) qbf[size_t(i) * ld + e] = __float2bfloat16_rn(v);
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0 && i < nq) qinv[i] = (ss > 0.0f) ? 1.0f / sqrtf(ss) : CUDART_INF_F;
+}
+
+}  // namespace mrag

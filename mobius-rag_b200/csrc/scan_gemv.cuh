@@ -1,0 +1,206 @@
+// scan_gemv.cuh -- K1 (small query batches) + K3 (fused select), CUDA cores, HBM-bound.
+//
+// Replaces the sequential-scan plan of
+//     ORDER BY embedding_vec <=> :q LIMIT :k      (corpus_search.py:1525-1536, vector_store.py:274-287)
+// for 1..4 queries per pass.  One warp owns one row at a time (4 rows in flight): every lane
+// streams 16-byte pieces of the row with ld.global.nc.L1::no_allocate, accumulates
+// <q_b, x> for each query and |x|^2 in fp32 in the SAME pass (the corpus is stored
+// un-normalised, like pgvector stores it), and a shuffle tree finishes the sums.
+// Rows whose mask bit is clear are never loaded, so a filtered scan reads only passing rows.
+//
+// Select: each warp keeps, per query, a private candidate buffer of 2*kp keys in shared
+// memory and a register threshold (the k-th best key it has seen).  A row is appended only
+// if its key beats the threshold; a full buffer is bitonic-sorted by the warp and cut back
+// to k.  At the end the block sorts all its warps' buffers and writes ONE sorted list of kp
+// keys per (query, block) -- no N-sized score array ever exists.
+#pragma once
+#include "common.cuh"
+
+namespace mrag {
+
+constexpr int kGemvThreads = 512;
+constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kGemvRows = 4;      // rows in flight per warp
+constexpr int kGemvVecs = 3;      // 16-byte vectors per lane per row per column block
+
+struct ScanArgs {
+    const void* rows;       // [n][ld] storage dtype, row-major
+    int64_t n;              // rows in the shard
+    int ld;                 // padded row length in elements (multiple of 64, zero padded)
+    const uint32_t* mask;   // row bitmap: valid AND filter; bits >= n are zero
+    const float* q;         // [*][ld] fp32 queries, zero padded
+    const float* qinv;      // [*]  1/|q|  (+inf for a zero query)
+    const uint64_t* ub;     // [*]  exclusive upper-bound key per query, or nullptr
+    uint64_t* part;         // [*][P][kp] per-block sorted candidate lists
+    int q0;                 // first query handled by this launch
+    int nq;                 // queries handled by this launch (<= NQ)
+    int k, kp, P;
+};
+
+inline size_t gemv_smem_bytes(int nq_tpl, int ld, int kp) {
+    return size_t(nq_tpl) * ld * 4 + size_t(nq_tpl) * kGemvWarps * (2 * kp) * 8;
+}
+
+// element j (0..E-1) of 16-byte vector v lives at  qs[plane(j)][v][j%4]
+template <int DT> struct VecTraits;
+template <> struct VecTraits<0> { static constexpr int E = 4; };   // fp32: 4 elements / 16 B
+template <> struct VecTraits<1> { static constexpr int E = 8; };   // bf16: 8 elements / 16 B
+
+template <int DT, int NQ>
+__global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanArgs a) {
+    constexpr int E = VecTraits<DT>::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bufs = reinterpret_cast<uint64_t*>(smem_raw + size_t(NQ) * a.ld * 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = a.ld;
+    const int nvec = ld / E;               // 16-byte vectors per row
+    const int cap = 2 * a.kp;
+
+    // ---- stage the queries: fp32, split in 4-float planes so every LDS.128 is conflict free
+    for (int i = tid; i < NQ * ld; i += kGemvThreads) {
+        int qi = i / ld, e = i - qi * ld;
+        float v = (qi < a.nq) ? a.q[size_t(a.q0 + qi) * ld + e] : 0.0f;
+        int dst;
+        if (DT == 1) {
+            int vv = e >> 3, w = e & 7;
+            dst = qi * ld + (w >> 2) * (ld >> 1) + vv * 4 + (w & 3);
+        } else {
+            dst = i;
+        }
+        qs[dst] = v;
+    }
+    uint64_t thr[NQ], ubk[NQ];
+    int cnt[NQ];
+    float qinv[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        thr[qi] = 0; cnt[qi] = 0;
+        ubk[qi] = (a.ub && qi < a.nq) ? a.ub[a.q0 + qi] : ~0ull;
+        qinv[qi] = (qi < a.nq) ? a.qinv[a.q0 + qi] : 0.0f;
+    }
+    __syncthreads();
+
+    const int64_t nwords = (a.n + 31) >> 5;
+    const int64_t W = int64_t(gridDim.x) * kGemvWarps;
+    const char* base = reinterpret_cast<const char*>(a.rows);
+    const size_t row_bytes = size_t(ld) * (DT == 1 ? 2 : 4);
+
+    int64_t w = int64_t(blockIdx.x) * kGemvWarps + warp;
+    uint32_t m_next = (w < nwords) ? __ldg(a.mask + w) : 0u;
+    for (; w < nwords; w += W) {
+        uint32_t m = m_next;
+        m_next = (w + W < nwords) ? __ldg(a.mask + w + W) : 0u;
+        while (m) {
+            uint32_t r[kGemvRows];
+            int nr = 0;
+#pragma unroll
+            for (int j = 0; j < kGemvRows; ++j) {
+                if (m) { int b = __ffs(m) - 1; m &= m - 1; r[j] = uint32_t(w * 32 + b); ++nr; }
+                else r[j] = r[0];
+            }
+            float acc[kGemvRows][NQ + 1];
+#pragma unroll
+            for (int j = 0; j < kGemvRows; ++j)
+#pragma unroll
+                for (int x = 0; x <= NQ; ++x) acc[j][x] = 0.0f;
+
+            for (int v0 = 0; v0 < nvec; v0 += kWarp * kGemvVecs) {
+                uint4 d[kGemvRows][kGemvVecs];
+#pragma unroll
+                for (int c = 0; c < kGemvVecs; ++c) {
+                    int v = v0 + c * kWarp + lane;
+                    bool ok = v < nvec;
+#pragma unroll
+                    for (int j = 0; j < kGemvRows; ++j) {
+                        if (ok && j < nr) d[j][c] = ldg_stream(base + size_t(r[j]) * row_bytes + size_t(v) * 16);
+                        else d[j][c] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < kGemvVecs; ++c) {
+                    int v = v0 + c * kWarp + lane;
+                    if (v < nvec) {
+                        float x[kGemvRows][E];
+#pragma unroll
+                        for (int j = 0; j < kGemvRows; ++j) {
+                            if (DT == 1) {
+                                x[j][0] = bf16lo(d[j][c].x); x[j][1] = bf16hi(d[j][c].x);
+                                x[j][2] = bf16lo(d[j][c].y); x[j][3] = bf16hi(d[j][c].y);
+                                x[j][4 % E] = bf16lo(d[j][c].z); x[j][5 % E] = bf16hi(d[j][c].z);
+                                x[j][6 % E] = bf16lo(d[j][c].w); x[j][7 % E] = bf16hi(d[j][c].w);
+                            } else {
+                                x[j][0] = __uint_as_float(d[j][c].x); x[j][1] = __uint_as_float(d[j][c].y);
+                                x[j][2] = __uint_as_float(d[j][c].z); x[j][3] = __uint_as_float(d[j][c].w);
+                            }
+#pragma unroll
+                            for (int e = 0; e < E; ++e) acc[j][NQ] = fmaf(x[j][e], x[j][e], acc[j][NQ]);
+                        }
+#pragma unroll
+                        for (int qi = 0; qi < NQ; ++qi) {
+                            float qv[E];
+                            const float4 q0v = *reinterpret_cast<const float4*>(qs + qi * ld + v * 4);
+                            qv[0] = q0v.x; qv[1] = q0v.y; qv[2] = q0v.z; qv[3] = q0v.w;
+                            if (DT == 1) {
+                                const float4 q1v = *reinterpret_cast<const float4*>(qs + qi * ld + (ld >> 1) + v * 4);
+                                qv[4 % E] = q1v.x; qv[5 % E] = q1v.y; qv[6 % E] = q1v.z; qv[7 % E] = q1v.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < kGemvRows; ++j)
+#pragma unroll
+                                for (int e = 0; e < E; ++e) acc[j][qi] = fmaf(x[j][e], qv[e], acc[j][qi]);
+                        }
+                    }
+                }
+            }
+            // ---- finish the sums: every lane ends up with every total
+#pragma unroll
+            for (int j = 0; j < kGemvRows; ++j)
+#pragma unroll
+                for (int x = 0; x <= NQ; ++x) acc[j][x] = warp_sum(acc[j][x]);
+
+            // ---- normalise and select (warp uniform)
+#pragma unroll
+            for (int j = 0; j < kGemvRows; ++j) {
+                if (j >= nr) break;
+                const float nx = acc[j][NQ];
+                if (!(nx > 0.0f)) continue;             // zero-norm row: similarity is NaN (NaN tail pass)
+                const float inv = rsqrtf(nx);
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    if (qi >= a.nq) break;
+                    const float s = acc[j][qi] * inv * qinv[qi];
+                    if (!(s == s)) continue;            // zero-norm query
+                    const uint64_t key = make_key(s, r[j]);
+                    if (key > thr[qi] && key < ubk[qi]) {
+                        uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
+                        if (lane == 0) b[cnt[qi]] = key;
+                        if (++cnt[qi] == cap) {
+                            __syncwarp();
+                            warp_sort_desc(b, cap, lane);
+                            cnt[qi] = a.k;
+                            thr[qi] = b[a.k - 1];
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- block merge: clear the unused tail of every warp buffer, sort the block's buffers together
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
+        for (int i = cnt[qi] + lane; i < cap; i += kWarp) b[i] = 0;
+    }
+    __syncthreads();
+    for (int qi = 0; qi < a.nq; ++qi) {
+        uint64_t* b = bufs + size_t(qi) * kGemvWarps * cap;
+        block_sort_desc(b, kGemvWarps * cap);
+        uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
+        for (int i = tid; i < a.kp; i += kGemvThreads) out[i] = (i < a.k) ? b[i] : 0ull;
+    }
+}
+
+}  // namespace mrag

@@ -1,0 +1,228 @@
+// select.cuh -- K3 block-level merge / finalize, NaN tail, K4 cross-shard k-way merge.
+//
+// Together with the per-producer lists written by the scan kernels these implement
+//     ORDER BY embedding_vec <=> :q LIMIT :k       (vector_store.py:284-285, corpus_search.py:1534-1535)
+// with Postgres float8 ordering (NaN last) and ties broken by ascending row.
+#pragma once
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace mrag {
+
+constexpr int kMergeThreads = 512;
+constexpr int kMergeSlots = 4096;   // u64 keys held in shared memory by one merge block
+
+struct MergeArgs {
+    const uint64_t* part;   // [nq][P][kp] sorted (desc) candidate lists, 0 = empty
+    int P, kp;
+    int nq;
+    int k;                  // results wanted from this round (<= MRAG_FUSED_K)
+    int k_total;            // row pitch of the outputs
+    int k_off;              // first output slot of this round
+    float* scores;          // [nq][k_total]
+    int64_t* rows;          // [nq][k_total]
+    int32_t* counts;        // [nq]
+    int64_t row_base;
+    uint64_t* ub_out;       // [nq] last key of this round (next round's exclusive bound), may be null
+    int* need_tail;         // set to 1 if some query is still short of k_total after this round
+};
+
+// One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
+// alone already holds k keys >= T), so only the survivors are gathered and sorted.
+__global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs a) {
+    __shared__ uint64_t s[kMergeSlots];
+    __shared__ unsigned long long s_T;
+    __shared__ int s_cnt;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const uint64_t* base = a.part + size_t(q) * a.P * a.kp;
+    if (tid == 0) { s_T = 0ull; s_cnt = 0; }
+    __syncthreads();
+    uint64_t t = 0;
+    for (int p = tid; p < a.P; p += kMergeThreads) {
+        uint64_t v = base[size_t(p) * a.kp + (a.k - 1)];
+        t = v > t ? v : t;
+    }
+    if (t) atomicMax(&s_T, (unsigned long long)t);
+    __syncthreads();
+    const uint64_t T = s_T;
+    const int total = a.P * a.kp;
+    int done = 0;
+    while (done < total) {
+        int kept = s_cnt;                       // uniform: read between two barriers
+        __syncthreads();
+        if (kept > kMergeSlots / 2) {           // make room: sort what we have, keep the best k
+            int n2 = next_pow2(kept);
+            for (int i = kept + tid; i < n2; i += kMergeThreads) s[i] = 0;
+            __syncthreads();
+            block_sort_desc(s, n2);
+            if (tid == 0) s_cnt = a.k;
+            __syncthreads();
+            kept = a.k;
+        }
+        int room = kMergeSlots - kept;
+        int take = total - done < room ? total - done : room;
+        for (int i = tid; i < take; i += kMergeThreads) {
+            uint64_t v = base[done + i];
+            if (v != 0 && v >= T) { int pos = atomicAdd(&s_cnt, 1); s[pos] = v; }
+        }
+        done += take;
+        __syncthreads();
+    }
+    int kept = s_cnt;
+    int n2 = next_pow2(kept < 2 ? 2 : kept);
+    for (int i = kept + tid; i < n2; i += kMergeThreads) s[i] = 0;
+    __syncthreads();
+    block_sort_desc(s, n2);
+    const int got = kept < a.k ? kept : a.k;
+    // round 0 starts at slot 0 and pads the whole row; later rounds continue at counts[q]
+    const int prev = (a.k_off == 0) ? 0 : a.counts[q];
+    __syncthreads();
+    const int hi = (a.k_off == 0) ? a.k_total : got;
+    for (int i = tid; i < hi; i += kMergeThreads) {
+        size_t o = size_t(q) * a.k_total + prev + i;
+        if (i < got) {
+            uint64_t key = s[i];
+            float sc = key_score(key);
+            sc = fminf(1.0f, fmaxf(-1.0f, sc));          // pgvector "keep in range"
+            a.scores[o] = sc;
+            a.rows[o] = int64_t(key_row(key)) + a.row_base;
+        } else {
+            a.scores[o] = CUDART_NAN_F;
+            a.rows[o] = -1;
+        }
+    }
+    if (tid == 0) {
+        a.counts[q] = prev + got;
+        if (a.ub_out) a.ub_out[q] = (got == a.k) ? s[a.k - 1] : 0ull;
+        if (prev + got < a.k_total && a.need_tail) *a.need_tail = 1;
+    }
+}
+
+// NaN tail.  Postgres sorts a NaN distance after every number, so rows whose similarity is NaN
+// (zero-norm row, or every row when the query itself has zero norm) are returned only when
+// fewer than k finite rows pass the filter.  One block per query walks the mask in row order.
+// inv_norm[r] == +inf marks a stored zero-norm row.
+struct TailArgs {
+    const float* inv_norm; const uint32_t* mask; int64_t n;
+    const float* qinv; int nq; int k_total;
+    float* scores; int64_t* rows; int32_t* counts; int64_t row_base;
+    const int* need_tail;
+};
+
+__global__ void __launch_bounds__(256, 1) nan_tail_kernel(const TailArgs a) {
+    if (*a.need_tail == 0) return;
+    __shared__ int s_scan[256];
+    __shared__ int s_count;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_count = a.counts[q];
+    __syncthreads();
+    if (s_count >= a.k_total) return;
+    const bool all_nan = isinf(a.qinv[q]);
+    // a zero query makes EVERY similarity NaN; the scan kernels then selected nothing for it
+    const int64_t nwords = (a.n + 31) >> 5;
+    for (int64_t w0 = 0; w0 < nwords; w0 += 256) {
+        int64_t w = w0 + tid;
+        uint32_t m = (w < nwords) ? a.mask[w] : 0u;
+        if (m && !all_nan) {
+            uint32_t keep = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                int b = __ffs(mm) - 1;
+                if (isinf(a.inv_norm[w * 32 + b])) keep |= 1u << b;
+            }
+            m = keep;
+        }
+        int c = __popc(m);
+        s_scan[tid] = c;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {          // inclusive scan
+            int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        int pos = s_count + s_scan[tid] - c;
+        for (; m && pos < a.k_total; m &= m - 1, ++pos) {
+            int b = __ffs(m) - 1;
+            size_t o = size_t(q) * a.k_total + pos;
+            a.scores[o] = CUDART_NAN_F;
+            a.rows[o] = w * 32 + b + a.row_base;
+        }
+        __syncthreads();
+        if (tid == 255) s_count = min(a.k_total, s_count + s_scan[255]);
+        __syncthreads();
+        if (s_count >= a.k_total) break;
+    }
+    if (tid == 0) a.counts[q] = s_count;
+}
+
+// K4: k-way merge of per-shard results after the allgather.  Entries are (score, global row);
+// order = score DESC, NaN last, row ASC.  Dynamic shared memory: next_pow2(n_lists*k) * 12 bytes.
+struct XMergeArgs {
+    int n_lists, nq, k;
+    const float* scores_in; const int64_t* rows_in; const int32_t* counts_in;
+    int64_t stride_scores, stride_rows, stride_counts;      // elements between consecutive lists
+    float* scores_out; int64_t* rows_out; int32_t* counts_out;
+};
+
+constexpr int kXMergeMaxSlots = 16384;
+
+MRAG_DEVINL bool xm_before(uint32_t ca, int64_t ra, uint32_t cb, int64_t rb) {
+    // class: 0 = empty, 1 = NaN, >= 2 = orderable(score) (a finite score never maps below 2)
+    if (ca != cb) return ca > cb;
+    return ra < rb;
+}
+
+__global__ void __launch_bounds__(kMergeThreads, 1) xmerge_kernel(const XMergeArgs a) {
+    extern __shared__ __align__(16) unsigned char xm_smem[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int total = a.n_lists * a.k;
+    const int n2 = next_pow2(total < 2 ? 2 : total);
+    int64_t* sr = reinterpret_cast<int64_t*>(xm_smem);
+    uint32_t* sc = reinterpret_cast<uint32_t*>(xm_smem + size_t(n2) * 8);
+    for (int i = tid; i < n2; i += kMergeThreads) {
+        uint32_t c = 0; int64_t r = INT64_MAX;
+        if (i < total) {
+            int l = i / a.k, j = i - l * a.k;
+            if (j < a.counts_in[l * a.stride_counts + q]) {
+                size_t o = size_t(q) * a.k + j;
+                float s = a.scores_in[l * a.stride_scores + o];
+                r = a.rows_in[l * a.stride_rows + o];
+                c = (s == s) ? f2ord(s) : 1u;
+                if (c < 2u) c = (s == s) ? 2u : 1u;
+            }
+        }
+        sc[i] = c; sr[i] = r;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += kMergeThreads) {
+                int p = i ^ j;
+                if (p > i) {
+                    uint32_t ci = sc[i], cp = sc[p]; int64_t ri = sr[i], rp = sr[p];
+                    bool first_half = (i & kk) == 0;
+                    bool swap = first_half ? xm_before(cp, rp, ci, ri) : xm_before(ci, ri, cp, rp);
+                    if (swap) { sc[i] = cp; sc[p] = ci; sr[i] = rp; sr[p] = ri; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int got = 0;
+    for (int l = 0; l < a.n_lists; ++l) got += a.counts_in[l * a.stride_counts + q];
+    got = got < a.k ? got : a.k;
+    for (int i = tid; i < a.k; i += kMergeThreads) {
+        size_t o = size_t(q) * a.k + i;
+        if (i < got) {
+            uint32_t c = sc[i];
+            a.scores_out[o] = (c == 1u) ? CUDART_NAN_F : ord2f(c);
+            a.rows_out[o] = sr[i];
+        } else {
+            a.scores_out[o] = CUDART_NAN_F;
+            a.rows_out[o] = -1;
+        }
+    }
+    if (tid == 0) a.counts_out[q] = got;
+}
+
+}  // namespace mrag

@@ -1,0 +1,105 @@
+"""Row-sharded search across the GPUs of one box.
+
+Every rank holds a contiguous, document-aligned block of rows in its own Index and sees every
+query.  One search = local scan + select on each rank, ONE allgather of the packed per-rank
+top-k lists (k*12 + 4 bytes per query) over NCCL / NVLink, then the k-way merge kernel (K4) on
+every rank.  No all-reduce: top-k merge is not a sum.
+
+The collective goes through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); the
+local search and the merge are injectable so the host logic can be exercised without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+
+def shard_bounds(doc_of_row: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """Contiguous [lo, hi) row blocks, cut at document boundaries nearest to r*n/world so a
+    document's chunks stay on one rank (doc_idx filters and tombstones stay local)."""
+    n = int(doc_of_row.shape[0])
+    cuts = [0]
+    for r in range(1, world):
+        t = (n * r) // world
+        t = max(t, cuts[-1])
+        if 0 < t < n:
+            # move forward to the first row of the next document
+            d = doc_of_row[t - 1]
+            while t < n and doc_of_row[t] == d:
+                t += 1
+        cuts.append(min(t, n))
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def packed_layout(nq: int, k: int) -> dict:
+    """Byte layout of one rank's slot in the allgather buffer: rows i64 | scores f32 | counts i32,
+    padded to 8 bytes."""
+    rows_off = 0
+    scores_off = nq * k * 8
+    counts_off = scores_off + nq * k * 4
+    size = counts_off + nq * 4
+    size = (size + 7) // 8 * 8
+    return {"rows_off": rows_off, "scores_off": scores_off, "counts_off": counts_off, "size": size}
+
+
+class ShardedSearcher:
+    """One per rank.  ``local_search(q, k, flt, out)`` must write the local top-k (global row
+    ids) into the three views of this rank's slot; ``merge(gathered, world, nq, k, layout)``
+    must return (scores, rows, counts) of the global top-k."""
+
+    def __init__(self, index=None, group=None, local_search: Callable | None = None, merge: Callable | None = None,
+                 device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.index = index
+        self.device = device
+        self._local = local_search or self._cuda_local
+        self._merge = merge or self._cuda_merge
+        self._buf_key = None
+
+    # -- buffers -----------------------------------------------------------------------------
+    def _buffers(self, nq: int, k: int):
+        import torch
+        key = (nq, k)
+        if self._buf_key != key:
+            lay = packed_layout(nq, k)
+            dev = self.device if self.device is not None else (f"cuda:{self.index.device}" if self.index is not None else "cpu")
+            self._lay = lay
+            self._gathered = torch.zeros(self.world * lay["size"], dtype=torch.uint8, device=dev)
+            self._slot = self._gathered[self.rank * lay["size"]:(self.rank + 1) * lay["size"]]
+            self._buf_key = key
+        return self._lay, self._slot, self._gathered
+
+    @staticmethod
+    def slot_views(slot, nq: int, k: int, lay: dict):
+        import torch
+        rows = slot[lay["rows_off"]:lay["rows_off"] + nq * k * 8].view(torch.int64).view(nq, k)
+        scores = slot[lay["scores_off"]:lay["scores_off"] + nq * k * 4].view(torch.float32).view(nq, k)
+        counts = slot[lay["counts_off"]:lay["counts_off"] + nq * 4].view(torch.int32)
+        return scores, rows, counts
+
+    # -- default (CUDA) implementations ----------------------------------------------------------
+    def _cuda_local(self, q, k, flt, out):
+        self.index.search_device(q, k, flt, out=out, sync=False)
+
+    def _cuda_merge(self, gathered, world, nq, k, lay):
+        from .index import merge_topk
+        scores0, rows0, counts0 = self.slot_views(gathered[:lay["size"]], nq, k, lay)
+        return merge_topk(self.index.device, scores0, rows0, counts0, world, nq, k,
+                          (lay["size"] // 4, lay["size"] // 8, lay["size"] // 4))
+
+    # -- the search --------------------------------------------------------------------------
+    def search(self, q, k: int, flt=None):
+        """q: [nq, dim] float32 on this rank's device, identical on every rank.
+        Returns (scores [nq,k], rows [nq,k] global ids, counts [nq]) on every rank."""
+        nq = int(q.shape[0])
+        lay, slot, gathered = self._buffers(nq, k)
+        self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(gathered, slot, group=self.group)
+        return self._merge(gathered, self.world, nq, k, lay)

@@ -1,0 +1,437 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/mrag.h) against the CPU oracle on
+the same seeded inputs.  Bar (BASELINE.json north_star): returned ids and their order identical
+except inside groups of tied scores; scores within 1e-4 relative for the fp32 corpus, 1e-2 for the
+bf16 corpus (where the oracle sees the bf16-rounded corpus upcast to fp32)."""
+import math
+import threading
+
+import numpy as np
+import pytest
+
+import mrag_b200
+from mrag_b200 import _native as N
+from mrag_b200 import synth
+from mrag_b200.index import Filter, Index, make_meta, merge_topk
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"f32": 1e-4, "bf16": 1e-2}
+# in bf16 mode the scores are still computed with fp32 accumulation from the rounded rows, so ties
+# are judged as tightly as in fp32 mode
+TIE_TOL = 1e-6
+
+
+def check_all(oracle, Xs, Q, mask, k, scores, rows, counts, dtype, row_base=0):
+    for i in range(Q.shape[0]):
+        sim_all = oracle.all_similarities(Xs, Q[i])
+        r = rows[i].copy()
+        r[r >= 0] -= row_base
+        oracle.check_topk(r, scores[i], int(counts[i]), sim_all, mask, k, rtol=RTOL[dtype], tie_tol=TIE_TOL)
+
+
+def stored(oracle, X, dtype):
+    return oracle.round_bf16(X) if dtype == "bf16" else X
+
+
+# ---------------------------------------------------------------------------------------------
+# C1: 100k x 768, single query, top-10 (BASELINE.json configs[0])
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_c1_100k_768_top10(oracle, dtype):
+    n, dim, k = 100_000, 768, 10
+    X, valid = synth.make_corpus(n, dim, seed=1234)
+    Q = synth.make_queries(X, 6, seed=4321)
+    idx = Index(dim, dtype, 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    Xs = stored(oracle, X, dtype)
+    for i in range(Q.shape[0]):                       # single-query calls, as /api/query issues them
+        s, r, c = idx.search(Q[i:i + 1], k)
+        check_all(oracle, Xs, Q[i:i + 1], valid.astype(bool), k, s, r, c, dtype)
+    assert idx.last_scan_kind() in ("gemv", "mma")
+    assert idx.last_kernel_ms(1) > 0
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# shapes: ragged dims, batch sizes, k (incl. the multi-round path k > MRAG_FUSED_K)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (5000, 768, 1, 10), (5000, 1536, 3, 10), (4097, 100, 5, 7), (33, 1, 2, 5), (31, 3, 1, 40),
+    (20000, 64, 64, 10), (20000, 768, 7, 100), (9000, 128, 4, 128), (9000, 128, 2, 129),
+    (6000, 96, 3, 300), (12000, 64, 1, 1600), (2000, 768, 17, 1),
+])
+def test_shapes(oracle, dtype, n, dim, nq, k):
+    X, valid = synth.make_corpus(n, dim, seed=n + dim, null_frac=3e-3)
+    Q = synth.make_queries(X, nq, seed=k)
+    idx = Index(dim, dtype, 0, n + 5)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k)
+    check_all(oracle, stored(oracle, X, dtype), Q, valid.astype(bool), k, s, r, c, dtype)
+    idx.close()
+
+
+def test_empty_and_tiny_index(oracle):
+    idx = Index(16, "f32", 0, 100)
+    s, r, c = idx.search(np.ones((2, 16), np.float32), 5)
+    assert (c == 0).all() and (r == -1).all() and np.isnan(s).all()
+    X = np.eye(16, dtype=np.float32)[:3]
+    idx.append(X)
+    s, r, c = idx.search(X[1:2] * 7.0, 5)
+    assert c[0] == 3 and r[0, 0] == 1 and s[0, 0] == pytest.approx(1.0, abs=1e-6)
+    assert sorted(r[0, 1:3].tolist()) == [0, 2] and r[0, 1] == 0 and (r[0, 3:] == -1).all()
+    idx.close()
+
+
+def test_incremental_append_matches_one_shot(oracle):
+    n, dim = 7001, 200
+    X, valid = synth.make_corpus(n, dim, seed=77)
+    Q = synth.make_queries(X, 4, seed=78)
+    idx = Index(dim, "f32", 0, n)
+    cuts = [0, 50, 51, 3000, 3033, n]          # the worker appends batches of 50 (embedding_worker.py:229-266)
+    for lo, hi in zip(cuts, cuts[1:]):
+        first = idx.append(X[lo:hi], make_meta(hi - lo, doc_idx=np.arange(lo, hi), valid=valid[lo:hi]))
+        assert first == lo
+    assert len(idx) == n
+    s, r, c = idx.search(Q, 20)
+    check_all(oracle, X, Q, valid.astype(bool), 20, s, r, c, "f32")
+    with pytest.raises(N.MragError) as e:
+        idx.append(X[:1])
+    assert e.value.code == N.MRAG_ERR_OOM
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# NaN / NULL / ties
+# ---------------------------------------------------------------------------------------------
+def test_nan_rows_sort_last_and_null_rows_never_return(oracle):
+    n, dim, k = 300, 24, 300
+    X, valid = synth.make_corpus(n, dim, seed=5, null_frac=0.05, zero_norm_rows=4)
+    Q = synth.make_queries(X, 3, seed=6)
+    idx = Index(dim, "f32", 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k)
+    mask = valid.astype(bool)
+    check_all(oracle, X, Q, mask, k, s, r, c, "f32")
+    zero = np.nonzero((np.abs(X).sum(axis=1) == 0) & mask)[0]
+    assert len(zero) >= 1
+    for i in range(3):
+        assert c[i] == mask.sum()
+        tail = r[i, c[i] - len(zero):c[i]]
+        assert tail.tolist() == zero.tolist() and np.isnan(s[i, c[i] - len(zero):c[i]]).all()
+        assert not set(r[i, :c[i]].tolist()) & set(np.nonzero(~mask)[0].tolist())
+    # a zero query: every distance is NaN -> the first k passing rows in row order
+    s, r, c = idx.search(np.zeros((1, dim), np.float32), 10)
+    assert c[0] == 10 and r[0].tolist() == np.nonzero(mask)[0][:10].tolist() and np.isnan(s[0]).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_duplicate_cluster_ties_break_by_row(oracle, dtype):
+    n, dim, k = 6000, 256, 50
+    X, valid = synth.make_corpus(n, dim, seed=9, dup_frac=0.0)
+    rng = np.random.default_rng(1)
+    dup_rows = np.sort(rng.choice(n, size=120, replace=False))
+    X[dup_rows] = X[dup_rows[0]]
+    valid[dup_rows] = 1
+    q = X[dup_rows[0]][None, :] * 3.0
+    idx = Index(dim, dtype, 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(q, k)
+    assert r[0].tolist() == dup_rows[:k].tolist()          # all tie at 1.0: ascending row
+    assert np.allclose(s[0], 1.0, atol=1e-6)
+    check_all(oracle, stored(oracle, X, dtype), q, valid.astype(bool), k, s, r, c, dtype)
+    idx.close()
+
+
+def test_scores_clamped_to_unit_range():
+    X = np.full((40, 7), 0.1, dtype=np.float32)
+    X[1::2] *= -1
+    idx = Index(7, "f32", 0, 40)
+    idx.append(X)
+    s, r, c = idx.search(X[:1], 40)
+    assert s.max() <= 1.0 and s.min() >= -1.0 and c[0] == 40
+    assert r[0, :20].tolist() == list(range(0, 40, 2)) and r[0, 20:].tolist() == list(range(1, 40, 2))
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# WHERE clauses on codes (K2) against numpy on the same codes
+# ---------------------------------------------------------------------------------------------
+def test_filter_clauses_codes(oracle):
+    n, dim, k = 30000, 64, 25
+    X, valid = synth.make_corpus(n, dim, seed=31, null_frac=2e-3)
+    meta, doc_tags, info = synth.make_metadata(n, seed=32, rows_per_doc=64, valid=valid)
+    Q = synth.make_queries(X, 3, seed=33)
+    idx = Index(dim, "f32", 0, n)
+    idx.append(X, meta)
+    idx.set_doc_tags(0, doc_tags)
+    v = valid.astype(bool)
+    P, S = synth.PAYERS, synth.STATES
+    fl = S.index("FL")
+    alt = [P.index(p) for p in ("AHCA", "Ahca.myflorida", "Florida Medicaid")]
+    doc = meta["doc_idx"]
+    rng = np.random.default_rng(3)
+    pools = [rng.choice(info["n_docs"], size=m, replace=False) for m in (1, 19, 50, 300)]
+    tagbits = lambda bits: np.array([any(info["tagmat"][d, b] for b in bits) for d in range(info["n_docs"])])[doc]
+    cases = [
+        ("payer", Filter().payer_in([P.index("Humana")]), meta["payer"] == P.index("Humana")),
+        ("payer+FL union", Filter().payer_in([P.index("Sunshine Health")], alt, fl),
+         (meta["payer"] == P.index("Sunshine Health")) | (np.isin(meta["payer"], alt) & (meta["state"] == fl))),
+        ("state", Filter().state_eq(S.index("TX")), meta["state"] == S.index("TX")),
+        ("program", Filter().program_eq(3), meta["program"] == 3),
+        ("authority", Filter().authority_eq(1), meta["authority"] == 1),
+        ("source_type", Filter().source_type_eq(2), meta["source_type"] == 2),
+        ("unknown value", Filter().payer_in([0xFFFE]), np.zeros(n, bool)),
+        ("doc_eq", Filter().doc_eq(int(doc[n // 2])), doc == doc[n // 2]),
+        ("tag relaxed 10%", Filter().tag_relaxed([0, 3]), tagbits([0, 3])),
+        ("tag relaxed 0.1%", Filter().tag_relaxed([2]), tagbits([2])),
+        ("tag strict", Filter().tag_strict([S.index("GA")], [5], [P.index("Aetna")]),
+         (meta["state"] == S.index("GA")) | (meta["program"] == 5) | (meta["payer"] == P.index("Aetna"))),
+        ("combo", Filter().payer_in([P.index("Sunshine Health")], alt, fl).authority_eq(0).tag_relaxed([0, 1, 3, 6]),
+         ((meta["payer"] == P.index("Sunshine Health")) | (np.isin(meta["payer"], alt) & (meta["state"] == fl)))
+         & (meta["authority"] == 0) & tagbits([0, 1, 3, 6])),
+        ("empty pool", Filter().doc_pool([]), np.zeros(n, bool)),
+    ] + [(f"pool{len(p)}", Filter().doc_pool(p), np.isin(doc, p)) for p in pools]
+    for name, flt, want in cases:
+        want = want & v
+        bits, n_pass = idx.filter_mask(flt)
+        got = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (got == want).all(), name
+        assert n_pass == int(want.sum()), name
+        s, r, c = idx.search(Q, k, flt)
+        check_all(oracle, X, Q, want, k, s, r, c, "f32")
+    bits, n_pass = idx.filter_mask(None)
+    assert n_pass == int(v.sum())
+    idx.close()
+
+
+def test_tombstone_document(oracle):
+    n, dim = 5000, 48
+    X, valid = synth.make_corpus(n, dim, seed=41)
+    meta, _, info = synth.make_metadata(n, seed=42, rows_per_doc=32, valid=valid)
+    Q = synth.make_queries(X, 2, seed=43)
+    idx = Index(dim, "f32", 0, n)
+    idx.append(X, meta)
+    d = int(meta["doc_idx"][2500])
+    want_gone = (meta["doc_idx"] == d) & valid.astype(bool)
+    assert idx.tombstone_doc(d) == int(want_gone.sum())
+    assert idx.tombstone_doc(d) == 0
+    mask = valid.astype(bool) & ~want_gone
+    s, r, c = idx.search(Q, 30)
+    check_all(oracle, X, Q, mask, 30, s, r, c, "f32")
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the plugin boundary: B200VectorStore and vector_arm against the statement-level oracle
+# ---------------------------------------------------------------------------------------------
+def _same_hits(got, want, key, rtol):
+    assert [g["id"] for g in got] == [w["id"] for w in want]
+    for g, w in zip(got, want):
+        assert {x: g[x] for x in g if x != key} == {x: w[x] for x in w if x != key}
+        if isinstance(w[key], float) and math.isnan(w[key]):
+            assert math.isnan(g[key])
+        else:
+            assert g[key] == pytest.approx(w[key], rel=rtol, abs=rtol * 1e-3)
+
+
+@pytest.fixture(scope="module")
+def tables(oracle):
+    from helpers import build_tables
+    ot, pt, X, valid, meta, info = build_tables(oracle, 6000, 96, seed=7, dtype="f32")
+    return ot, pt, X, valid
+
+
+def test_store_search_matches_pg_statement(oracle, tables):
+    ot, pt, X, valid = tables
+    store = mrag_b200.B200VectorStore(table=pt)
+    rng = np.random.default_rng(0)
+    doc = ot.document_id[1234]
+    cases = [
+        dict(k=10), dict(k=1), dict(k=100), dict(k=10, document_id=doc), dict(k=5, document_id="not-a-doc"),
+        dict(k=10, filters={"payer": "Humana"}), dict(k=10, filters={"state": "FL", "authority_level": "payer_policy"}),
+        dict(k=10, filters={"payer": "", "state": None, "bogus": "x"}),           # all skipped (vector_store.py:250-258)
+        dict(k=10, filters={"source_type": "fact", "payer": "Nobody"}),
+        dict(k=10, filters={"document_id": doc}), dict(k=10, document_id=doc, filters={"document_id": ot.document_id[0]}),
+    ]
+    for i, kw in enumerate(cases):
+        emb = (X[int(rng.integers(0, len(X)))] + 0.05 * rng.standard_normal(X.shape[1])).tolist() if i % 2 else \
+            rng.standard_normal(X.shape[1]).tolist()
+        want = oracle.pg_store_search(ot, emb, kw["k"], kw.get("document_id"), kw.get("filters"))
+        got = store.search(emb, kw["k"], kw.get("document_id"), kw.get("filters"))
+        _same_hits(got, want, "distance", 1e-4)
+        assert all(set(g) == {"id", "document_id", "source_type", "source_id", "distance"} for g in got)
+    import asyncio
+    emb = X[77].tolist()
+    assert [g["id"] for g in asyncio.run(store.asearch(emb, 10))] == [w["id"] for w in oracle.pg_store_search(ot, emb, 10)]
+    with pytest.raises(ValueError):
+        store.search(emb[:-1], 10)
+
+
+def test_vector_arm_matches_reference_restatement(oracle, tables):
+    from mrag_b200.vector_arm import CorpusFilters, LexiconExpansion
+    ot, pt, X, valid = tables
+    rng = np.random.default_rng(1)
+    docs = sorted(set(ot.document_id))
+    pool19 = [docs[i] for i in rng.choice(len(docs), 19, replace=False)]
+    pool_big = [docs[i] for i in rng.choice(len(docs), min(300, len(docs)), replace=False)] + ["ffffffff-0000-0000-0000-000000000000"]
+    E = LexiconExpansion
+    cases = [
+        dict(k=10), dict(k=20, over_fetch_factor=8, min_similarity=0.3), dict(k=200, over_fetch_factor=8),
+        dict(k=10, filters=CorpusFilters(payer="Sunshine Health")), dict(k=10, filters=CorpusFilters(payer="Centene", state="FL")),
+        dict(k=10, filters=CorpusFilters(program="Medicaid", authority_level="payer_policy")),
+        dict(k=10, include_document_ids=pool19), dict(k=40, include_document_ids=pool_big, filters=CorpusFilters(state="FL")),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:state.fl", "j:bad"]), tag_mode="auto"),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:payor.molina_healthcare", "j:program.medic"]), tag_mode="strict"),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:regulatory_authority.ahca"], domain_tags=["d:topic_000.leaf"]), tag_mode="auto"),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:state.zz"], domain_tags=["d:topic_000.leaf"], process_tags=["p:topic_003.leaf"]), tag_mode="auto"),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:state.zz"], domain_tags=["d:topic_000.leaf"]), tag_mode="strict"),
+        dict(k=10, expansion=E(domain_tags=["d:topic_006.leaf", "d:unknown.key"], process_tags=["p:topic_001.leaf"]), tag_mode="relaxed"),
+        dict(k=10, expansion=E(jurisdiction_tags=["j:state.fl"], domain_tags=["d:topic_000.leaf"]), tag_mode="none"),
+        dict(k=10, expansion=E(domain_tags=["d:topic_000.leaf"]), tag_mode="auto"),      # strict empty -> unfiltered, no retry
+        dict(k=5, min_similarity=0.999),
+    ]
+    for i, kw in enumerate(cases):
+        emb = (X[int(rng.integers(0, len(X)))] + 0.05 * rng.standard_normal(X.shape[1])).tolist() if i % 2 == 0 else \
+            rng.standard_normal(X.shape[1]).tolist()
+        args = (emb, kw["k"], kw.get("filters"), kw.get("include_document_ids"))
+        opt = dict(expansion=kw.get("expansion"), tag_mode=kw.get("tag_mode", "auto"),
+                   min_similarity=kw.get("min_similarity"), over_fetch_factor=kw.get("over_fetch_factor", 1))
+        want = oracle.vector_arm(ot, *args, **opt)
+        got = mrag_b200.vector_arm(pt, *args, search_id=f"case{i}", **opt)
+        assert [g["id"] for g in got] == [w["id"] for w in want], f"case {i}"
+        for g, w in zip(got, want):
+            assert set(g) == set(w)
+            for key in w:
+                if key in ("similarity", "match_score"):
+                    assert g[key] == pytest.approx(w[key], rel=1e-4, abs=1e-7)
+                else:
+                    assert g[key] == w[key], (i, key)
+    # NaN quirk of corpus_search.py:1569: a NaN similarity reports 1.0
+    z = int(np.nonzero((np.abs(X).sum(axis=1) == 0) & valid.astype(bool))[0][0])
+    want = oracle.vector_arm(ot, X[5].tolist(), 10, None, [ot.document_id[z]])
+    got = mrag_b200.vector_arm(pt, X[5].tolist(), 10, None, [ot.document_id[z]])
+    assert [g["id"] for g in got] == [w["id"] for w in want]
+    assert any(g["id"] == ot.id[z] and g["similarity"] == 1.0 for g in got)
+    # over the LIMIT cap -> logged and [] (fail-soft), never raised
+    assert mrag_b200.vector_arm(pt, X[5].tolist(), 300, None, None, over_fetch_factor=8) == []
+
+
+def test_republish_document(oracle):
+    """DELETE + INSERT of one document (publish.py:310-313): old rows vanish, new rows are found."""
+    from helpers import build_tables
+    ot, pt, X, valid, meta, info = build_tables(oracle, 800, 32, seed=13)
+    store = mrag_b200.B200VectorStore(table=pt)
+    doc = ot.document_id[400]
+    old_ids = {ot.id[i] for i in range(800) if ot.document_id[i] == doc}
+    store.delete_by_document(doc)
+    emb = X[400].tolist()
+    assert not {h["id"] for h in store.search(emb, 50)} & old_ids
+    store.add(["new-1"], [emb], [{"document_id": doc, "source_type": "fact", "source_id": "s"}])
+    hits = store.search(emb, 3)
+    assert hits[0]["id"] == "new-1" and hits[0]["distance"] == pytest.approx(1.0, abs=1e-6)
+    assert [h["id"] for h in store.search(emb, 5, document_id=doc)] == ["new-1"]
+
+
+# ---------------------------------------------------------------------------------------------
+# device I/O, re-entrancy, K4
+# ---------------------------------------------------------------------------------------------
+def test_device_io_and_row_base(oracle):
+    import torch
+    n, dim, k = 8000, 128, 16
+    X, valid = synth.make_corpus(n, dim, seed=51)
+    Q = synth.make_queries(X, 9, seed=52)
+    idx = Index(dim, "bf16", 0, n)
+    idx.append_device(torch.from_numpy(X).cuda(), make_meta(n, valid=valid))
+    idx.set_row_base(1_000_000)
+    qd = torch.from_numpy(Q).cuda()
+    s, r, c = idx.search_device(qd, k)
+    s2, r2, c2 = idx.search_device(qd, k, sync=False)
+    torch.cuda.synchronize()
+    assert torch.equal(r, r2) and torch.equal(c, c2) and torch.equal(s, s2)
+    check_all(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, s.cpu().numpy(), r.cpu().numpy(),
+              c.cpu().numpy(), "bf16", row_base=1_000_000)
+    idx.close()
+
+
+def test_concurrent_searches_on_one_handle(oracle):
+    """Up to 5 narrow searches run concurrently per request (corpus_search_agent.py:794-797)."""
+    n, dim, k = 20000, 96, 10
+    X, valid = synth.make_corpus(n, dim, seed=61)
+    Q = synth.make_queries(X, 40, seed=62)
+    idx = Index(dim, "f32", 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    want_s, want_r, want_c = idx.search(Q, k)
+    errs = []
+
+    def work(t):
+        try:
+            for rep in range(5):
+                for i in range(t, 40, 8):
+                    s, r, c = idx.search(Q[i:i + 1], k)
+                    assert (r[0] == want_r[i]).all() and c[0] == want_c[i]
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    check_all(oracle, X, Q[:5], valid.astype(bool), k, want_s[:5], want_r[:5], want_c[:5], "f32")
+    idx.close()
+
+
+def test_merge_topk_kernel():
+    import torch
+    rng = np.random.default_rng(5)
+    for n_lists, nq, k in [(2, 3, 10), (8, 5, 100), (3, 1, 1), (8, 2, 1600)]:
+        stride = nq * k + 13
+        sc = np.full((n_lists, stride), np.nan, np.float32)
+        ro = np.full((n_lists, stride), -1, np.int64)
+        co = np.zeros((n_lists, nq + 3), np.int32)
+        want = []
+        for q in range(nq):
+            cand = []
+            for l in range(n_lists):
+                m = int(rng.integers(0, k + 1))
+                vals = np.sort(rng.choice(np.round(rng.standard_normal(40), 1), size=m).astype(np.float32))[::-1]
+                n_nan = int(rng.integers(0, 3)) if m > 2 else 0
+                vals = vals.copy()
+                if n_nan:
+                    vals[m - n_nan:] = np.nan
+                rws = rng.choice(10_000_000, size=m, replace=False).astype(np.int64) + l * 10_000_000
+                # lists arrive sorted: score desc, NaN last, row asc inside ties
+                order = sorted(range(m), key=lambda j: (math.isnan(vals[j]), -vals[j] if not math.isnan(vals[j]) else 0, rws[j]))
+                vals, rws = vals[order], rws[order]
+                sc[l, q * k:q * k + m] = vals
+                ro[l, q * k:q * k + m] = rws
+                co[l, q] = m
+                cand += list(zip(vals.tolist(), rws.tolist()))
+            cand.sort(key=lambda t: (math.isnan(t[0]), -t[0] if not math.isnan(t[0]) else 0, t[1]))
+            want.append(cand[:k])
+        s, r, c = merge_topk(0, torch.from_numpy(sc).cuda(), torch.from_numpy(ro).cuda(), torch.from_numpy(co).cuda(),
+                             n_lists, nq, k, (stride, stride, nq + 3))
+        torch.cuda.synchronize()
+        s, r, c = s.cpu().numpy(), r.cpu().numpy(), c.cpu().numpy()
+        for q in range(nq):
+            assert c[q] == len(want[q])
+            assert r[q, :c[q]].tolist() == [w[1] for w in want[q]]
+            got_s = s[q, :c[q]]
+            ws = np.array([w[0] for w in want[q]], np.float32)
+            assert ((got_s == ws) | (np.isnan(got_s) & np.isnan(ws))).all()
+            assert (r[q, c[q]:] == -1).all()
+
+
+def test_bad_arguments():
+    idx = Index(8, "f32", 0, 10)
+    with pytest.raises(N.MragError):
+        idx.search(np.zeros((1, 8), np.float32), 0)
+    with pytest.raises(N.MragError):
+        idx.search(np.zeros((1, 8), np.float32), N.MRAG_MAX_K + 1)
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((1, 9), np.float32), 1)
+    with pytest.raises(ValueError):
+        idx.append(np.full((1, 8), np.nan, np.float32))
+    with pytest.raises(N.MragError):
+        Index(8, "f32", 99, 10)
+    idx.close()
