@@ -156,7 +156,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["seconds"] / steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.cpu_queries),
+        "config": workload_config(args, args.batch),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = Postgres+pgvector, not runnable here (no Postgres, extension not vendored): this arm "

@@ -176,7 +176,8 @@ enum {
  *   counts  nq    int32     rows returned (< k when fewer rows pass the filter)
  * Ordering: similarity descending, NaN last, ties by ascending row (pgvector leaves ties
  * unspecified; this library fixes them so results do not depend on sharding).
- * `stream`: cudaStream_t to run on, or NULL for an internal per-call stream.
+ * `stream`: cudaStream_t to run on.  NULL means: with host buffers, an internal per-call stream
+ * (concurrent callers overlap); with MRAG_OPT_DEVICE_IO, the CUDA default (legacy) stream.
  */
 int mrag_search(mrag_index* idx, const float* q, int nq, int k, const mrag_filter* filter,
                 float* scores, int64_t* rows, int32_t* counts, uint32_t options, void* stream);

@@ -9,12 +9,12 @@ Layout
   index.py         Index / Filter: one row shard in HBM
   table.py         PublishedTable: host half of rag_published_embeddings (ids, text, vocabularies)
   vector_store.py  VectorStore ABC + B200VectorStore + get_vector_store()  (reference: vector_store.py)
-  vector_arm.py    vector_arm / _vector_arm                                (reference: corpus_search.py:1427)
+  corpus_search.py vector_arm / _vector_arm                                (reference: corpus_search.py:1427)
   sharded.py       row-sharded search across GPUs (allgather + k-way merge)
   synth.py         deterministic synthetic corpora / metadata / queries
 """
 from .vector_store import B200VectorStore, NoopVectorStore, VectorStore, get_vector_store  # noqa: F401
-from .vector_arm import CorpusFilters, LexiconExpansion, _vector_arm, vector_arm  # noqa: F401
+from .corpus_search import CorpusFilters, LexiconExpansion, _vector_arm, vector_arm  # noqa: F401
 from .table import PublishedTable  # noqa: F401
 from .index import Filter, Index, make_meta, merge_topk  # noqa: F401
 

@@ -640,9 +640,13 @@ extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const m
     std::shared_lock<std::shared_mutex> rl(x->lock);
     DeviceGuard g(x->device);
     if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_search: cudaSetDevice(%d) failed (no CPU path)", x->device);
-    Workspace* w = acquire_ws(x, static_cast<cudaStream_t>(stream));
+    // host buffers + NULL stream: an internal per-call stream (concurrent callers overlap);
+    // device buffers + NULL stream: the CUDA default (legacy) stream, as for any CUDA library
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    if (dev_io && !user) user = cudaStreamLegacy;
+    Workspace* w = acquire_ws(x, user);
     if (!w) return fail(MRAG_ERR_OOM, "mrag_search: cannot create a workspace");
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : w->own_stream;
+    cudaStream_t s = user ? user : w->own_stream;
 
     EventSet* ev = &w->ev;
     if (t_ring_used < int(t_ring.size()) && t_ring_device == x->device) ev = &t_ring[size_t(t_ring_used++)];

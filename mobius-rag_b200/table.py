@@ -50,6 +50,7 @@ class PublishedTable:
         self.document_authority_level: list[str | None] = []
         self.extra: dict[str, list] = {c: [] for c in HYDRATE_COLS}
         self.doc_idx: dict[str, int] = {}
+        self._next_doc = 0          # doc_idx values are never reused (tombstoned rows keep theirs)
         self.doc_d_tags: dict[str, set] = {}
         self.doc_p_tags: dict[str, set] = {}
 
@@ -60,7 +61,8 @@ class PublishedTable:
     def _doc(self, document_id: str) -> int:
         d = self.doc_idx.get(document_id)
         if d is None:
-            d = len(self.doc_idx)
+            d = self._next_doc
+            self._next_doc += 1
             self.doc_idx[document_id] = d
         return d
 

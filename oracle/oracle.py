@@ -210,6 +210,8 @@ class Table:
 
 def sql_ilike(value: str, pattern: str) -> bool:
     """Postgres ``value ILIKE pattern``: case-insensitive, ``%`` any run, ``_`` any one char."""
+    if value is None:            # NULL ILIKE pattern is NULL, i.e. not true
+        return False
     rx = "".join(".*" if c == "%" else "." if c == "_" else re.escape(c) for c in pattern)
     return re.fullmatch(rx, value, flags=re.IGNORECASE | re.DOTALL) is not None
 

@@ -270,7 +270,7 @@ def test_store_search_matches_pg_statement(oracle, tables):
 
 
 def test_vector_arm_matches_reference_restatement(oracle, tables):
-    from mrag_b200.vector_arm import CorpusFilters, LexiconExpansion
+    from mrag_b200.corpus_search import CorpusFilters, LexiconExpansion
     ot, pt, X, valid = tables
     rng = np.random.default_rng(1)
     docs = sorted(set(ot.document_id))

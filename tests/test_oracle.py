@@ -113,7 +113,7 @@ def test_ilike(oracle):
 def test_vector_arm_restatement_semantics(oracle):
     """Hand-checkable table: LIMIT, strict->relaxed retry, clamp, min_similarity, stop-at-k."""
     from helpers import build_tables
-    from mrag_b200.vector_arm import CorpusFilters, LexiconExpansion
+    from mrag_b200.corpus_search import CorpusFilters, LexiconExpansion
     ot, _, X, valid, meta, info = build_tables(oracle, 600, 32, seed=3, with_product=False)
     q = (X[10] * 1.0).tolist()
     res = oracle.vector_arm(ot, q, 5, None, None)
