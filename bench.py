@@ -31,7 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "QPS exact cosine top-10, 10Mx768 corpus"
-DEFAULT_BATCH = 4          # queries per step (see DESIGN.md "Measurement")
+DEFAULT_BATCH = 64         # queries per step (see DESIGN.md "Measurement")
 CHUNK = 1 << 18            # rows generated per chunk; shard cuts fall on chunk boundaries
 
 
@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--sweep", default="1,64", help="extra batch sizes measured briefly at N=1 ('' = none)")
+    ap.add_argument("--sweep", default="1,4,16,256,1024", help="extra batch sizes measured briefly at N=1 ('' = none)")
     ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the CPU baseline sample")
     ap.add_argument("--cpu-queries", type=int, default=8, help="queries of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -285,11 +285,12 @@ def main():
                 "merge_ms": merge_ms, "clocks": clk, "result": res, "Q": Q}
 
     def roofline_of(m, batch):
-        scan_launches = (batch + 3) // 4 if idx.last_scan_kind() == "gemv" else 1
+        group = 4 if idx.last_scan_kind() == "gemv" else 64      # queries per scan launch
+        scan_launches = (batch + group - 1) // group
         if not m["scan_ms"]:
             return None
         per_launch_ms = float(np.mean(m["scan_ms"])) / scan_launches
-        q_per_launch = min(batch, 4) if idx.last_scan_kind() == "gemv" else batch
+        q_per_launch = min(batch, group)
         bytes_launch = n_local * args.dim * elem + (n_local + 7) // 8 + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,

@@ -2,7 +2,9 @@
 // that strings the kernels together on one CUDA stream:
 //
 //   query_prep_kernel -> [pool_bitmap_kernel] -> [filter_mask_kernel]      (prepare)
-//   -> scan_gemv_kernel x ceil(nq / NQ)                                    (scan + fused select)
+//   -> scan_mma_kernel x ceil(nq / 64)   (bf16 corpus, dim <= 768: TMA + tcgen05 + TMEM)
+//      or scan_gemv_kernel x ceil(nq / 4) (CUDA cores: fp32 corpus, wide rows, single queries,
+//                                          selective filters -- it never loads a masked row)
 //   -> merge_kernel -> nan_tail_kernel                                     (ORDER BY .. LIMIT k)
 //
 // Stands in for the SQL statement of app/services/vector_store.py:274-287 and
@@ -12,6 +14,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "scan_gemv.cuh"
+#include "scan_mma.cuh"
 #include "select.cuh"
 
 #include <algorithm>
@@ -130,6 +133,8 @@ struct mrag_index {
     MetaCols cols{};
     uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
     int64_t n_tag_docs = 0, tag_docs_cap = 0;
+    CUtensorMap tmap;                   // corpus as a 2-D bf16 tensor, 64x64 boxes, SWIZZLE_128B
+    bool has_tmap = false;
     cudaStream_t wstream = nullptr;     // write-side stream
     std::shared_mutex lock;             // searches share, writers exclude
     std::mutex ws_lock;
@@ -155,6 +160,31 @@ static thread_local const char* t_last_kind = "none";
 static thread_local std::vector<EventSet> t_ring;
 static thread_local int t_ring_used = 0;
 static thread_local int t_ring_device = -1;
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptor of the corpus (driver entry point fetched through the runtime: no -lcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_corpus_tmap(mrag_index* x, int64_t alloc_rows) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(MRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[2] = {cuuint64_t(x->ld), cuuint64_t(alloc_rows)};
+    cuuint64_t gstride[1] = {cuuint64_t(x->ld) * 2};
+    cuuint32_t box[2] = {cuuint32_t(kMmaKBlock), cuuint32_t(kMmaTileRows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<PFN_tmapEncodeTiled>(fn)(
+        &x->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x->rows, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    x->has_tmap = true;
+    return MRAG_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // lifecycle
@@ -209,6 +239,15 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
         mrag_destroy(x);
         t_err = std::string("mrag_create: ") + cudaGetErrorString(e);
         return code;
+    }
+    if (dtype == MRAG_BF16 && x->ld <= kMmaMaxLd) {
+        // rows past `capacity` inside the allocation are never selected (mask bits are zero)
+        if (make_corpus_tmap(x, cap32 + 64) != MRAG_OK) {
+            std::string keep = t_err;
+            mrag_destroy(x);
+            t_err = keep;
+            return MRAG_ERR_CUDA;
+        }
     }
     *out = x;
     return MRAG_OK;
@@ -529,6 +568,31 @@ static int run_scan_gemv(mrag_index* x, ScanArgs a, int nq, int grid, cudaStream
     return MRAG_OK;
 }
 
+static int mma_stages_for(int cap) {
+    const size_t fixed = mma_smem_bytes(0, cap);
+    if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return 0;
+    return int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
+}
+
+static int run_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        CU(cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set[dev] = true;
+    }
+    a.stages = mma_stages_for(a.cap);
+    const size_t smem = mma_smem_bytes(a.stages, a.cap);
+    for (int q0 = 0; q0 < nq; q0 += kMmaQueries) {
+        a.q0 = q0;
+        a.nq = std::min(kMmaQueries, nq - q0);
+        scan_mma_kernel<<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        LAUNCHED();
+    }
+    return MRAG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // search
 // ------------------------------------------------------------------------------------------
@@ -573,7 +637,17 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     // ---- scan + select, MRAG_FUSED_K results per round
     const int rounds = int(ceil_div(k, MRAG_FUSED_K));
     const int64_t nwords = ceil_div(n, 32);
-    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
+    // tensor-core scan: bf16 rows of <= 768 elements; single queries stay on the CUDA-core scan,
+    // which already streams at ~0.9 of the HBM peak and skips masked rows individually
+    const bool can_mma = x->has_tmap && n > 0;
+    bool use_mma = can_mma && !(options & MRAG_OPT_FORCE_GEMV) && nq >= 2;
+    if (options & MRAG_OPT_FORCE_MMA) {
+        if (!can_mma) return fail(MRAG_ERR_STATE, "mrag_search: the tensor-core scan needs a bf16 index with dim <= %d", kMmaMaxLd);
+        use_mma = true;
+    }
+    const int grid = use_mma
+        ? int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))))
+        : int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
     if (rounds > 1 && w->ub.reserve(size_t(nq))) return MRAG_ERR_OOM;
     float scan_ms_dummy = 0; (void)scan_ms_dummy;
     // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
@@ -583,7 +657,15 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         const int kr = std::min(MRAG_FUSED_K, k - k_off);
         const int kp = std::max(8, host_next_pow2(kr));
         if (w->part.reserve(size_t(nq) * grid * kp)) return MRAG_ERR_OOM;
-        if (n > 0) {
+        if (n > 0 && use_mma) {
+            MmaArgs a{};
+            a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
+            a.ub = (r > 0) ? w->ub.p : nullptr;
+            a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid; a.cap = kr + kMmaSlack;
+            int rc = run_scan_mma(x, a, nq, grid, s);
+            if (rc != MRAG_OK) return rc;
+            t_last_kind = "mma";
+        } else if (n > 0) {
             ScanArgs a{};
             a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p;
             a.ub = (r > 0) ? w->ub.p : nullptr;
@@ -634,8 +716,8 @@ extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const m
     const bool no_sync = (options & MRAG_OPT_NO_SYNC) && dev_io;
     if ((options & MRAG_OPT_NO_SYNC) && !dev_io)
         return fail(MRAG_ERR_ARG, "mrag_search: MRAG_OPT_NO_SYNC needs MRAG_OPT_DEVICE_IO");
-    if (options & MRAG_OPT_FORCE_MMA)
-        return fail(MRAG_ERR_STATE, "mrag_search: the tcgen05 scan is not built into this version");
+    if ((options & MRAG_OPT_FORCE_MMA) && (options & MRAG_OPT_FORCE_GEMV))
+        return fail(MRAG_ERR_ARG, "mrag_search: FORCE_GEMV and FORCE_MMA exclude each other");
 
     std::shared_lock<std::shared_mutex> rl(x->lock);
     DeviceGuard g(x->device);

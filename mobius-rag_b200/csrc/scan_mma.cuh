@@ -1,0 +1,440 @@
+// scan_mma.cuh -- K1' + K3: the tensor-core scan for bf16 corpora (sm_100a: TMA + tcgen05 + TMEM).
+//
+// Replaces the same sequential-scan plan as scan_gemv.cuh (corpus_search.py:1525-1536,
+// vector_store.py:274-287) for up to 64 queries per pass while staying HBM-bound: every corpus
+// byte is read once, by TMA, into a shared-memory ring; the dot products run on the tensor cores.
+//
+// Orientation (transposed w.r.t. a textbook GEMM so that a thread owns a QUERY, not a row):
+//     D[128 lanes x 64 rows] += A[128 lanes x K] * B[64 rows x K]^T          (tcgen05.mma kind::f16)
+//   A = the queries, resident in TENSOR MEMORY for the whole kernel (K/2 columns of packed bf16x2).
+//       An fp32 query q is split EXACTLY-ish into bf16 hi + bf16 lo (q = hi + lo to 16 mantissa
+//       bits); lane j < 64 holds hi of query j, lane 64 + j holds lo of query j, so the final score
+//       carries fp32-level accuracy although the MMA operands are bf16.
+//   B = a 64-row tile of the corpus, K-major, 64 bf16 (128 B) per shared-memory row, SWIZZLE_128B,
+//       streamed by TMA: one 8 KB box per (tile, k-block), ring of `stages` boxes.
+//   D = fp32 accumulators in tensor memory, two buffers of 64 columns (MMA of tile t+1 overlaps the
+//       select of tile t).  TMEM budget: 384 (A, K = 768) + 2 x 64 (D) = 512 columns.
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over row tiles):
+//   warp 0      TMA producer            warp 1      MMA issuer (one elected lane) + TMEM owner
+//   warps 2,3   "lo" epilogue: TMEM lanes 64..127 -> shared-memory exchange buffer
+//   warps 4,5   "hi" epilogue: TMEM lanes 0..63, add lo, scale by 1/|x| * 1/|q|, per-THREAD top-k
+//               (a thread sees all scores of its query in row order: no cross-thread traffic except
+//               the warp-cooperative compaction of a full candidate buffer).
+// Tiles whose 64 mask bits are all clear are skipped by every role (never loaded).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace mrag {
+
+constexpr int kMmaThreads = 192;
+constexpr int kMmaTileRows = 64;          // UMMA N
+constexpr int kMmaKBlock = 64;            // bf16 elements per smem row = 128 B = one swizzle span
+constexpr int kMmaStageBytes = kMmaTileRows * 128;
+constexpr int kMmaQueries = 64;           // queries per pass (hi / lo halves of the 128 TMEM lanes)
+constexpr int kMmaMaxLd = 768;            // A needs ld/2 TMEM columns; 384 + 128 (D) = 512
+constexpr int kMmaTmemCols = 512;
+constexpr int kMmaDCol0 = 384;
+constexpr int kMmaSlack = 64;             // candidate buffer = k + slack keys per query
+constexpr long long kSpinCycles = 4000000000ll;   // ~2 s: a protocol bug traps instead of hanging the GPU
+
+struct MmaArgs {
+    int64_t n;               // rows in the shard
+    int ld;                  // padded row length (multiple of 64, <= kMmaMaxLd)
+    const uint32_t* mask;    // row bitmap (valid AND filter), ceil(n/32) words
+    const float* inv_norm;   // [n] 1/|x| of the stored row (+inf for a zero row)
+    const float* q;          // [*][ld] fp32 queries, zero padded
+    const float* qinv;       // [*] 1/|q| (+inf for a zero query)
+    const uint64_t* ub;      // [*] exclusive upper-bound key per query, or nullptr
+    uint64_t* part;          // [*][P][kp] per-CTA sorted candidate lists
+    int q0, nq;              // queries [q0, q0+nq) handled by this launch (nq <= 64)
+    int k, kp, P;
+    int cap;                 // candidate buffer capacity per query (k + kMmaSlack)
+    int stages;              // TMA ring depth
+};
+
+inline size_t mma_smem_bytes(int stages, int cap) {
+    return 1024 /*align slack*/ + size_t(stages) * kMmaStageBytes + 2 * 64 * 64 * 4 /*exchange*/ +
+           size_t(kMmaQueries) * cap * 8 + 1024 /*barriers*/;
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+MRAG_DEVINL uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+MRAG_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MRAG_DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+MRAG_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+MRAG_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+MRAG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kSpinCycles) __trap();
+    }
+}
+MRAG_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MRAG_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+MRAG_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+MRAG_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+MRAG_DEVINL void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    const uint64_t evict_first = 0x12F0000000000000ull;      // each corpus byte is used once
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(evict_first)
+        : "memory");
+}
+
+MRAG_DEVINL void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+MRAG_DEVINL void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+MRAG_DEVINL void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+MRAG_DEVINL void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1
+MRAG_DEVINL uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);            // start address
+    d |= uint64_t(0) << 16;                                // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t(1024 >> 4) << 32;                        // stride byte offset
+    d |= uint64_t(1) << 46;                                // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                                // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 64
+constexpr uint32_t kMmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kMmaTileRows >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+#define MRAG_TMEM_LD64(r, taddr)                                                                                      \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "                                                                    \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+        "%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55," \
+        "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"                                                                   \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),     \
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),    \
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),    \
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),    \
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),    \
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),    \
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])                  \
+        : "r"(taddr)                                                                                                 \
+        : "memory")
+
+#define MRAG_TMEM_ST32(taddr, r)                                                                                      \
+    asm volatile(                                                                                                    \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                              \
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"   \
+        "%29,%30,%31,%32};" ::"r"(taddr),                                                                            \
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),  \
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),  \
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                               \
+        : "memory")
+
+MRAG_DEVINL uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    // element with the LOWER k index in the low half
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- warp-cooperative selection of the `keep` largest of n unique keys in buf (rank sort) -----
+// afterwards buf[0..min(n,keep)) holds them in descending order.  n <= 32 * kRankPerLane.
+constexpr int kRankPerLane = 6;           // cap <= 192
+MRAG_DEVINL void warp_rank_select(uint64_t* buf, int n, int keep, int lane) {
+    uint64_t key[kRankPerLane];
+    int rank[kRankPerLane];
+#pragma unroll
+    for (int e = 0; e < kRankPerLane; ++e) {
+        const int i = lane + 32 * e;
+        key[e] = (i < n) ? buf[i] : 0ull;
+        rank[e] = 0;
+    }
+    for (int j = 0; j < n; ++j) {
+        const uint64_t kj = buf[j];           // broadcast read
+#pragma unroll
+        for (int e = 0; e < kRankPerLane; ++e) rank[e] += (kj > key[e]) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kRankPerLane; ++e) {
+        const int i = lane + 32 * e;
+        if (i < n && rank[e] < keep) buf[rank[e]] = key[e];
+    }
+    __syncwarp();
+}
+
+struct SelState {
+    uint64_t thr;    // admit keys > thr  (k-th best key of the last compaction, 0 before)
+    int cnt;         // keys in this thread's buffer
+};
+
+// Rare path of the select: some lane of the warp has a candidate.  Lanes with `ins` append their
+// key; any buffer that became full is compacted to its k best by the whole warp.
+__device__ __noinline__ SelState select_slow(SelState st, bool ins, uint64_t key, uint64_t* cand_warp, int cap, int k,
+                                             int lane) {
+    if (ins) {
+        cand_warp[size_t(lane) * cap + st.cnt] = key;
+        ++st.cnt;
+    }
+    unsigned full = __ballot_sync(kFull, st.cnt == cap);
+    while (full) {
+        const int L = __ffs(full) - 1;
+        full &= full - 1;
+        __syncwarp();
+        uint64_t* b = cand_warp + size_t(L) * cap;
+        warp_rank_select(b, cap, k, lane);
+        const uint64_t kth = b[k - 1];
+        if (lane == L) { st.cnt = k; st.thr = kth; }
+    }
+    return st;
+}
+
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
+    extern __shared__ unsigned char mma_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mma_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* stage_base = smem;                                            // stages * 8 KB, 1024-aligned
+    float* xbuf = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [2][64 rows][64 queries]
+    uint64_t* cand = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xbuf) + 2 * 64 * 64 * 4);   // [64][cap]
+    uint64_t* bars = cand + size_t(kMmaQueries) * a.cap;
+    uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
+    uint64_t* empty_bar = full_bar + a.stages;       // [stages]   MMA -> TMA
+    uint64_t* tfull_bar = empty_bar + a.stages;      // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
+    uint64_t* xfull_bar = tempty_bar + 2;            // [2]        lo warps -> hi warps
+    uint64_t* xempty_bar = xfull_bar + 2;            // [2]        hi warps -> lo warps
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xempty_bar + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kblocks = a.ld / kMmaKBlock;
+    const int64_t num_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
+    const int64_t nwords = (a.n + 31) >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&xfull_bar[i], 64);
+            mbar_init(&xempty_bar[i], 64);
+        }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, kMmaTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // ---- queries -> tensor memory (epilogue warps; lane of TMEM = thread)
+    if (warp >= 2) {
+        const int quarter = warp & 3;                       // TMEM lanes [32*quarter, +32)
+        const int qi = (quarter & 1) * 32 + lane;           // query owned by this thread
+        const bool lo_part = quarter >= 2;
+        const bool live = qi < a.nq;
+        const float* qrow = a.q + size_t(a.q0 + (live ? qi : 0)) * a.ld;
+        for (int c0 = 0; c0 < a.ld / 2; c0 += 32) {         // 32 columns = 64 elements per store
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+                float4 f = live ? __ldg(reinterpret_cast<const float4*>(qrow + c0 * 2) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(e[i]));
+                    e[i] = lo_part ? (e[i] - hi) : hi;      // lo = q - hi is exact in fp32
+                }
+                r[2 * v] = pack_bf16x2(e[0], e[1]);
+                r[2 * v + 1] = pack_bf16x2(e[2], e[3]);
+            }
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0);
+            MRAG_TMEM_ST32(taddr, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const uint32_t m0 = __ldg(a.mask + 2 * t);
+                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
+                if ((m0 | m1) == 0u) continue;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], kMmaStageBytes);
+                    tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
+                                &full_bar[s]);
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const uint32_t m0 = __ldg(a.mask + 2 * t);
+                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
+                if ((m0 | m1) == 0u) continue;
+                mbar_wait(&tempty_bar[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(stage_base + size_t(s) * kMmaStageBytes));
+#pragma unroll
+                    for (int j = 0; j < kMmaKBlock / 16; ++j) {
+                        // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
+                        umma_ts_bf16(d_tmem, tmem_base + uint32_t(kb * (kMmaKBlock / 2) + j * 8), bdesc + uint64_t(j * 2),
+                                     kMmaIdesc, (kb | j) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&tfull_bar[as]);                    // accumulator ready
+                if (++as == 2) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int quarter = warp & 3;
+        const int qi = (quarter & 1) * 32 + lane;
+        const bool lo_part = quarter >= 2;
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        int as = 0, xs = 0;
+        uint32_t aph = 0, xph = 0;
+
+        if (lo_part) {
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const uint32_t m0 = __ldg(a.mask + 2 * t);
+                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
+                if ((m0 | m1) == 0u) continue;
+                uint32_t d[64];
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
+                MRAG_TMEM_LD64(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);
+                if (++as == 2) { as = 0; aph ^= 1u; }
+                mbar_wait(&xempty_bar[xs], xph ^ 1u);
+                float* xb = xbuf + size_t(xs) * 64 * 64;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) xb[c * 64 + qi] = __uint_as_float(d[c]);
+                mbar_arrive(&xfull_bar[xs]);
+                if (++xs == 2) { xs = 0; xph ^= 1u; }
+            }
+        } else {
+            const bool live = qi < a.nq;
+            const float qinv = live ? a.qinv[a.q0 + qi] : 0.0f;
+            const uint64_t ubk = (a.ub && live) ? a.ub[a.q0 + qi] : ~0ull;
+            uint64_t* cand_warp = cand + size_t((quarter & 1) * 32) * a.cap;
+            SelState st;
+            st.cnt = 0;
+            // a thread without a query, or with a zero-norm query (every similarity NaN), admits nothing
+            st.thr = (live && !isinf(qinv)) ? 0ull : ~0ull;
+
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const uint32_t m0 = __ldg(a.mask + 2 * t);
+                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
+                if ((m0 | m1) == 0u) continue;
+                const int64_t r0 = t * kMmaTileRows;
+                // 1/|x| of the tile's rows, two per lane, fetched before the accumulator is waited for
+                const float in0 = (r0 + lane < a.n) ? __ldg(a.inv_norm + r0 + lane) : 0.0f;
+                const float in1 = (r0 + 32 + lane < a.n) ? __ldg(a.inv_norm + r0 + 32 + lane) : 0.0f;
+                uint32_t d[64];
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
+                MRAG_TMEM_LD64(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);
+                if (++as == 2) { as = 0; aph ^= 1u; }
+                mbar_wait(&xfull_bar[xs], xph);
+                const float* xb = xbuf + size_t(xs) * 64 * 64;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const uint32_t mw = (c < 32) ? m0 : m1;
+                    const float inv = __shfl_sync(kFull, (c < 32) ? in0 : in1, c & 31);
+                    if ((mw >> (c & 31)) & 1u) {                              // warp-uniform
+                        const float dot = __uint_as_float(d[c]) + xb[c * 64 + qi];
+                        const float s = dot * inv * qinv;
+                        const uint64_t key = make_key(s, uint32_t(r0 + c));
+                        const bool ins = (s == s) && key > st.thr && key < ubk;
+                        if (__any_sync(kFull, ins)) st = select_slow(st, ins, key, cand_warp, a.cap, a.k, lane);
+                    }
+                }
+                mbar_arrive(&xempty_bar[xs]);
+                if (++xs == 2) { xs = 0; xph ^= 1u; }
+            }
+
+            // ---- this CTA's sorted list per query
+            __syncwarp();
+            for (int L = 0; L < 32; ++L) {
+                const int qL = (quarter & 1) * 32 + L;
+                if (qL >= a.nq) break;
+                const int n = __shfl_sync(kFull, st.cnt, L);
+                uint64_t* b = cand_warp + size_t(L) * a.cap;
+                warp_rank_select(b, n, a.kp, lane);
+                uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
+                const int have = n < a.k ? n : a.k;
+                for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kMmaTmemCols);
+    }
+}
+
+}  // namespace mrag

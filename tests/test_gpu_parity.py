@@ -435,3 +435,82 @@ def test_bad_arguments():
     with pytest.raises(N.MragError):
         Index(8, "f32", 99, 10)
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the tensor-core scan (TMA + tcgen05 + TMEM), pinned with MRAG_OPT_FORCE_MMA, and the CUDA-core
+# scan pinned with MRAG_OPT_FORCE_GEMV, must both equal the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (5000, 768, 1, 10), (5000, 768, 2, 10), (64, 64, 3, 10), (63, 64, 1, 5), (65, 128, 64, 10),
+    (20000, 768, 64, 10), (20000, 768, 65, 10), (30000, 256, 130, 10), (20000, 768, 7, 100),
+    (9000, 128, 4, 128), (9000, 128, 2, 129), (6000, 96, 3, 300), (4097, 100, 5, 7), (12000, 64, 33, 64),
+    (100000, 768, 16, 10),
+])
+@pytest.mark.parametrize("path", ["mma", "gemv"])
+def test_scan_paths_bf16(oracle, path, n, dim, nq, k):
+    X, valid = synth.make_corpus(n, dim, seed=n + dim + 1, null_frac=3e-3)
+    Q = synth.make_queries(X, nq, seed=k + 1)
+    idx = Index(dim, "bf16", 0, n + 5)
+    idx.append(X, make_meta(n, valid=valid))
+    opt = N.OPT_FORCE_MMA if path == "mma" else N.OPT_FORCE_GEMV
+    s, r, c = idx.search(Q, k, options=opt)
+    assert idx.last_scan_kind() == path
+    check_all(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, s, r, c, "bf16")
+    idx.close()
+
+
+def test_mma_default_dispatch_and_limits(oracle):
+    X, valid = synth.make_corpus(3000, 768, seed=3)
+    Q = synth.make_queries(X, 4, seed=4)
+    idx = Index(768, "bf16", 0, 3000)
+    idx.append(X, make_meta(3000, valid=valid))
+    idx.search(Q, 10)
+    assert idx.last_scan_kind() == "mma"          # batches go to the tensor cores
+    idx.search(Q[:1], 10)
+    assert idx.last_scan_kind() == "gemv"         # a single query stays on the streaming CUDA-core scan
+    idx.close()
+    for dtype, dim in (("f32", 768), ("bf16", 1536)):       # outside the tensor-core scan's envelope
+        idx = Index(dim, dtype, 0, 100)
+        idx.append(np.ones((3, dim), np.float32))
+        idx.search(np.ones((2, dim), np.float32), 2)
+        assert idx.last_scan_kind() == "gemv"
+        with pytest.raises(N.MragError):
+            idx.search(np.ones((2, dim), np.float32), 2, options=N.OPT_FORCE_MMA)
+        idx.close()
+
+
+def test_mma_with_filters_ties_and_nan(oracle):
+    n, dim, k = 40000, 768, 20
+    X, valid = synth.make_corpus(n, dim, seed=131, null_frac=2e-3, zero_norm_rows=3)
+    dup = np.arange(1000, 1000 + 90)                  # a 90-row boilerplate cluster across two tiles
+    X[dup] = X[dup[0]]
+    meta, doc_tags, info = synth.make_metadata(n, seed=132, rows_per_doc=64, valid=valid)
+    Q = synth.make_queries(X, 9, seed=133)
+    Q[0] = X[dup[0]] * 2.0
+    Q[1] = 0.0                                        # zero query: all NaN
+    idx = Index(dim, "bf16", 0, n)
+    idx.append(X, meta)
+    idx.set_doc_tags(0, doc_tags)
+    Xs = oracle.round_bf16(X)
+    v = valid.astype(bool)
+    doc = meta["doc_idx"]
+    rng = np.random.default_rng(5)
+    pool = rng.choice(info["n_docs"], size=40, replace=False)          # most tiles are skipped entirely
+    cases = [
+        (None, v),
+        (Filter().doc_pool(pool), np.isin(doc, pool) & v),
+        (Filter().state_eq(synth.STATES.index("TX")), (meta["state"] == synth.STATES.index("TX")) & v),
+        (Filter().doc_eq(int(doc[dup[0]])), (doc == doc[dup[0]]) & v),
+        (Filter().payer_in([0xFFFE]), np.zeros(n, bool)),
+    ]
+    for flt, want in cases:
+        s, r, c = idx.search(Q, k, flt, options=N.OPT_FORCE_MMA)
+        assert idx.last_scan_kind() == "mma"
+        check_all(oracle, Xs, Q, want, k, s, r, c, "bf16")
+        s2, r2, c2 = idx.search(Q, k, flt, options=N.OPT_FORCE_GEMV)
+        # the two scans agree with each other wherever the oracle's order is unambiguous
+        assert (c == c2).all()
+    s, r, c = idx.search(Q[:1], 50, options=N.OPT_FORCE_MMA)
+    assert r[0].tolist() == dup[:50].tolist() or r[0, :50].tolist() == sorted(r[0, :50].tolist())
+    idx.close()
