@@ -8,7 +8,7 @@
 //     D[128 lanes x 64 rows] += A[128 lanes x K] * B[64 rows x K]^T          (tcgen05.mma kind::f16)
 //   A = the queries, resident in TENSOR MEMORY for the whole kernel (K/2 columns of packed bf16x2).
 //       An fp32 query q is split EXACTLY-ish into bf16 hi + bf16 lo (q = hi + lo to 16 mantissa
-//       bits); lane j < 64 holds hi of query j, lane 64 + j holds lo of query j, so the final score
+//       bits); lane 64 + j holds hi of query j, lane j holds lo of query j, so the final score
 //       carries fp32-level accuracy although the MMA operands are bf16.
 //   B = a 64-row tile of the corpus, K-major, 64 bf16 (128 B) per shared-memory row, SWIZZLE_128B,
 //       streamed by TMA: one 8 KB box per (tile, k-block), ring of `stages` boxes.
@@ -17,14 +17,17 @@
 //
 // Warp roles (192 threads, 1 CTA per SM, persistent over row tiles):
 //   warp 0      TMA producer            warp 1      MMA issuer (one elected lane) + TMEM owner
-//   warps 2,3   "lo" epilogue: TMEM lanes 64..127 -> shared-memory exchange buffer
-//   warps 4,5   "hi" epilogue: TMEM lanes 0..63, add lo, scale by 1/|x| * 1/|q|, per-THREAD top-k
-//               (a thread sees all scores of its query in row order: no cross-thread traffic except
-//               the warp-cooperative compaction of a full candidate buffer).
+//   warps 4,5   "lo" epilogue: TMEM lanes 0..63 (lo halves) -> shared-memory exchange buffer
+//   warps 2,3   "hi" epilogue: TMEM lanes 64..127 (hi halves), add lo, scale by 1/|x| * 1/|q|,
+//               per-THREAD top-k (a thread sees all scores of its query in row order: no
+//               cross-thread traffic except the warp-cooperative compaction of a full buffer).
+//               The two heavy warps sit alone on scheduler partitions 2 and 3 (warp % 4); the
+//               waiting roles share partitions 0 and 1.
 // Tiles whose 64 mask bits are all clear are skipped by every role (never loaded).
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <math_constants.h>
 
 namespace mrag {
 
@@ -56,7 +59,7 @@ struct MmaArgs {
 
 inline size_t mma_smem_bytes(int stages, int cap) {
     return 1024 /*align slack*/ + size_t(stages) * kMmaStageBytes + 2 * 64 * 64 * 4 /*exchange*/ +
-           size_t(kMmaQueries) * cap * 8 + 1024 /*barriers*/;
+           2 * 64 * 4 /*1/|x| of the tile*/ + size_t(kMmaQueries) * cap * 8 + 1024 /*barriers*/;
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -77,10 +80,10 @@ MRAG_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep, do not spin
         : "memory");
     return ok != 0;
 }
@@ -157,6 +160,18 @@ constexpr uint32_t kMmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kM
         : "r"(taddr)                                                                                                 \
         : "memory")
 
+#define MRAG_TMEM_LD32(r, taddr)                                                                                      \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+        "%29,%30,%31}, [%32];"                                                                                       \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),     \
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),    \
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                  \
+        : "r"(taddr)                                                                                                 \
+        : "memory")
+
 #define MRAG_TMEM_ST32(taddr, r)                                                                                      \
     asm volatile(                                                                                                    \
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                              \
@@ -201,19 +216,13 @@ MRAG_DEVINL void warp_rank_select(uint64_t* buf, int n, int keep, int lane) {
 }
 
 struct SelState {
-    uint64_t thr;    // admit keys > thr  (k-th best key of the last compaction, 0 before)
+    float thr_s;     // admit scores > thr_s (score of the k-th best key of the last compaction)
     int cnt;         // keys in this thread's buffer
 };
 
-// Rare path of the select: some lane of the warp has a candidate.  Lanes with `ins` append their
-// key; any buffer that became full is compacted to its k best by the whole warp.
-__device__ __noinline__ SelState select_slow(SelState st, bool ins, uint64_t key, uint64_t* cand_warp, int cap, int k,
-                                             int lane) {
-    if (ins) {
-        cand_warp[size_t(lane) * cap + st.cnt] = key;
-        ++st.cnt;
-    }
-    unsigned full = __ballot_sync(kFull, st.cnt == cap);
+// Rare path of the select: the buffers of the lanes in `full` are at capacity; the whole warp
+// compacts each of them to its k best keys and raises that lane's threshold.
+__device__ __noinline__ SelState select_compact(SelState st, unsigned full, uint64_t* cand_warp, int cap, int k, int lane) {
     while (full) {
         const int L = __ffs(full) - 1;
         full &= full - 1;
@@ -221,18 +230,20 @@ __device__ __noinline__ SelState select_slow(SelState st, bool ins, uint64_t key
         uint64_t* b = cand_warp + size_t(L) * cap;
         warp_rank_select(b, cap, k, lane);
         const uint64_t kth = b[k - 1];
-        if (lane == L) { st.cnt = k; st.thr = kth; }
+        if (lane == L) { st.cnt = k; st.thr_s = key_score(kth); }
     }
     return st;
 }
 
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
-    extern __shared__ unsigned char mma_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mma_smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* stage_base = smem;                                            // stages * 8 KB, 1024-aligned
-    float* xbuf = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [2][64 rows][64 queries]
-    uint64_t* cand = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xbuf) + 2 * 64 * 64 * 4);   // [64][cap]
+    extern __shared__ __align__(1024) unsigned char mma_smem[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; stay in the shared address space (no integer casts)
+    unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;                                            // stages * 8 KB
+    float* xbuf = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [2][64 rows][64 queries] lo parts
+    float* xinv = xbuf + 2 * 64 * 64;                                            // [2][64 rows] 1/|x|, NaN = masked row
+    uint64_t* cand = reinterpret_cast<uint64_t*>(xinv + 2 * 64);                 // [64 queries][cap]
     uint64_t* bars = cand + size_t(kMmaQueries) * a.cap;
     uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
     uint64_t* empty_bar = full_bar + a.stages;       // [stages]   MMA -> TMA
@@ -246,6 +257,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     const int kblocks = a.ld / kMmaKBlock;
     const int64_t num_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
     const int64_t nwords = (a.n + 31) >> 5;
+    const int64_t G = gridDim.x;
+
+    // 64 mask bits of tile t (zero past the end); every role skips a tile whose bits are all clear
+    auto tile_mask = [&](int64_t t) -> uint2 {
+        uint2 m = make_uint2(0u, 0u);
+        if (t < num_tiles) {
+            m.x = __ldg(a.mask + 2 * t);
+            if (2 * t + 1 < nwords) m.y = __ldg(a.mask + 2 * t + 1);
+        }
+        return m;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -264,11 +286,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
+    // epilogue geometry: TMEM lanes [32*quarter, +32); quarters 2,3 hold the hi halves
+    const int quarter = warp & 3;
+    const int qi = (quarter & 1) * 32 + lane;           // query owned by this thread
+    const bool hi_part = quarter >= 2;
+
     // ---- queries -> tensor memory (epilogue warps; lane of TMEM = thread)
     if (warp >= 2) {
-        const int quarter = warp & 3;                       // TMEM lanes [32*quarter, +32)
-        const int qi = (quarter & 1) * 32 + lane;           // query owned by this thread
-        const bool lo_part = quarter >= 2;
         const bool live = qi < a.nq;
         const float* qrow = a.q + size_t(a.q0 + (live ? qi : 0)) * a.ld;
         for (int c0 = 0; c0 < a.ld / 2; c0 += 32) {         // 32 columns = 64 elements per store
@@ -280,7 +304,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float hi = __bfloat162float(__float2bfloat16_rn(e[i]));
-                    e[i] = lo_part ? (e[i] - hi) : hi;      // lo = q - hi is exact in fp32
+                    e[i] = hi_part ? hi : (e[i] - hi);      // lo = q - hi is exact in fp32
                 }
                 r[2 * v] = pack_bf16x2(e[0], e[1]);
                 r[2 * v + 1] = pack_bf16x2(e[2], e[3]);
@@ -299,17 +323,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const uint32_t m0 = __ldg(a.mask + 2 * t);
-                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
-                if ((m0 | m1) == 0u) continue;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    mbar_expect_tx(&full_bar[s], kMmaStageBytes);
-                    tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
-                                &full_bar[s]);
-                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+            uint2 m = tile_mask(blockIdx.x);
+            for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+                const uint2 mn = tile_mask(t + G);              // next tile's bits, off the critical path
+                if ((m.x | m.y) != 0u) {
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        mbar_expect_tx(&full_bar[s], kMmaStageBytes);
+                        tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
+                                    &full_bar[s]);
+                        if (++s == a.stages) { s = 0; ph ^= 1u; }
+                    }
                 }
+                m = mn;
             }
         }
     } else if (warp == 1) {
@@ -317,44 +343,49 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         if (lane == 0) {
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const uint32_t m0 = __ldg(a.mask + 2 * t);
-                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
-                if ((m0 | m1) == 0u) continue;
-                mbar_wait(&tempty_bar[as], aph ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
+            uint2 m = tile_mask(blockIdx.x);
+            for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+                const uint2 mn = tile_mask(t + G);
+                if ((m.x | m.y) != 0u) {
+                    mbar_wait(&tempty_bar[as], aph ^ 1u);
                     tc_fence_after();
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(stage_base + size_t(s) * kMmaStageBytes));
+                    const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_sw128_desc(smem_u32(stage_base + size_t(s) * kMmaStageBytes));
 #pragma unroll
-                    for (int j = 0; j < kMmaKBlock / 16; ++j) {
-                        // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
-                        umma_ts_bf16(d_tmem, tmem_base + uint32_t(kb * (kMmaKBlock / 2) + j * 8), bdesc + uint64_t(j * 2),
-                                     kMmaIdesc, (kb | j) != 0 ? 1u : 0u);
+                        for (int j = 0; j < kMmaKBlock / 16; ++j) {
+                            // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
+                            umma_ts_bf16(d_tmem, tmem_base + uint32_t(kb * (kMmaKBlock / 2) + j * 8), bdesc + uint64_t(j * 2),
+                                         kMmaIdesc, (kb | j) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
+                        if (++s == a.stages) { s = 0; ph ^= 1u; }
                     }
-                    umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
-                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                    umma_commit(&tfull_bar[as]);                // accumulator ready
+                    if (++as == 2) { as = 0; aph ^= 1u; }
                 }
-                umma_commit(&tfull_bar[as]);                    // accumulator ready
-                if (++as == 2) { as = 0; aph ^= 1u; }
+                m = mn;
             }
         }
-    } else {
-        // ================= epilogue =================
-        const int quarter = warp & 3;
-        const int qi = (quarter & 1) * 32 + lane;
-        const bool lo_part = quarter >= 2;
+    } else if (!hi_part) {
+        // ================= lo epilogue (warps 4,5): TMEM lanes 0..63 -> exchange buffer =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         int as = 0, xs = 0;
         uint32_t aph = 0, xph = 0;
-
-        if (lo_part) {
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const uint32_t m0 = __ldg(a.mask + 2 * t);
-                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
-                if ((m0 | m1) == 0u) continue;
+        uint2 m = tile_mask(blockIdx.x);
+        for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+            const uint2 mn = tile_mask(t + G);
+            if ((m.x | m.y) != 0u) {
+                // warp 4 also publishes 1/|x| of the tile's rows (NaN for a masked row: the mask is
+                // folded into the score); fetched before the accumulator is waited for
+                const int64_t r0 = t * kMmaTileRows;
+                float in0 = CUDART_NAN_F, in1 = CUDART_NAN_F;
+                if (quarter == 0) {
+                    if ((m.x >> lane) & 1u) in0 = __ldg(a.inv_norm + r0 + lane);
+                    if ((m.y >> lane) & 1u) in1 = __ldg(a.inv_norm + r0 + 32 + lane);
+                }
                 uint32_t d[64];
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
@@ -367,65 +398,113 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 float* xb = xbuf + size_t(xs) * 64 * 64;
 #pragma unroll
                 for (int c = 0; c < 64; ++c) xb[c * 64 + qi] = __uint_as_float(d[c]);
+                if (quarter == 0) {
+                    xinv[xs * 64 + lane] = in0;
+                    xinv[xs * 64 + 32 + lane] = in1;
+                }
                 mbar_arrive(&xfull_bar[xs]);
                 if (++xs == 2) { xs = 0; xph ^= 1u; }
             }
-        } else {
-            const bool live = qi < a.nq;
-            const float qinv = live ? a.qinv[a.q0 + qi] : 0.0f;
-            const uint64_t ubk = (a.ub && live) ? a.ub[a.q0 + qi] : ~0ull;
-            uint64_t* cand_warp = cand + size_t((quarter & 1) * 32) * a.cap;
-            SelState st;
-            st.cnt = 0;
-            // a thread without a query, or with a zero-norm query (every similarity NaN), admits nothing
-            st.thr = (live && !isinf(qinv)) ? 0ull : ~0ull;
+            m = mn;
+        }
+    } else {
+        // ================= hi epilogue (warps 2,3): score + per-thread top-k =================
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        int as = 0, xs = 0;
+        uint32_t aph = 0, xph = 0;
+        const bool live = qi < a.nq;
+        const bool warp_live = (quarter & 1) * 32 < a.nq;       // any query in this warp at all?
+        const float qinv = live ? a.qinv[a.q0 + qi] : 0.0f;
+        const uint64_t ubk = (a.ub && live) ? a.ub[a.q0 + qi] : ~0ull;
+        uint64_t* cand_warp = cand + size_t((quarter & 1) * 32) * a.cap;
+        uint64_t* mybuf = cand_warp + size_t(lane) * a.cap;
+        const int cap = a.cap;
+        SelState st;
+        st.cnt = 0;
+        // a thread without a query, or with a zero-norm query (every similarity NaN), admits nothing
+        st.thr_s = (live && !isinf(qinv)) ? -CUDART_INF_F : CUDART_INF_F;
 
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const uint32_t m0 = __ldg(a.mask + 2 * t);
-                const uint32_t m1 = (2 * t + 1 < nwords) ? __ldg(a.mask + 2 * t + 1) : 0u;
-                if ((m0 | m1) == 0u) continue;
+        uint2 m = tile_mask(blockIdx.x);
+        for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+            const uint2 mn = tile_mask(t + G);
+            if ((m.x | m.y) != 0u) {
                 const int64_t r0 = t * kMmaTileRows;
-                // 1/|x| of the tile's rows, two per lane, fetched before the accumulator is waited for
-                const float in0 = (r0 + lane < a.n) ? __ldg(a.inv_norm + r0 + lane) : 0.0f;
-                const float in1 = (r0 + 32 + lane < a.n) ? __ldg(a.inv_norm + r0 + 32 + lane) : 0.0f;
-                uint32_t d[64];
+                float sc[64];
+                float best = -CUDART_INF_F;
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
-                MRAG_TMEM_LD64(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                mbar_wait(&xfull_bar[xs], xph);
+                if (warp_live) {
+                    const float* xb = xbuf + size_t(xs) * 64 * 64;
+                    const float4* inv4 = reinterpret_cast<const float4*>(xinv + xs * 64);
+                    // ---- all 64 scores of this thread's query, branch free (masked / zero rows give
+                    //      NaN), in two halves of 32 accumulator columns to bound register pressure
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t d[32];
+                        MRAG_TMEM_LD32(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows + h * 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 iv = inv4[h * 8 + c4];                  // broadcast
+                            const float ivv[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = h * 32 + c4 * 4 + i;
+                                const float dot = __uint_as_float(d[c4 * 4 + i]) + xb[c * 64 + qi];
+                                sc[c] = dot * ivv[i] * qinv;
+                                best = fmaxf(best, sc[c]);                       // fmaxf drops NaN
+                            }
+                        }
+                    }
+                }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);
                 if (++as == 2) { as = 0; aph ^= 1u; }
-                mbar_wait(&xfull_bar[xs], xph);
-                const float* xb = xbuf + size_t(xs) * 64 * 64;
+                if (warp_live) {
+                    mbar_arrive(&xempty_bar[xs]);
+                    // ---- rows arrive in increasing order, so a later row never beats an equal score:
+                    //      only scores strictly above the threshold can enter
+                    if (__any_sync(kFull, best > st.thr_s)) {
+                        int c_start = 0;
+                        for (;;) {
+                            int ovf = 64;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    const uint32_t mw = (c < 32) ? m0 : m1;
-                    const float inv = __shfl_sync(kFull, (c < 32) ? in0 : in1, c & 31);
-                    if ((mw >> (c & 31)) & 1u) {                              // warp-uniform
-                        const float dot = __uint_as_float(d[c]) + xb[c * 64 + qi];
-                        const float s = dot * inv * qinv;
-                        const uint64_t key = make_key(s, uint32_t(r0 + c));
-                        const bool ins = (s == s) && key > st.thr && key < ubk;
-                        if (__any_sync(kFull, ins)) st = select_slow(st, ins, key, cand_warp, a.cap, a.k, lane);
+                            for (int c = 0; c < 64; ++c) {
+                                if (c >= c_start && sc[c] > st.thr_s) {
+                                    const uint64_t key = make_key(sc[c], uint32_t(r0 + c));
+                                    if (key < ubk) {
+                                        if (st.cnt < cap) mybuf[st.cnt++] = key;
+                                        else ovf = min(ovf, c);
+                                    }
+                                }
+                            }
+                            const unsigned full = __ballot_sync(kFull, st.cnt == cap);
+                            if (!full) break;
+                            st = select_compact(st, full, cand_warp, cap, a.k, lane);
+                            c_start = ovf;
+                            if (!__any_sync(kFull, ovf < 64)) break;
+                        }
                     }
+                } else {
+                    mbar_arrive(&xempty_bar[xs]);
                 }
-                mbar_arrive(&xempty_bar[xs]);
                 if (++xs == 2) { xs = 0; xph ^= 1u; }
             }
+            m = mn;
+        }
 
-            // ---- this CTA's sorted list per query
-            __syncwarp();
-            for (int L = 0; L < 32; ++L) {
-                const int qL = (quarter & 1) * 32 + L;
-                if (qL >= a.nq) break;
-                const int n = __shfl_sync(kFull, st.cnt, L);
-                uint64_t* b = cand_warp + size_t(L) * a.cap;
-                warp_rank_select(b, n, a.kp, lane);
-                uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
-                const int have = n < a.k ? n : a.k;
-                for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
-            }
+        // ---- this CTA's sorted list per query
+        __syncwarp();
+        for (int L = 0; L < 32; ++L) {
+            const int qL = (quarter & 1) * 32 + L;
+            if (qL >= a.nq) break;
+            const int n = __shfl_sync(kFull, st.cnt, L);
+            uint64_t* b = cand_warp + size_t(L) * a.cap;
+            warp_rank_select(b, n, a.kp, lane);
+            uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
+            const int have = n < a.k ? n : a.k;
+            for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
         }
     }
 
