@@ -21,6 +21,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -105,16 +106,16 @@ struct Workspace {
     EventSet ev;
     DevBuf<float> qraw, qpad, qinv, scores;
     DevBuf<__nv_bfloat16> qbf;
-    DevBuf<uint32_t> mask, pool, pool_bits;
+    DevBuf<uint32_t> mask, pool, pool_bits, gthr;
     DevBuf<uint64_t> part, ub;
     DevBuf<int64_t> rows;
     DevBuf<int32_t> counts;
     DevBuf<int> flags;              // [0] need_tail
-    DevBuf<unsigned long long> npass;
+    DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
-        mask.release(); pool.release(); pool_bits.release(); part.release(); ub.release();
-        rows.release(); counts.release(); flags.release(); npass.release();
+        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); ub.release();
+        rows.release(); counts.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -157,6 +158,7 @@ static size_t elem_size(int dtype) { return dtype == MRAG_BF16 ? 2 : 4; }
 static thread_local EventSet t_last_ev;          // borrowed handles (owned by a workspace / ring)
 static thread_local bool t_last_valid = false;
 static thread_local const char* t_last_kind = "none";
+static thread_local unsigned long long* t_stats_ptr = nullptr;
 static thread_local std::vector<EventSet> t_ring;
 static thread_local int t_ring_used = 0;
 static thread_local int t_ring_device = -1;
@@ -593,6 +595,20 @@ static int run_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t
     return MRAG_OK;
 }
 
+// Threshold sampling for large shards: scan every kSampleStride-th tile first, take the k-th best
+// score of that sample per query, and let the full scan admit only rows scoring at least that.
+// (k rows of the sample already reach the bound, so nothing below it can be in the top-k.)  It
+// cuts the candidates a CTA has to buffer from ~k ln(n/k) to ~k * kSampleStride / #CTAs.
+static const int kSampleStride = 64;
+static int64_t sample_min_tiles() {
+    // default: shards of >= 4M rows; MRAG_SAMPLE_MIN_TILES overrides it (tests exercise the path on small shards)
+    static const int64_t v = [] {
+        const char* e = getenv("MRAG_SAMPLE_MIN_TILES");
+        return (e && *e) ? std::max<int64_t>(1, atoll(e)) : int64_t(64) * 1024;
+    }();
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // search
 // ------------------------------------------------------------------------------------------
@@ -662,6 +678,32 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
             a.ub = (r > 0) ? w->ub.p : nullptr;
             a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid; a.cap = kr + kMmaSlack;
+            if (w->gthr.reserve(size_t(nq))) return MRAG_ERR_OOM;
+            CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
+            a.gthr = w->gthr.p;
+            a.tile_mul = 1;
+            a.stats = nullptr;
+            if (getenv("MRAG_SCAN_STATS")) {
+                if (w->stats.reserve(8)) return MRAG_ERR_OOM;
+                CU(cudaMemsetAsync(w->stats.p, 0, 64, s));
+                a.stats = w->stats.p;
+                t_stats_ptr = w->stats.p;
+            }
+            const int64_t tiles = ceil_div(n, kMmaTileRows);
+            if (tiles >= sample_min_tiles()) {
+                MmaArgs sa = a;
+                sa.stats = nullptr;
+                sa.tile_mul = kSampleStride;
+                const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, kSampleStride)));
+                sa.P = sgrid;
+                int rc = run_scan_mma(x, sa, nq, sgrid, s);
+                if (rc != MRAG_OK) return rc;
+                MergeArgs sm{};
+                sm.part = w->part.p; sm.P = sgrid; sm.kp = kp; sm.nq = nq; sm.k = kr; sm.k_total = k; sm.k_off = k_off;
+                sm.gthr_out = w->gthr.p;
+                merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
+                LAUNCHED();
+            }
             int rc = run_scan_mma(x, a, nq, grid, s);
             if (rc != MRAG_OK) return rc;
             t_last_kind = "mma";
@@ -861,6 +903,13 @@ extern "C" int mrag_profile_read(int what, float* out_ms, int max) {
     int n = 0;
     for (int i = 0; i < t_ring_used && n < max; ++i) out_ms[n++] = phase_ms(t_ring[size_t(i)], what);
     return n;
+}
+
+// debugging aid (not in mrag.h): counters of the last tensor-core scan on this thread, if the
+// environment variable MRAG_SCAN_STATS was set; the caller must have synchronised the search.
+extern "C" int mrag_debug_scan_stats(unsigned long long* out8) {
+    if (!t_stats_ptr || !out8) return MRAG_ERR_STATE;
+    return cudaMemcpy(out8, t_stats_ptr, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? MRAG_OK : MRAG_ERR_CUDA;
 }
 
 extern "C" int64_t mrag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

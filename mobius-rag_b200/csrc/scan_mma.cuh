@@ -51,10 +51,14 @@ struct MmaArgs {
     const float* qinv;       // [*] 1/|q| (+inf for a zero query)
     const uint64_t* ub;      // [*] exclusive upper-bound key per query, or nullptr
     uint64_t* part;          // [*][P][kp] per-CTA sorted candidate lists
+    uint32_t* gthr;          // [*] orderable(score) of the best k-th score any CTA has proven so far (0 = none)
     int q0, nq;              // queries [q0, q0+nq) handled by this launch (nq <= 64)
     int k, kp, P;
     int cap;                 // candidate buffer capacity per query (k + kMmaSlack)
     int stages;              // TMA ring depth
+    unsigned long long* stats;   // optional counters: [0] tiles, [1] tiles with a candidate, [2] keys appended,
+                                 // [3] compactions, [4] overflow retries  (summed over hi warps / lanes)
+    int tile_mul;            // 1: every 64-row tile; m > 1: only tiles 0, m, 2m, ... (threshold sampling pass)
 };
 
 inline size_t mma_smem_bytes(int stages, int cap) {
@@ -93,6 +97,17 @@ MRAG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > kSpinCycles) __trap();
     }
+}
+// one lane of a CONVERGED warp (the compiler then knows the guarded block runs on a single lane and
+// emits the uniform-datapath tcgen05 / TMA instructions without per-instruction election loops)
+MRAG_DEVINL bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 MRAG_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 MRAG_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -255,9 +270,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kblocks = a.ld / kMmaKBlock;
-    const int64_t num_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
+    const int64_t all_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
     const int64_t nwords = (a.n + 31) >> 5;
-    const int64_t G = gridDim.x;
+    // tile index space of this launch: t = 0, tile_mul, 2*tile_mul, ...; CTA b takes every gridDim-th of them
+    const int64_t tmul = a.tile_mul;
+    const int64_t num_tiles = all_tiles;
+    const int64_t G = int64_t(gridDim.x) * tmul;
+    const int64_t t_first = int64_t(blockIdx.x) * tmul;
 
     // 64 mask bits of tile t (zero past the end); every role skips a tile whose bits are all clear
     auto tile_mask = [&](int64_t t) -> uint2 {
@@ -319,63 +338,66 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     tc_fence_after();
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            uint2 m = tile_mask(blockIdx.x);
-            for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
-                const uint2 mn = tile_mask(t + G);              // next tile's bits, off the critical path
-                if ((m.x | m.y) != 0u) {
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&empty_bar[s], ph ^ 1u);
+        // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        int s = 0;
+        uint32_t ph = 0;
+        uint2 m = tile_mask(t_first);
+        for (int64_t t = t_first; t < num_tiles; t += G) {
+            const uint2 mn = tile_mask(t + G);                  // next tile's bits, off the critical path
+            if ((m.x | m.y) != 0u) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], kMmaStageBytes);
                         tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
                                     &full_bar[s]);
-                        if (++s == a.stages) { s = 0; ph ^= 1u; }
                     }
+                    __syncwarp();
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
                 }
-                m = mn;
             }
+            m = mn;
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            int s = 0, as = 0;
-            uint32_t ph = 0, aph = 0;
-            uint2 m = tile_mask(blockIdx.x);
-            for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
-                const uint2 mn = tile_mask(t + G);
-                if ((m.x | m.y) != 0u) {
-                    mbar_wait(&tempty_bar[as], aph ^ 1u);
+        // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
+        uint2 m = tile_mask(t_first);
+        for (int64_t t = t_first; t < num_tiles; t += G) {
+            const uint2 mn = tile_mask(t + G);
+            if ((m.x | m.y) != 0u) {
+                mbar_wait(&tempty_bar[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_sw128_desc(smem_u32(stage_base + size_t(s) * kMmaStageBytes));
-#pragma unroll
-                        for (int j = 0; j < kMmaKBlock / 16; ++j) {
-                            // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
-                            umma_ts_bf16(d_tmem, tmem_base + uint32_t(kb * (kMmaKBlock / 2) + j * 8), bdesc + uint64_t(j * 2),
-                                         kMmaIdesc, (kb | j) != 0 ? 1u : 0u);
-                        }
+                    if (elect_one()) {
+                        const uint64_t bdesc = bdesc0 + uint64_t(s) * (kMmaStageBytes >> 4);
+                        const uint32_t a_tmem = tmem_base + uint32_t(kb * (kMmaKBlock / 2));
+                        // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
+                        umma_ts_bf16(d_tmem, a_tmem, bdesc, kMmaIdesc, kb != 0 ? 1u : 0u);
+                        umma_ts_bf16(d_tmem, a_tmem + 8, bdesc + 2, kMmaIdesc, 1u);
+                        umma_ts_bf16(d_tmem, a_tmem + 16, bdesc + 4, kMmaIdesc, 1u);
+                        umma_ts_bf16(d_tmem, a_tmem + 24, bdesc + 6, kMmaIdesc, 1u);
                         umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
-                        if (++s == a.stages) { s = 0; ph ^= 1u; }
+                        if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);   // accumulator ready
                     }
-                    umma_commit(&tfull_bar[as]);                // accumulator ready
-                    if (++as == 2) { as = 0; aph ^= 1u; }
+                    __syncwarp();
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
                 }
-                m = mn;
+                if (++as == 2) { as = 0; aph ^= 1u; }
             }
+            m = mn;
         }
     } else if (!hi_part) {
         // ================= lo epilogue (warps 4,5): TMEM lanes 0..63 -> exchange buffer =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         int as = 0, xs = 0;
         uint32_t aph = 0, xph = 0;
-        uint2 m = tile_mask(blockIdx.x);
-        for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+        uint2 m = tile_mask(t_first);
+        for (int64_t t = t_first; t < num_tiles; t += G) {
             const uint2 mn = tile_mask(t + G);
             if ((m.x | m.y) != 0u) {
                 // warp 4 also publishes 1/|x| of the tile's rows (NaN for a masked row: the mask is
@@ -423,14 +445,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         st.cnt = 0;
         // a thread without a query, or with a zero-norm query (every similarity NaN), admits nothing
         st.thr_s = (live && !isinf(qinv)) ? -CUDART_INF_F : CUDART_INF_F;
+        // Cross-CTA bound: once ANY CTA holds k keys with score >= g, a row scoring below g cannot be
+        // in the global top-k.  Rows scoring exactly g may still win a tie by row index, so the bound
+        // admits s >= g, i.e. s > prev(g).  Read relaxed once per tile, raised after each compaction.
+        uint32_t* gslot = a.gthr + a.q0 + (live ? qi : 0);
+        unsigned long long n_tiles = 0, n_slow = 0, n_keys = 0, n_compact = 0, n_retry = 0;
 
-        uint2 m = tile_mask(blockIdx.x);
-        for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+        uint2 m = tile_mask(t_first);
+        for (int64_t t = t_first; t < num_tiles; t += G) {
             const uint2 mn = tile_mask(t + G);
             if ((m.x | m.y) != 0u) {
                 const int64_t r0 = t * kMmaTileRows;
                 float sc[64];
                 float best = -CUDART_INF_F;
+                uint32_t gord;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gord) : "l"(gslot) : "memory");
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 mbar_wait(&xfull_bar[xs], xph);
@@ -465,13 +494,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                     mbar_arrive(&xempty_bar[xs]);
                     // ---- rows arrive in increasing order, so a later row never beats an equal score:
                     //      only scores strictly above the threshold can enter
-                    if (__any_sync(kFull, best > st.thr_s)) {
+                    float thr = fmaxf(st.thr_s, gord ? ord2f(gord - 1u) : -CUDART_INF_F);
+                    ++n_tiles;
+                    if (__any_sync(kFull, best > thr)) {
+                        ++n_slow;
+                        const int cnt_before = st.cnt;
                         int c_start = 0;
                         for (;;) {
                             int ovf = 64;
 #pragma unroll
                             for (int c = 0; c < 64; ++c) {
-                                if (c >= c_start && sc[c] > st.thr_s) {
+                                if (c >= c_start && sc[c] > thr) {
                                     const uint64_t key = make_key(sc[c], uint32_t(r0 + c));
                                     if (key < ubk) {
                                         if (st.cnt < cap) mybuf[st.cnt++] = key;
@@ -480,8 +513,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                                 }
                             }
                             const unsigned full = __ballot_sync(kFull, st.cnt == cap);
-                            if (!full) break;
+                            if (!full) { n_keys += st.cnt - cnt_before; break; }
+                            n_compact += (full >> lane) & 1u;
+                            ++n_retry;
                             st = select_compact(st, full, cand_warp, cap, a.k, lane);
+                            if ((full >> lane) & 1u) atomicMax(gslot, f2ord(st.thr_s));
+                            thr = fmaxf(thr, st.thr_s);
                             c_start = ovf;
                             if (!__any_sync(kFull, ovf < 64)) break;
                         }
@@ -494,6 +531,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             m = mn;
         }
 
+        if (a.stats) {
+            if (lane == 0) { atomicAdd(a.stats + 0, n_tiles); atomicAdd(a.stats + 1, n_slow); atomicAdd(a.stats + 4, n_retry); }
+            if (n_keys) atomicAdd(a.stats + 2, n_keys);
+            if (n_compact) atomicAdd(a.stats + 3, n_compact);
+        }
         // ---- this CTA's sorted list per query
         __syncwarp();
         for (int L = 0; L < 32; ++L) {

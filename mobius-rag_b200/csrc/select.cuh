@@ -25,6 +25,8 @@ struct MergeArgs {
     int64_t row_base;
     uint64_t* ub_out;       // [nq] last key of this round (next round's exclusive bound), may be null
     int* need_tail;         // set to 1 if some query is still short of k_total after this round
+    uint32_t* gthr_out;     // if set: ONLY write orderable(score of the k-th best) per query (0 if fewer
+                            // than k candidates) -- the admission bound the sampling pass hands to the scan
 };
 
 // One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
@@ -74,6 +76,10 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     __syncthreads();
     block_sort_desc(s, n2);
     const int got = kept < a.k ? kept : a.k;
+    if (a.gthr_out) {
+        if (tid == 0) a.gthr_out[q] = (got == a.k) ? uint32_t(s[a.k - 1] >> 32) : 0u;
+        return;
+    }
     // round 0 starts at slot 0 and pads the whole row; later rounds continue at counts[q]
     const int prev = (a.k_off == 0) ? 0 : a.counts[q];
     __syncthreads();

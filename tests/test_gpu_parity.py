@@ -514,3 +514,40 @@ def test_mma_with_filters_ties_and_nan(oracle):
     s, r, c = idx.search(Q[:1], 50, options=N.OPT_FORCE_MMA)
     assert r[0].tolist() == dup[:50].tolist() or r[0, :50].tolist() == sorted(r[0, :50].tolist())
     idx.close()
+
+
+def test_mma_threshold_sampling_pass(oracle):
+    """Large shards first scan every 64th tile to get an admission bound per query; run it on a small
+    shard (MRAG_SAMPLE_MIN_TILES=1 in a child process) incl. duplicates that tie exactly at the bound."""
+    import subprocess, sys, textwrap, os
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        import mrag_b200
+        from mrag_b200 import synth, _native as N
+        from mrag_b200.index import Index, make_meta, Filter
+        from oracle import oracle
+        n, dim = 150000, 128
+        X, valid = synth.make_corpus(n, dim, seed=77, null_frac=1e-3)
+        dup = np.arange(0, n, 64 * 64)[:40] + 3          # duplicates sitting exactly in sampled tiles
+        X[dup] = X[dup[0]]; valid[dup] = 1
+        Q = synth.make_queries(X, 70, seed=78)
+        Q[0] = X[dup[0]]
+        idx = Index(dim, "bf16", 0, n)
+        idx.append(X, make_meta(n, valid=valid))
+        Xs = oracle.round_bf16(X)
+        for k in (10, 100, 200):
+            s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA)
+            for i in range(Q.shape[0]):
+                oracle.check_topk(r[i], s[i], int(c[i]), oracle.all_similarities(Xs, Q[i]), valid.astype(bool), k, rtol=1e-2)
+        # a filter that empties most sampled tiles: the bound may be absent for some queries
+        flt = Filter().doc_pool(list(range(0, n, 997)))
+        s, r, c = idx.search(Q[:5], 10, flt, options=N.OPT_FORCE_MMA)
+        mask = valid.astype(bool) & np.isin(np.arange(n), np.arange(0, n, 997))
+        for i in range(5):
+            oracle.check_topk(r[i], s[i], int(c[i]), oracle.all_similarities(Xs, Q[i]), mask, 10, rtol=1e-2)
+        print("SAMPLING-OK")
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MRAG_SAMPLE_MIN_TILES="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "SAMPLING-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
