@@ -576,37 +576,48 @@ static int mma_stages_for(int cap) {
     return int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
 }
 
-static int run_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
+template <int KREG>
+static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(scan_mma_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
+    if (KREG > 0) a.cap = 0;                   // candidates live in registers: no shared-memory buffers
     a.stages = mma_stages_for(a.cap);
     const size_t smem = mma_smem_bytes(a.stages, a.cap);
     for (int q0 = 0; q0 < nq; q0 += kMmaQueries) {
         a.q0 = q0;
         a.nq = std::min(kMmaQueries, nq - q0);
-        scan_mma_kernel<<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        scan_mma_kernel<KREG><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
         LAUNCHED();
     }
     return MRAG_OK;
 }
 
-// Threshold sampling for large shards: scan every kSampleStride-th tile first, take the k-th best
+// reg_topk: keep each query's top-k in registers (k <= 16).  It wins whenever most rows a CTA sees
+// are still candidates (short streams: small shards and the sampling pass), because all 32 queries
+// of a warp insert in lock step; on long streams the shared-memory buffers + a sampled bound win.
+static int run_scan_mma(mrag_index* x, const MmaArgs& a, int nq, int grid, bool reg_topk, cudaStream_t s) {
+    return (reg_topk && a.k <= kMmaRegK) ? launch_scan_mma<kMmaRegK>(x, a, nq, grid, s)
+                                         : launch_scan_mma<0>(x, a, nq, grid, s);
+}
+
+// Threshold sampling for large shards: scan a strided sample of the tiles first, take the k-th best
 // score of that sample per query, and let the full scan admit only rows scoring at least that.
-// (k rows of the sample already reach the bound, so nothing below it can be in the top-k.)  It
-// cuts the candidates a CTA has to buffer from ~k ln(n/k) to ~k * kSampleStride / #CTAs.
-static const int kSampleStride = 64;
-static int64_t sample_min_tiles() {
-    // default: shards of >= 4M rows; MRAG_SAMPLE_MIN_TILES overrides it (tests exercise the path on small shards)
-    static const int64_t v = [] {
+// (k rows of the sample already reach the bound, so nothing below it can be in the top-k.)  It cuts
+// the candidates a CTA buffers from ~k ln(n/k), most of them in a costly warm-up, to ~k * stride / #CTAs.
+//   k <= 16: two tiles per CTA with the register top-k kernel (about 1/500 of a 10M-row shard)
+//   k  > 16: every 64th tile with the buffer kernel
+static int64_t sample_min_tiles(int num_sms) {
+    // default: shards of >= 64 tiles per SM (~600k rows); MRAG_SAMPLE_MIN_TILES overrides (tests)
+    static const int64_t env = [] {
         const char* e = getenv("MRAG_SAMPLE_MIN_TILES");
-        return (e && *e) ? std::max<int64_t>(1, atoll(e)) : int64_t(64) * 1024;
+        return (e && *e) ? std::max<int64_t>(1, atoll(e)) : int64_t(0);
     }();
-    return v;
+    return env ? env : int64_t(64) * num_sms;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -690,13 +701,15 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 t_stats_ptr = w->stats.p;
             }
             const int64_t tiles = ceil_div(n, kMmaTileRows);
-            if (tiles >= sample_min_tiles()) {
+            const bool sampled = tiles >= sample_min_tiles(x->num_sms);
+            if (sampled) {
                 MmaArgs sa = a;
                 sa.stats = nullptr;
-                sa.tile_mul = kSampleStride;
-                const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, kSampleStride)));
+                const bool reg = kr <= kMmaRegK;
+                sa.tile_mul = reg ? int(std::max<int64_t>(1, tiles / (2 * int64_t(x->num_sms)))) : 64;
+                const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
                 sa.P = sgrid;
-                int rc = run_scan_mma(x, sa, nq, sgrid, s);
+                int rc = run_scan_mma(x, sa, nq, sgrid, reg, s);
                 if (rc != MRAG_OK) return rc;
                 MergeArgs sm{};
                 sm.part = w->part.p; sm.P = sgrid; sm.kp = kp; sm.nq = nq; sm.k = kr; sm.k_total = k; sm.k_off = k_off;
@@ -704,7 +717,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
                 LAUNCHED();
             }
-            int rc = run_scan_mma(x, a, nq, grid, s);
+            int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!sampled, s);
             if (rc != MRAG_OK) return rc;
             t_last_kind = "mma";
         } else if (n > 0) {

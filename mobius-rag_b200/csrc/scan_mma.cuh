@@ -251,6 +251,14 @@ __device__ __noinline__ SelState select_compact(SelState st, unsigned full, uint
 }
 
 // ----------------------------------------------------------------------------------------------
+// KREG = 0: candidates go to per-query shared-memory buffers of k + 64 keys, compacted when full
+//           (k up to 128; large shards get their admission bound from a sampling pass first).
+// KREG > 0: k <= KREG; every thread keeps the sorted top-KREG keys of its query in REGISTERS
+//           (branch-free insertion), so its threshold is always the exact k-th best so far:
+//           ~k ln(n/k) insertions per query and CTA, no buffers, no compaction, no sampling pass.
+constexpr int kMmaRegK = 16;
+
+template <int KREG>
 __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     // SWIZZLE_128B tiles need 1024-byte alignment; stay in the shared address space (no integer casts)
@@ -445,6 +453,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         st.cnt = 0;
         // a thread without a query, or with a zero-norm query (every similarity NaN), admits nothing
         st.thr_s = (live && !isinf(qinv)) ? -CUDART_INF_F : CUDART_INF_F;
+        // register-resident sorted top-k (KREG mode): the k live slots are the LAST k of top[], the
+        // slots before them hold an unbeatable sentinel, so the k-th best is always top[KREG-1]
+        // (every index stays a compile-time constant: the array must not fall into local memory)
+        uint64_t top[KREG > 0 ? KREG : 1];
+        const int top_off = (KREG > 0 ? KREG : 1) - a.k;
+#pragma unroll
+        for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = (i < top_off) ? ~0ull : 0ull;
         // Cross-CTA bound: once ANY CTA holds k keys with score >= g, a row scoring below g cannot be
         // in the global top-k.  Rows scoring exactly g may still win a tie by row index, so the bound
         // admits s >= g, i.e. s > prev(g).  Read relaxed once per tile, raised after each compaction.
@@ -498,6 +513,35 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                     ++n_tiles;
                     if (__any_sync(kFull, best > thr)) {
                         ++n_slow;
+                        if constexpr (KREG > 0) {
+                            const float thr_in = st.thr_s;
+#pragma unroll
+                            for (int c = 0; c < 64; ++c) {
+                                const bool ins = sc[c] > thr;
+                                if (__any_sync(kFull, ins)) {                    // warp-uniform
+                                    uint64_t key = 0ull;
+                                    if (ins) {
+                                        key = make_key(sc[c], uint32_t(r0 + c));
+                                        if (key >= ubk) key = 0ull;
+                                    }
+                                    n_keys += key != 0ull;
+                                    // sorted insertion into top[] (descending); a zero key falls through
+#pragma unroll
+                                    for (int i = 0; i < KREG; ++i) {
+                                        const bool gt = key > top[i];
+                                        const uint64_t lower = gt ? top[i] : key;
+                                        top[i] = gt ? key : top[i];
+                                        key = lower;
+                                    }
+                                    const uint64_t kth = top[KREG - 1];
+                                    if (kth) {                                   // k keys held: exact k-th best so far
+                                        st.thr_s = key_score(kth);
+                                        thr = fmaxf(thr, st.thr_s);
+                                    }
+                                }
+                            }
+                            if (st.thr_s > thr_in) atomicMax(gslot, f2ord(st.thr_s));
+                        } else {
                         const int cnt_before = st.cnt;
                         int c_start = 0;
                         for (;;) {
@@ -522,6 +566,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                             c_start = ovf;
                             if (!__any_sync(kFull, ovf < 64)) break;
                         }
+                        }
                     }
                 } else {
                     mbar_arrive(&xempty_bar[xs]);
@@ -538,15 +583,25 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         }
         // ---- this CTA's sorted list per query
         __syncwarp();
-        for (int L = 0; L < 32; ++L) {
-            const int qL = (quarter & 1) * 32 + L;
-            if (qL >= a.nq) break;
-            const int n = __shfl_sync(kFull, st.cnt, L);
-            uint64_t* b = cand_warp + size_t(L) * a.cap;
-            warp_rank_select(b, n, a.kp, lane);
-            uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
-            const int have = n < a.k ? n : a.k;
-            for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
+        if constexpr (KREG > 0) {
+            if (live) {
+                uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
+#pragma unroll
+                for (int i = 0; i < KREG; ++i)
+                    if (i >= top_off) out[i - top_off] = top[i];
+                for (int i = a.k; i < a.kp; ++i) out[i] = 0ull;
+            }
+        } else {
+            for (int L = 0; L < 32; ++L) {
+                const int qL = (quarter & 1) * 32 + L;
+                if (qL >= a.nq) break;
+                const int n = __shfl_sync(kFull, st.cnt, L);
+                uint64_t* b = cand_warp + size_t(L) * a.cap;
+                warp_rank_select(b, n, a.kp, lane);
+                uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
+                const int have = n < a.k ? n : a.k;
+                for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
+            }
         }
     }
 
