@@ -72,7 +72,10 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and _build.nvcc_path() is not None:
+    override = os.environ.get("MRAG_LIB")          # A/B experiments: load exactly this build
+    if override:
+        _build.LIB = override
+    elif build_if_missing and _build.nvcc_path() is not None:
         _build.build_lib()
     if not os.path.exists(_build.LIB):
         raise ImportError(

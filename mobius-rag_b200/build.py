@@ -45,7 +45,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libmrag.so (there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MRAG_NVCC_EXTRA", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     tmp = LIB + ".tmp"

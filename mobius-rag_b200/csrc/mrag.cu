@@ -107,14 +107,14 @@ struct Workspace {
     DevBuf<float> qraw, qpad, qinv, scores;
     DevBuf<__nv_bfloat16> qbf;
     DevBuf<uint32_t> mask, pool, pool_bits, gthr;
-    DevBuf<uint64_t> part, ub;
+    DevBuf<uint64_t> part, part2, ub;
     DevBuf<int64_t> rows;
     DevBuf<int32_t> counts;
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
-        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); ub.release();
+        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); ub.release();
         rows.release(); counts.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -611,6 +611,14 @@ static int run_scan_mma(mrag_index* x, const MmaArgs& a, int nq, int grid, bool 
 // the candidates a CTA buffers from ~k ln(n/k), most of them in a costly warm-up, to ~k * stride / #CTAs.
 //   k <= 16: two tiles per CTA with the register top-k kernel (about 1/500 of a 10M-row shard)
 //   k  > 16: every 64th tile with the buffer kernel
+static uint32_t mma_sleep_ns() {
+    static const uint32_t v = [] {
+        const char* e = getenv("MRAG_MMA_SLEEP_NS");
+        return (e && *e) ? uint32_t(strtoul(e, nullptr, 10)) : 0x989680u;
+    }();
+    return v;
+}
+
 static int64_t sample_min_tiles(int num_sms) {
     // default: shards of >= 64 tiles per SM (~600k rows); MRAG_SAMPLE_MIN_TILES overrides (tests)
     static const int64_t env = [] {
@@ -683,7 +691,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         const int k_off = r * MRAG_FUSED_K;
         const int kr = std::min(MRAG_FUSED_K, k - k_off);
         const int kp = std::max(8, host_next_pow2(kr));
-        if (w->part.reserve(size_t(nq) * grid * kp)) return MRAG_ERR_OOM;
+        if (w->part.reserve(size_t(nq) * grid * std::max(kp, kMmaRegK))) return MRAG_ERR_OOM;
         if (n > 0 && use_mma) {
             MmaArgs a{};
             a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
@@ -694,25 +702,37 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             a.gthr = w->gthr.p;
             a.tile_mul = 1;
             a.stats = nullptr;
+            a.tstamps = nullptr;
+            a.sleep_ns = mma_sleep_ns();
+            unsigned long long* ts_sample = nullptr;
             if (getenv("MRAG_SCAN_STATS")) {
-                if (w->stats.reserve(8)) return MRAG_ERR_OOM;
-                CU(cudaMemsetAsync(w->stats.p, 0, 64, s));
+                // [0..8) counters, [8..24) stamps of the sampling launch, [24..40) stamps of the main launch
+                if (w->stats.reserve(40)) return MRAG_ERR_OOM;
+                CU(cudaMemsetAsync(w->stats.p, 0, 40 * 8, s));
                 a.stats = w->stats.p;
+                a.tstamps = w->stats.p + 24;
+                ts_sample = w->stats.p + 8;
                 t_stats_ptr = w->stats.p;
             }
             const int64_t tiles = ceil_div(n, kMmaTileRows);
             const bool sampled = tiles >= sample_min_tiles(x->num_sms);
             if (sampled) {
+                // always the register top-k kernel: each CTA keeps the 16 best of a few tiles per query and
+                // the merge takes the k-th best of the union (k known rows reach it, so it is a valid bound;
+                // a CTA holds 1/#CTAs of the sample, so its top 16 almost never truncate the sample's top k)
                 MmaArgs sa = a;
                 sa.stats = nullptr;
-                const bool reg = kr <= kMmaRegK;
-                sa.tile_mul = reg ? int(std::max<int64_t>(1, tiles / (2 * int64_t(x->num_sms)))) : 64;
+                sa.tstamps = ts_sample;
+                const int per_cta = kr <= kMmaRegK ? 2 : (kr <= 64 ? 4 : 8);
+                sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
                 const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
                 sa.P = sgrid;
-                int rc = run_scan_mma(x, sa, nq, sgrid, reg, s);
+                sa.k = std::min(kr, kMmaRegK);
+                sa.kp = kMmaRegK;
+                int rc = run_scan_mma(x, sa, nq, sgrid, /*reg_topk=*/true, s);
                 if (rc != MRAG_OK) return rc;
                 MergeArgs sm{};
-                sm.part = w->part.p; sm.P = sgrid; sm.kp = kp; sm.nq = nq; sm.k = kr; sm.k_total = k; sm.k_off = k_off;
+                sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kr; sm.lk = sa.k; sm.k_total = k; sm.k_off = k_off;
                 sm.gthr_out = w->gthr.p;
                 merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
                 LAUNCHED();
@@ -734,6 +754,18 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (r == rounds - 1) CU(cudaEventRecord(ev.e[2], s));
         MergeArgs m{};
         m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = kr; m.k_total = k; m.k_off = k_off;
+        if (int64_t(grid) * kp > kMergeSlots / 2) {
+            // two levels: (query, group of <= 2048 / kp lists) blocks first -- one sort of <= 2048 keys each,
+            // many blocks in flight -- then one block per query over the group lists
+            MergeArgs m1 = m;
+            m1.Pg = std::max(2, (kMergeSlots / 2) / kp);
+            const int groups = int(ceil_div(grid, m1.Pg));
+            if (w->part2.reserve(size_t(nq) * groups * kp)) return MRAG_ERR_OOM;
+            m1.part_out = w->part2.p;
+            merge_kernel<<<dim3(unsigned(nq), unsigned(groups)), kMergeThreads, 0, s>>>(m1);
+            LAUNCHED();
+            m.part = w->part2.p; m.P = groups;
+        }
         m.scores = d_scores; m.rows = d_rows; m.counts = d_counts; m.row_base = x->row_base;
         m.ub_out = (rounds > 1) ? w->ub.p : nullptr;
         m.need_tail = w->flags.p;
@@ -920,9 +952,9 @@ extern "C" int mrag_profile_read(int what, float* out_ms, int max) {
 
 // debugging aid (not in mrag.h): counters of the last tensor-core scan on this thread, if the
 // environment variable MRAG_SCAN_STATS was set; the caller must have synchronised the search.
-extern "C" int mrag_debug_scan_stats(unsigned long long* out8) {
-    if (!t_stats_ptr || !out8) return MRAG_ERR_STATE;
-    return cudaMemcpy(out8, t_stats_ptr, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? MRAG_OK : MRAG_ERR_CUDA;
+extern "C" int mrag_debug_scan_stats(unsigned long long* out40) {
+    if (!t_stats_ptr || !out40) return MRAG_ERR_STATE;
+    return cudaMemcpy(out40, t_stats_ptr, 40 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? MRAG_OK : MRAG_ERR_CUDA;
 }
 
 extern "C" int64_t mrag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -31,6 +31,14 @@
 
 namespace mrag {
 
+#ifndef MRAG_SLEEP_REG
+#define MRAG_SLEEP_REG 1
+#endif
+#ifndef MRAG_STAMPS
+// %globaltimer stamps of CTA 0's phases (tools/stats_probe.py).  OFF in the shipped build: merely
+// compiling the (never taken) stamp branches in costs the hot loop 2.3x (measured, r1f A/B run).
+#define MRAG_STAMPS 0
+#endif
 constexpr int kMmaThreads = 192;
 constexpr int kMmaTileRows = 64;          // UMMA N
 constexpr int kMmaKBlock = 64;            // bf16 elements per smem row = 128 B = one swizzle span
@@ -59,6 +67,8 @@ struct MmaArgs {
     unsigned long long* stats;   // optional counters: [0] tiles, [1] tiles with a candidate, [2] keys appended,
                                  // [3] compactions, [4] overflow retries  (summed over hi warps / lanes)
     int tile_mul;            // 1: every 64-row tile; m > 1: only tiles 0, m, 2m, ... (threshold sampling pass)
+    uint32_t sleep_ns;       // suspend-time hint of the barrier waits
+    unsigned long long* tstamps;   // optional [16] %globaltimer stamps of CTA 0 (debugging aid)
 };
 
 inline size_t mma_smem_bytes(int stages, int cap) {
@@ -80,23 +90,32 @@ MRAG_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
-MRAG_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+MRAG_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep, do not spin
+#if MRAG_SLEEP_REG
+        : "r"(smem_u32(bar)), "r"(parity), "r"(sleep_ns)      // suspend-time hint: sleep, do not spin
+#else
+        : "r"(smem_u32(bar)), "r"(parity), "n"(0x989680)
+#endif
         : "memory");
     return ok != 0;
 }
-MRAG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+MRAG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 0x989680u) {
+    if (mbar_try_wait(bar, parity, sleep_ns)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity, sleep_ns)) {
         if (clock64() - t0 > kSpinCycles) __trap();
     }
+}
+MRAG_DEVINL unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 // one lane of a CONVERGED warp (the compiler then knows the guarded block runs on a single lane and
 // emits the uniform-datapath tcgen05 / TMA instructions without per-instruction election loops)
@@ -277,6 +296,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xempty_bar + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t slp = a.sleep_ns;
+#if MRAG_STAMPS
+    auto stamp = [&](int i) { if (a.tstamps && blockIdx.x == 0 && lane == 0) a.tstamps[i] = globaltimer_ns(); };
+#else
+    auto stamp = [&](int) {};
+#endif
+    if (tid == 0) stamp(0);
     const int kblocks = a.ld / kMmaKBlock;
     const int64_t all_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
     const int64_t nwords = (a.n + 31) >> 5;
@@ -312,6 +338,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (tid == 0) stamp(1);
 
     // epilogue geometry: TMEM lanes [32*quarter, +32); quarters 2,3 hold the hi halves
     const int quarter = warp & 3;
@@ -344,6 +371,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) stamp(2);
 
     if (warp == 0) {
         // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             const uint2 mn = tile_mask(t + G);                  // next tile's bits, off the critical path
             if ((m.x | m.y) != 0u) {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_wait(&empty_bar[s], ph ^ 1u, slp);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], kMmaStageBytes);
                         tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
@@ -366,6 +394,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             }
             m = mn;
         }
+        stamp(3);
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
         int s = 0, as = 0;
@@ -375,11 +404,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         for (int64_t t = t_first; t < num_tiles; t += G) {
             const uint2 mn = tile_mask(t + G);
             if ((m.x | m.y) != 0u) {
-                mbar_wait(&tempty_bar[as], aph ^ 1u);
+                mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait(&full_bar[s], ph, slp);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t bdesc = bdesc0 + uint64_t(s) * (kMmaStageBytes >> 4);
@@ -399,6 +428,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             }
             m = mn;
         }
+        stamp(4);
     } else if (!hi_part) {
         // ================= lo epilogue (warps 4,5): TMEM lanes 0..63 -> exchange buffer =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
@@ -417,14 +447,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                     if ((m.y >> lane) & 1u) in1 = __ldg(a.inv_norm + r0 + 32 + lane);
                 }
                 uint32_t d[64];
-                mbar_wait(&tfull_bar[as], aph);
+                mbar_wait(&tfull_bar[as], aph, slp);
                 tc_fence_after();
                 MRAG_TMEM_LD64(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);
                 if (++as == 2) { as = 0; aph ^= 1u; }
-                mbar_wait(&xempty_bar[xs], xph ^ 1u);
+                mbar_wait(&xempty_bar[xs], xph ^ 1u, slp);
                 float* xb = xbuf + size_t(xs) * 64 * 64;
 #pragma unroll
                 for (int c = 0; c < 64; ++c) xb[c * 64 + qi] = __uint_as_float(d[c]);
@@ -437,6 +467,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             }
             m = mn;
         }
+        if (warp == 4) stamp(5);
     } else {
         // ================= hi epilogue (warps 2,3): score + per-thread top-k =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
@@ -475,9 +506,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 float best = -CUDART_INF_F;
                 uint32_t gord;
                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gord) : "l"(gslot) : "memory");
-                mbar_wait(&tfull_bar[as], aph);
+                mbar_wait(&tfull_bar[as], aph, slp);
                 tc_fence_after();
-                mbar_wait(&xfull_bar[xs], xph);
+                mbar_wait(&xfull_bar[xs], xph, slp);
                 if (warp_live) {
                     const float* xb = xbuf + size_t(xs) * 64 * 64;
                     const float4* inv4 = reinterpret_cast<const float4*>(xinv + xs * 64);
@@ -576,6 +607,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             m = mn;
         }
 
+        if (warp == 2) stamp(6);
         if (a.stats) {
             if (lane == 0) { atomicAdd(a.stats + 0, n_tiles); atomicAdd(a.stats + 1, n_slow); atomicAdd(a.stats + 4, n_retry); }
             if (n_keys) atomicAdd(a.stats + 2, n_keys);
@@ -605,8 +637,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         }
     }
 
+    if (warp == 2) stamp(7);
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) stamp(8);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kMmaTmemCols);

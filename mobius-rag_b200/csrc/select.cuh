@@ -17,6 +17,8 @@ struct MergeArgs {
     int P, kp;
     int nq;
     int k;                  // results wanted from this round (<= MRAG_FUSED_K)
+    int lk;                 // keys a producer list holds at most; 0 means k.  With lk < k (sampling pass
+                            // that keeps only each CTA's top 16) no per-list prefilter bound exists.
     int k_total;            // row pitch of the outputs
     int k_off;              // first output slot of this round
     float* scores;          // [nq][k_total]
@@ -27,6 +29,10 @@ struct MergeArgs {
     int* need_tail;         // set to 1 if some query is still short of k_total after this round
     uint32_t* gthr_out;     // if set: ONLY write orderable(score of the k-th best) per query (0 if fewer
                             // than k candidates) -- the admission bound the sampling pass hands to the scan
+    // first level of a two-level merge (wide producer sets x large k): gridDim.y groups of `Pg` lists
+    // each; block (q, g) writes the sorted top-k keys of its group to part_out[q][g][kp] and nothing else
+    uint64_t* part_out;
+    int Pg;
 };
 
 // One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
@@ -36,18 +42,22 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     __shared__ unsigned long long s_T;
     __shared__ int s_cnt;
     const int q = blockIdx.x, tid = threadIdx.x;
-    const uint64_t* base = a.part + size_t(q) * a.P * a.kp;
+    const int p_lo = a.part_out ? int(blockIdx.y) * a.Pg : 0;
+    const int P = a.part_out ? min(a.Pg, a.P - p_lo) : a.P;
+    const uint64_t* base = a.part + (size_t(q) * a.P + p_lo) * a.kp;
     if (tid == 0) { s_T = 0ull; s_cnt = 0; }
     __syncthreads();
     uint64_t t = 0;
-    for (int p = tid; p < a.P; p += kMergeThreads) {
-        uint64_t v = base[size_t(p) * a.kp + (a.k - 1)];
-        t = v > t ? v : t;
+    if (a.lk == 0 || a.lk >= a.k) {
+        for (int p = tid; p < P; p += kMergeThreads) {
+            uint64_t v = base[size_t(p) * a.kp + (a.k - 1)];
+            t = v > t ? v : t;
+        }
     }
     if (t) atomicMax(&s_T, (unsigned long long)t);
     __syncthreads();
     const uint64_t T = s_T;
-    const int total = a.P * a.kp;
+    const int total = P * a.kp;
     int done = 0;
     while (done < total) {
         int kept = s_cnt;                       // uniform: read between two barriers
@@ -76,6 +86,11 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     __syncthreads();
     block_sort_desc(s, n2);
     const int got = kept < a.k ? kept : a.k;
+    if (a.part_out) {
+        uint64_t* out = a.part_out + (size_t(q) * gridDim.y + blockIdx.y) * a.kp;
+        for (int i = tid; i < a.kp; i += kMergeThreads) out[i] = (i < got) ? s[i] : 0ull;
+        return;
+    }
     if (a.gthr_out) {
         if (tid == 0) a.gthr_out[q] = (got == a.k) ? uint32_t(s[a.k - 1] >> 32) : 0u;
         return;
