@@ -53,6 +53,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_traffic(kernel: str, args, n_local: int, q_per_launch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json), if one exists for this shape."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    key = f"{kernel}:{n_local}x{args.dim}:{args.dtype}:q{q_per_launch}:k{args.k}"
+    e = d.get(key)
+    return float(e["dram_bytes"]) if e else None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -168,7 +181,7 @@ def run_reference(args):
 def workload_config(args, batch):
     return {
         "workload": f"{args.rows}x{args.dim} {args.dtype} corpus, top-{args.k}, query batch {batch}, row-sharded",
-        "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "k": args.k, "batch": batch,
+        "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "accumulate": "f32", "k": args.k, "batch": batch,
         "filter": "embedding_vec IS NOT NULL only", "l2": "inputs larger than L2 (no flush needed)",
         "parallelism": f"rowshard{args.gpus}",
     }
@@ -293,7 +306,8 @@ def main():
         q_per_launch = min(batch, group)
         bytes_launch = n_local * args.dim * elem + (n_local + 7) // 8 + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        traffic = load_traffic(f"scan_{idx.last_scan_kind()}", args, n_local, q_per_launch)
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                 "kernel": f"scan_{idx.last_scan_kind()}", "launches_per_step": scan_launches,
                 "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src}
 
@@ -355,7 +369,7 @@ def main():
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": m["ms"] / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": workload_config(args, args.batch),
             "e2e": {"value": e2e_qps, "unit": "queries/s",
                     "h2d_bytes_per_step": args.batch * args.dim * 4,

@@ -82,3 +82,37 @@ def build_tables(oracle, n: int, dim: int, seed: int = 7, dtype: str = "f32", nu
         for did in d_tags:
             pt.set_document_tags(did, sorted(d_tags[did]), sorted(p_tags[did]))
     return ot, pt, X, valid, meta, info
+
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+
+
+def load_golden_table(oracle, with_product: bool = False, dtype: str = "f32", device: int = 0):
+    """The table the golden fixtures were generated on (tests/golden/make_golden.py), rebuilt from the
+    committed files -- NOT from synth, so generator changes cannot silently move the fixtures."""
+    import json
+    import os
+    tj = json.load(open(os.path.join(GOLDEN_DIR, "table.json")))
+    vz = np.load(os.path.join(GOLDEN_DIR, "table_vectors.npz"))
+    X, has_vec = vz["X"], vz["has_vec"].astype(bool)
+    c = tj["columns"]
+    ot = oracle.Table(id=c["id"], document_id=c["document_id"], source_type=c["source_type"], source_id=c["source_id"],
+                      document_payer=c["document_payer"], document_state=c["document_state"],
+                      document_program=c["document_program"], document_authority_level=c["document_authority_level"],
+                      has_vec=has_vec, X=X, doc_d_tags={k: set(v) for k, v in tj["doc_d_tags"].items()},
+                      doc_p_tags={k: set(v) for k, v in tj["doc_p_tags"].items()}, extra=tj["extra"])
+    pt = None
+    if with_product:
+        n, dim = tj["n"], tj["dim"]
+        pt = mrag_b200.PublishedTable(dim, dtype=dtype, device=device, capacity=n + 64)
+        rows = []
+        for i in range(n):
+            r = {name: col[i] for name, col in c.items()}
+            for name, col in tj["extra"].items():
+                r[name] = col[i]
+            rows.append(r)
+        embs = [X[i].tolist() if has_vec[i] else None for i in range(n)]
+        pt.insert(rows, embs)
+        for did in tj["doc_d_tags"]:
+            pt.set_document_tags(did, tj["doc_d_tags"][did], tj["doc_p_tags"].get(did, []))
+    return ot, pt, X, has_vec
