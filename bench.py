@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the CPU baseline sample")
     ap.add_argument("--cpu-queries", type=int, default=8, help="queries of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tag-filter", type=int, default=0, metavar="M",
+                    help="document-tag filter passing every M-th document (0 = no filter); C2 uses 10")
+    ap.add_argument("--workload", default="", choices=["", "c2", "c3"],
+                    help="shortcut: c2 = 1Mx768 fp32, batch 256, top-10, tag filter 10%%; c3 = 10Mx768 bf16 top-100")
     return ap.parse_args()
 
 
@@ -182,7 +186,8 @@ def workload_config(args, batch):
     return {
         "workload": f"{args.rows}x{args.dim} {args.dtype} corpus, top-{args.k}, query batch {batch}, row-sharded",
         "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "accumulate": "f32", "k": args.k, "batch": batch,
-        "filter": "embedding_vec IS NOT NULL only", "l2": "inputs larger than L2 (no flush needed)",
+        "filter": ("embedding_vec IS NOT NULL only" if not args.tag_filter else
+                   f"document tag filter (relaxed, 1 tag) passing 1/{args.tag_filter} of the documents"), "l2": "inputs larger than L2 (no flush needed)",
         "parallelism": f"rowshard{args.gpus}",
     }
 
@@ -192,6 +197,11 @@ def workload_config(args, batch):
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    if args.workload == "c2":
+        args.rows, args.dim, args.dtype, args.batch, args.k, args.tag_filter = 1_000_000, 768, "f32", 256, 10, 10
+        args.sweep = ""
+    elif args.workload == "c3":
+        args.rows, args.dim, args.dtype, args.k = 10_000_000, 768, "bf16", 100
     if args.impl == "reference":
         run_reference(args)
         return
@@ -235,6 +245,15 @@ def main():
         m = X.shape[0]
         meta = mi.make_meta(m, doc_idx=(np.arange(first, first + m) // 64).astype(np.uint32))
         idx.append_device(X, meta)
+    flt = None
+    pass_frac = 1.0
+    if args.tag_filter:
+        n_docs = (args.rows + 63) // 64
+        bits = np.zeros((n_docs, 8), dtype=np.uint64)
+        bits[::args.tag_filter, 0] = 1                       # tag bit 0 on every M-th document
+        idx.set_doc_tags(0, bits)
+        flt = mi.Filter().tag_relaxed([0])
+        pass_frac = float(np.ceil(n_docs / args.tag_filter) / n_docs)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     assert len(idx) == n_local
@@ -250,8 +269,8 @@ def main():
 
     def one_step(qd, k, out=None):
         if ss is not None:
-            return ss.search(qd, k)
-        return idx.search_device(qd, k, out=out, sync=False)
+            return ss.search(qd, k, flt)
+        return idx.search_device(qd, k, flt, out=out, sync=False)
 
     def barrier():
         if world > 1:
@@ -298,13 +317,20 @@ def main():
                 "merge_ms": merge_ms, "clocks": clk, "result": res, "Q": Q}
 
     def roofline_of(m, batch):
-        group = 4 if idx.last_scan_kind() == "gemv" else 64      # queries per scan launch
+        kind = idx.last_scan_kind()
+        group = {"gemv": 4, "mma": 64, "mma128": 128}[kind]      # queries per scan launch
         scan_launches = (batch + group - 1) // group
         if not m["scan_ms"]:
             return None
         per_launch_ms = float(np.mean(m["scan_ms"])) / scan_launches
         q_per_launch = min(batch, group)
-        bytes_launch = n_local * args.dim * elem + (n_local + 7) // 8 + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12
+        # bytes the scan kernel has to stream: the rows that pass the filter in the storage it reads (the
+        # tensor-core kernels read bf16 rows -- for an fp32 corpus its bf16 shadow; the rows are 64-row tiles,
+        # so with a document filter whole passing tiles are read), the mask, 1/|x|, queries in, lists out
+        scan_elem = 2 if kind in ("mma", "mma128") else elem
+        n_pass = int(n_local * pass_frac)
+        bytes_launch = (n_pass * args.dim * scan_elem + (n_local + 7) // 8 + (n_pass * 4 if kind != "gemv" else 0)
+                        + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12)
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         traffic = load_traffic(f"scan_{idx.last_scan_kind()}", args, n_local, q_per_launch)
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
@@ -325,10 +351,10 @@ def main():
 
     def e2e_step():
         if ss is None:
-            idx.search_pinned(Qh, args.k, hs, hr, hc)          # H2D + scan + select + D2H + sync inside the C ABI
+            idx.search_pinned(Qh, args.k, hs, hr, hc, flt)     # H2D + scan + select + D2H + sync inside the C ABI
         else:
             qd.copy_(Qh, non_blocking=True)
-            s, r, c = ss.search(qd, args.k)
+            s, r, c = ss.search(qd, args.k, flt)
             hs.copy_(s, non_blocking=True); hr.copy_(r, non_blocking=True); hc.copy_(c, non_blocking=True)
             torch.cuda.current_stream().synchronize()
     for _ in range(3):

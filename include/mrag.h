@@ -164,7 +164,8 @@ enum {
     MRAG_OPT_DEVICE_IO   = 1u << 0, /* q / scores / rows / counts are DEVICE pointers on the index's device */
     MRAG_OPT_FORCE_GEMV  = 1u << 1, /* pin the CUDA-core streaming kernel (testing / tuning) */
     MRAG_OPT_FORCE_MMA   = 1u << 2, /* pin the tcgen05 kernel (testing / tuning)             */
-    MRAG_OPT_NO_SYNC     = 1u << 3  /* with DEVICE_IO: enqueue only, do not synchronise the stream */
+    MRAG_OPT_NO_SYNC     = 1u << 3, /* with DEVICE_IO: enqueue only, do not synchronise the stream */
+    MRAG_OPT_FORCE_MMA128 = 1u << 4 /* pin the 128-query candidate scan + exact rescoring (testing / tuning) */
 };
 
 /*

@@ -18,7 +18,7 @@ MRAG_PAYER_WORDS, MRAG_SMALL_WORDS, MRAG_TAG_WORDS = 16, 4, 8
 MRAG_CODE_NONE = 0xFFFF
 F_PAYER, F_STATE, F_PROGRAM, F_AUTHORITY, F_SOURCE_TYPE = 1, 2, 4, 8, 16
 F_DOC_EQ, F_DOC_POOL, F_TAG_STRICT, F_TAG_RELAXED = 32, 64, 128, 256
-OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC = 1, 2, 4, 8
+OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC, OPT_FORCE_MMA128 = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "mrag_create", "mrag_destroy", "mrag_append", "mrag_append_device", "mrag_set_doc_tags",

@@ -15,7 +15,9 @@
 #include "prep.cuh"
 #include "scan_gemv.cuh"
 #include "scan_mma.cuh"
+#include "scan_mma128.cuh"
 #include "select.cuh"
+#include "rescore.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -108,14 +110,17 @@ struct Workspace {
     DevBuf<__nv_bfloat16> qbf;
     DevBuf<uint32_t> mask, pool, pool_bits, gthr;
     DevBuf<uint64_t> part, part2, ub;
-    DevBuf<int64_t> rows;
-    DevBuf<int32_t> counts;
+    DevBuf<int64_t> rows, crows;
+    DevBuf<int32_t> counts, ccounts;
+    DevBuf<float> cscores;
+    DevBuf<uint64_t> ckeys;
+    DevBuf<int> fb;                 // [0] count, [1..] query list of the exact fallback
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); ub.release();
-        rows.release(); counts.release(); flags.release(); npass.release(); stats.release();
+        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -130,11 +135,12 @@ struct mrag_index {
     int64_t capacity = 0, size = 0, row_base = 0;
     int64_t n_docs = 0;                 // max doc_idx seen + 1
     void* rows = nullptr;               // [capacity][ld] storage dtype
+    __nv_bfloat16* shadow = nullptr;    // fp32 indexes, ld <= 768: bf16 copy scanned by the candidate-generating kernel
     float* inv_norm = nullptr;          // [capacity] 1/|x| of the stored row (+inf: zero norm)
     MetaCols cols{};
     uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
     int64_t n_tag_docs = 0, tag_docs_cap = 0;
-    CUtensorMap tmap;                   // corpus as a 2-D bf16 tensor, 64x64 boxes, SWIZZLE_128B
+    CUtensorMap tmap;                   // bf16 rows (or the shadow) as a 2-D tensor, 64x64 boxes, SWIZZLE_128B
     bool has_tmap = false;
     cudaStream_t wstream = nullptr;     // write-side stream
     std::shared_mutex lock;             // searches share, writers exclude
@@ -159,6 +165,7 @@ static thread_local EventSet t_last_ev;          // borrowed handles (owned by a
 static thread_local bool t_last_valid = false;
 static thread_local const char* t_last_kind = "none";
 static thread_local unsigned long long* t_stats_ptr = nullptr;
+static thread_local int* t_fb_ptr = nullptr;      // fallback counter of the last approx+rescore search
 static thread_local std::vector<EventSet> t_ring;
 static thread_local int t_ring_used = 0;
 static thread_local int t_ring_device = -1;
@@ -170,7 +177,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_corpus_tmap(mrag_index* x, int64_t alloc_rows) {
+static int make_corpus_tmap(mrag_index* x, void* base, int64_t alloc_rows) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -181,7 +188,7 @@ static int make_corpus_tmap(mrag_index* x, int64_t alloc_rows) {
     cuuint32_t box[2] = {cuuint32_t(kMmaKBlock), cuuint32_t(kMmaTileRows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<PFN_tmapEncodeTiled>(fn)(
-        &x->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x->rows, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        &x->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
     x->has_tmap = true;
@@ -222,7 +229,7 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     cudaError_t e = cudaSuccess;
     // 2 MB of slack after the last row: the TMA / vector paths may touch a whole tile past `size`
     if (e == cudaSuccess) e = cudaMalloc(&x->rows, size_t(cap32) * row_bytes + (2u << 20));
-    if (e == cudaSuccess) e = cudaMalloc(&x->inv_norm, size_t(cap32) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&x->inv_norm, size_t(cap32 + 64) * 4);   // bulk-copied per 64-row tile
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.doc_idx, size_t(cap32) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.payer, size_t(cap32) * 2);
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.state, size_t(cap32));
@@ -231,7 +238,7 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.source_type, size_t(cap32));
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.valid, size_t(cap32 / 32 + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(x->cols.valid, 0, size_t(cap32 / 32 + 1) * 4);
-    if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32) * 4);
+    if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32 + 64) * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->wstream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         int code = (e == cudaErrorMemoryAllocation) ? MRAG_ERR_OOM : MRAG_ERR_CUDA;
@@ -242,9 +249,15 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
         t_err = std::string("mrag_create: ") + cudaGetErrorString(e);
         return code;
     }
-    if (dtype == MRAG_BF16 && x->ld <= kMmaMaxLd) {
+    const char* shadow_env = getenv("MRAG_F32_SHADOW");
+    if (dtype == MRAG_F32 && x->ld <= kMmaMaxLd && !(shadow_env && shadow_env[0] == '0')) {
+        // +50% memory buys the 128-queries-per-pass tensor-core scan for large batches
+        cudaError_t es = cudaMalloc(&x->shadow, size_t(cap32) * x->ld * 2 + (2u << 20));
+        if (es != cudaSuccess) { x->shadow = nullptr; cudaGetLastError(); }   // not fatal: exact scan only
+    }
+    if ((dtype == MRAG_BF16 || x->shadow) && x->ld <= kMmaMaxLd) {
         // rows past `capacity` inside the allocation are never selected (mask bits are zero)
-        if (make_corpus_tmap(x, cap32 + 64) != MRAG_OK) {
+        if (make_corpus_tmap(x, dtype == MRAG_BF16 ? x->rows : static_cast<void*>(x->shadow), cap32 + 64) != MRAG_OK) {
             std::string keep = t_err;
             mrag_destroy(x);
             t_err = keep;
@@ -262,6 +275,7 @@ extern "C" int mrag_destroy(mrag_index* x) {
     for (Workspace* w : x->pool) { w->release(); delete w; }
     x->pool.clear();
     if (x->rows) cudaFree(x->rows);
+    if (x->shadow) cudaFree(x->shadow);
     if (x->inv_norm) cudaFree(x->inv_norm);
     if (x->cols.doc_idx) cudaFree(x->cols.doc_idx);
     if (x->cols.payer) cudaFree(x->cols.payer);
@@ -297,9 +311,9 @@ static int append_device_locked(mrag_index* x, const float* d_rows, int64_t n, c
                                 int64_t first, cudaStream_t s, mrag_rowmeta* d_meta_scratch) {
     const int wpb = 256 / 32;
     if (x->dtype == MRAG_BF16)
-        store_rows_kernel<1><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm);
+        store_rows_kernel<1><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm, nullptr);
     else
-        store_rows_kernel<0><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm);
+        store_rows_kernel<0><<<unsigned(ceil_div(n, wpb)), 256, 0, s>>>(d_rows, n, x->dim, x->rows, x->ld, first, x->inv_norm, x->shadow);
     LAUNCHED();
     CU(cudaMemcpyAsync(d_meta_scratch, meta, size_t(n) * sizeof(mrag_rowmeta), cudaMemcpyHostToDevice, s));
     scatter_meta_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, s>>>(d_meta_scratch, n, first, x->cols);
@@ -628,6 +642,124 @@ static int64_t sample_min_tiles(int num_sms) {
     return env ? env : int64_t(64) * num_sms;
 }
 
+
+// ORDER BY .. LIMIT over the per-producer lists: one block per query, or two levels when the producer
+// set is wide (many blocks in flight sorting <= 2048 keys each, then one block per query)
+static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
+    if (int64_t(m.P) * m.kp > kMergeSlots / 2 && !m.gthr_out) {
+        MergeArgs m1 = m;
+        m1.Pg = std::max(2, (kMergeSlots / 2) / m.kp);
+        const int groups = int(ceil_div(m.P, m1.Pg));
+        if (w->part2.reserve(size_t(nq) * groups * m.kp)) return MRAG_ERR_OOM;
+        m1.part_out = w->part2.p;
+        merge_kernel<<<dim3(unsigned(nq), unsigned(groups)), kMergeThreads, 0, s>>>(m1);
+        LAUNCHED();
+        m.part = w->part2.p; m.P = groups;
+    }
+    merge_kernel<<<nq, kMergeThreads, 0, s>>>(m);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
+static int approx_min_nq() {
+    static const int v = [] {
+        const char* e = getenv("MRAG_APPROX_MIN_NQ");
+        return (e && *e) ? std::max(1, atoi(e)) : 5;
+    }();
+    return v;
+}
+
+static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        CU(cudaFuncSetAttribute(scan_mma128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set[dev] = true;
+    }
+    const size_t fixed = mma128_smem_bytes(0, a.cap);
+    if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma128: candidate buffers do not fit");
+    a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
+    const size_t smem = mma128_smem_bytes(a.stages, a.cap);
+    for (int q0 = 0; q0 < nq; q0 += kMma128Queries) {
+        a.q0 = q0;
+        a.nq = std::min(kMma128Queries, nq - q0);
+        scan_mma128_kernel<<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        LAUNCHED();
+    }
+    return MRAG_OK;
+}
+
+// Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or
+// the bf16 shadow), exact rescoring of the K' = k + 32 nominees from the primary rows, certificate,
+// exact CUDA-core rescan of the queries that fail it.  Results are EXACT (same arithmetic as scan_gemv).
+static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int nq, int k, const uint32_t* mask,
+                                 float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t s) {
+    const int64_t n = x->size;
+    const int ld = x->ld;
+    const int kc = k + 32, kpc = host_next_pow2(kc);
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))));
+    const int64_t nwords = ceil_div(n, 32);
+    const int ggrid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
+    const int kp = std::max(8, host_next_pow2(k));
+    const char* eps_env = getenv("MRAG_APPROX_EPS_SCALE");     // tests: a huge scale sends every query to the rescan
+    const float eps_scale = (eps_env && *eps_env) ? float(atof(eps_env)) : 1.0f;
+    // |approx - exact| <= 2^-9 (bf16 query) + 2^-9 (the shadow's rounding, fp32 corpora) + accumulation slop
+    const float eps = (0x1p-9f + (x->dtype == MRAG_F32 ? 0x1p-9f : 0.0f) + 5e-5f) * eps_scale;
+
+    if (w->part.reserve(size_t(nq) * std::max(grid * kpc, ggrid * kp)) || w->gthr.reserve(size_t(nq)) ||
+        w->cscores.reserve(size_t(nq) * kc) || w->crows.reserve(size_t(nq) * kc) || w->ccounts.reserve(size_t(nq)) ||
+        w->ckeys.reserve(size_t(nq) * kc) || w->fb.reserve(size_t(nq) + 1))
+        return MRAG_ERR_OOM;
+    CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
+    CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
+    MmaArgs a{};
+    a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
+    a.part = w->part.p; a.k = kc; a.kp = kpc; a.P = grid; a.cap = kc + kMma128Slack;
+    a.gthr = w->gthr.p; a.tile_mul = 1; a.sleep_ns = mma_sleep_ns();
+    int rc = launch_scan_mma128(x, a, nq, grid, s);
+    if (rc != MRAG_OK) return rc;
+    CU(cudaEventRecord(ev.e[2], s));
+    // nominees per query, by approximate score
+    MergeArgs m{};
+    m.part = w->part.p; m.P = grid; m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
+    m.scores = w->cscores.p; m.rows = w->crows.p; m.counts = w->ccounts.p; m.row_base = 0;
+    rc = launch_merge(w, m, nq, s);
+    if (rc != MRAG_OK) return rc;
+    RescoreArgs ra{};
+    ra.rows = x->rows; ra.ld = ld; ra.inv_norm = x->inv_norm; ra.q = w->qpad.p; ra.qinv = w->qinv.p;
+    ra.cand_rows = w->crows.p; ra.cand_scores = w->cscores.p; ra.cand_counts = w->ccounts.p; ra.nq = nq; ra.kc = kc;
+    ra.keys = w->ckeys.p;
+    const unsigned rblocks = unsigned(ceil_div(int64_t(nq) * kc * 32, 256));
+    if (x->dtype == MRAG_BF16) rescore_kernel<1><<<rblocks, 256, 0, s>>>(ra);
+    else rescore_kernel<0><<<rblocks, 256, 0, s>>>(ra);
+    LAUNCHED();
+    FinalizeArgs fa{};
+    fa.keys = w->ckeys.p; fa.cand_scores = w->cscores.p; fa.cand_counts = w->ccounts.p; fa.nq = nq; fa.kc = kc; fa.k = k;
+    fa.eps = eps; fa.scores = d_scores; fa.rows = d_rows; fa.counts = d_counts; fa.row_base = x->row_base;
+    fa.need_tail = w->flags.p; fa.fb_count = w->fb.p; fa.fb_list = w->fb.p + 1;
+    finalize_kernel<<<nq, kFinalizeThreads, 0, s>>>(fa);
+    LAUNCHED();
+    // exact rescan of the queries whose certificate failed (a no-op launch when there are none)
+    ScanArgs g{};
+    g.rows = x->rows; g.n = n; g.ld = ld; g.mask = mask; g.q = w->qpad.p; g.qinv = w->qinv.p; g.ub = nullptr;
+    g.part = w->part.p; g.k = k; g.kp = kp; g.P = ggrid; g.qlist = w->fb.p + 1; g.qcount = w->fb.p;
+    const int gq = gemv_nq_for(4, ld, kp);
+    if (x->dtype == MRAG_BF16)
+        rc = gq == 4 ? launch_gemv<1, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<1, 2>(g, ggrid, s) : launch_gemv<1, 1>(g, ggrid, s);
+    else
+        rc = gq == 4 ? launch_gemv<0, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<0, 2>(g, ggrid, s) : launch_gemv<0, 1>(g, ggrid, s);
+    if (rc != MRAG_OK) return rc;
+    MergeArgs fm{};
+    fm.part = w->part.p; fm.P = ggrid; fm.kp = kp; fm.nq = nq; fm.k = k; fm.k_total = k; fm.k_off = 0;
+    fm.scores = d_scores; fm.rows = d_rows; fm.counts = d_counts; fm.row_base = x->row_base;
+    fm.need_tail = w->flags.p; fm.qlist = w->fb.p + 1; fm.qcount = w->fb.p;
+    rc = launch_merge(w, fm, nq, s);
+    if (rc != MRAG_OK) return rc;
+    t_fb_ptr = w->fb.p;
+    return MRAG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // search
 // ------------------------------------------------------------------------------------------
@@ -674,11 +806,28 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     const int64_t nwords = ceil_div(n, 32);
     // tensor-core scan: bf16 rows of <= 768 elements; single queries stay on the CUDA-core scan,
     // which already streams at ~0.9 of the HBM peak and skips masked rows individually
-    const bool can_mma = x->has_tmap && n > 0;
-    bool use_mma = can_mma && !(options & MRAG_OPT_FORCE_GEMV) && nq >= 2;
+    // kernels:  gemv   CUDA cores, exact, <= 4 queries per pass, any dtype / dim, skips masked rows individually
+    //           mma    tcgen05, exact (hi/lo split queries), 64 queries per pass, bf16 rows, dim <= 768
+    //           mma128 tcgen05 candidate generation, 128 queries per pass over bf16 rows / the bf16 shadow,
+    //                  + exact rescoring with certificate (k <= 32)
+    const bool can_mma = x->has_tmap && x->dtype == MRAG_BF16 && n > 0;
+    const bool can_mma128 = x->has_tmap && n > 0 && k <= 32;
+    bool use_mma = can_mma && nq >= 2;
+    bool use_mma128 = can_mma128 && (x->dtype == MRAG_BF16 ? nq > kMmaQueries : nq >= approx_min_nq());
+    if (options & MRAG_OPT_FORCE_GEMV) use_mma = use_mma128 = false;
     if (options & MRAG_OPT_FORCE_MMA) {
         if (!can_mma) return fail(MRAG_ERR_STATE, "mrag_search: the tensor-core scan needs a bf16 index with dim <= %d", kMmaMaxLd);
-        use_mma = true;
+        use_mma = true; use_mma128 = false;
+    }
+    if (options & MRAG_OPT_FORCE_MMA128) {
+        if (!can_mma128)
+            return fail(MRAG_ERR_STATE, "mrag_search: the 128-query scan needs bf16 rows or a bf16 shadow, dim <= %d, k <= 32", kMmaMaxLd);
+        use_mma128 = true;
+    }
+    if (use_mma128) {
+        int rc = search_approx_rescore(x, w, ev, nq, k, mask, d_scores, d_rows, d_counts, s);
+        if (rc != MRAG_OK) return rc;
+        t_last_kind = "mma128";
     }
     const int grid = use_mma
         ? int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))))
@@ -687,7 +836,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     float scan_ms_dummy = 0; (void)scan_ms_dummy;
     // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
     // earlier rounds is attributed to the scan phase
-    for (int r = 0; r < rounds; ++r) {
+    for (int r = 0; r < rounds && !use_mma128; ++r) {
         const int k_off = r * MRAG_FUSED_K;
         const int kr = std::min(MRAG_FUSED_K, k - k_off);
         const int kp = std::max(8, host_next_pow2(kr));
@@ -754,23 +903,11 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (r == rounds - 1) CU(cudaEventRecord(ev.e[2], s));
         MergeArgs m{};
         m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = kr; m.k_total = k; m.k_off = k_off;
-        if (int64_t(grid) * kp > kMergeSlots / 2) {
-            // two levels: (query, group of <= 2048 / kp lists) blocks first -- one sort of <= 2048 keys each,
-            // many blocks in flight -- then one block per query over the group lists
-            MergeArgs m1 = m;
-            m1.Pg = std::max(2, (kMergeSlots / 2) / kp);
-            const int groups = int(ceil_div(grid, m1.Pg));
-            if (w->part2.reserve(size_t(nq) * groups * kp)) return MRAG_ERR_OOM;
-            m1.part_out = w->part2.p;
-            merge_kernel<<<dim3(unsigned(nq), unsigned(groups)), kMergeThreads, 0, s>>>(m1);
-            LAUNCHED();
-            m.part = w->part2.p; m.P = groups;
-        }
         m.scores = d_scores; m.rows = d_rows; m.counts = d_counts; m.row_base = x->row_base;
         m.ub_out = (rounds > 1) ? w->ub.p : nullptr;
         m.need_tail = w->flags.p;
-        merge_kernel<<<nq, kMergeThreads, 0, s>>>(m);
-        LAUNCHED();
+        int rcm = launch_merge(w, m, nq, s);
+        if (rcm != MRAG_OK) return rcm;
     }
     // ---- NaN tail (Postgres: NaN distances sort last)
     if (n > 0) {
@@ -803,8 +940,10 @@ extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const m
     const bool no_sync = (options & MRAG_OPT_NO_SYNC) && dev_io;
     if ((options & MRAG_OPT_NO_SYNC) && !dev_io)
         return fail(MRAG_ERR_ARG, "mrag_search: MRAG_OPT_NO_SYNC needs MRAG_OPT_DEVICE_IO");
-    if ((options & MRAG_OPT_FORCE_MMA) && (options & MRAG_OPT_FORCE_GEMV))
-        return fail(MRAG_ERR_ARG, "mrag_search: FORCE_GEMV and FORCE_MMA exclude each other");
+    {
+        const uint32_t forced = options & (MRAG_OPT_FORCE_GEMV | MRAG_OPT_FORCE_MMA | MRAG_OPT_FORCE_MMA128);
+        if (forced & (forced - 1)) return fail(MRAG_ERR_ARG, "mrag_search: the FORCE_* options exclude each other");
+    }
 
     std::shared_lock<std::shared_mutex> rl(x->lock);
     DeviceGuard g(x->device);
@@ -955,6 +1094,13 @@ extern "C" int mrag_profile_read(int what, float* out_ms, int max) {
 extern "C" int mrag_debug_scan_stats(unsigned long long* out40) {
     if (!t_stats_ptr || !out40) return MRAG_ERR_STATE;
     return cudaMemcpy(out40, t_stats_ptr, 40 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? MRAG_OK : MRAG_ERR_CUDA;
+}
+
+// debugging aid (not in mrag.h): queries of the last approx+rescore search on this thread that went to the exact rescan
+extern "C" int mrag_debug_fallback_count(void) {
+    if (!t_fb_ptr) return -1;
+    int c = -1;
+    return cudaMemcpy(&c, t_fb_ptr, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? c : -1;
 }
 
 extern "C" int64_t mrag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

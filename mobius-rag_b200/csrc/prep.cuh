@@ -15,10 +15,13 @@
 namespace mrag {
 
 // one warp per row
+// `shadow` (fp32 indexes only, may be null): bf16 copy of the row for the candidate-generating
+// tensor-core scan; 1/|x| is always that of the PRIMARY row.
 template <int DT>
 __global__ void __launch_bounds__(256) store_rows_kernel(const float* __restrict__ src, int64_t n, int dim,
                                                         void* __restrict__ dst, int ld, int64_t first_row,
-                                                        float* __restrict__ inv_norm) {
+                                                        float* __restrict__ inv_norm,
+                                                        __nv_bfloat16* __restrict__ shadow) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
@@ -32,6 +35,7 @@ __global__ void __launch_bounds__(256) store_rows_kernel(const float* __restrict
             v = __bfloat162float(b);
         } else {
             reinterpret_cast<float*>(dst)[(first_row + r) * ld + e] = v;
+            if (shadow) shadow[(first_row + r) * ld + e] = __float2bfloat16_rn(v);
         }
         ss = fmaf(v, v, ss);
     }

@@ -35,6 +35,10 @@ struct ScanArgs {
     int q0;                 // first query handled by this launch
     int nq;                 // queries handled by this launch (<= NQ)
     int k, kp, P;
+    // exact-fallback mode (rescore.cuh): scan the queries qlist[0 .. *qcount) instead, NQ at a time,
+    // one full pass per group; *qcount == 0 makes the launch a no-op.  q0 / nq are ignored.
+    const int* qlist;
+    const int* qcount;
 };
 
 inline size_t gemv_smem_bytes(int nq_tpl, int ld, int kp) {
@@ -58,148 +62,159 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
     const int nvec = ld / E;               // 16-byte vectors per row
     const int cap = 2 * a.kp;
 
-    // ---- stage the queries: fp32, split in 4-float planes so every LDS.128 is conflict free
-    for (int i = tid; i < NQ * ld; i += kGemvThreads) {
-        int qi = i / ld, e = i - qi * ld;
-        float v = (qi < a.nq) ? a.q[size_t(a.q0 + qi) * ld + e] : 0.0f;
-        int dst;
-        if (DT == 1) {
-            int vv = e >> 3, w = e & 7;
-            dst = qi * ld + (w >> 2) * (ld >> 1) + vv * 4 + (w & 3);
-        } else {
-            dst = i;
-        }
-        qs[dst] = v;
-    }
-    uint64_t thr[NQ], ubk[NQ];
-    int cnt[NQ];
-    float qinv[NQ];
+    const int total = a.qlist ? *a.qcount : a.nq;
+    for (int g0 = 0; g0 < total; g0 += NQ) {
+        const int nq_here = min(NQ, total - g0);
+        int qid[NQ];
 #pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-        thr[qi] = 0; cnt[qi] = 0;
-        ubk[qi] = (a.ub && qi < a.nq) ? a.ub[a.q0 + qi] : ~0ull;
-        qinv[qi] = (qi < a.nq) ? a.qinv[a.q0 + qi] : 0.0f;
-    }
-    __syncthreads();
-
-    const int64_t nwords = (a.n + 31) >> 5;
-    const int64_t W = int64_t(gridDim.x) * kGemvWarps;
-    const char* base = reinterpret_cast<const char*>(a.rows);
-    const size_t row_bytes = size_t(ld) * (DT == 1 ? 2 : 4);
-
-    int64_t w = int64_t(blockIdx.x) * kGemvWarps + warp;
-    uint32_t m_next = (w < nwords) ? __ldg(a.mask + w) : 0u;
-    for (; w < nwords; w += W) {
-        uint32_t m = m_next;
-        m_next = (w + W < nwords) ? __ldg(a.mask + w + W) : 0u;
-        while (m) {
-            uint32_t r[kGemvRows];
-            int nr = 0;
+        for (int qi = 0; qi < NQ; ++qi) qid[qi] = qi < nq_here ? (a.qlist ? a.qlist[g0 + qi] : a.q0 + g0 + qi) : 0;
+        if (g0) __syncthreads();               // the previous group's buffers are still being read
+        // ---- stage the queries: fp32, split in 4-float planes so every LDS.128 is conflict free
+        for (int i = tid; i < NQ * ld; i += kGemvThreads) {
+            int qi = i / ld, e = i - qi * ld;
+            int src_q = 0;
 #pragma unroll
-            for (int j = 0; j < kGemvRows; ++j) {
-                if (m) { int b = __ffs(m) - 1; m &= m - 1; r[j] = uint32_t(w * 32 + b); ++nr; }
-                else r[j] = r[0];
+            for (int j = 0; j < NQ; ++j) src_q = (qi == j) ? qid[j] : src_q;   // keeps qid[] in registers
+            float v = (qi < nq_here) ? a.q[size_t(src_q) * ld + e] : 0.0f;
+            int dst;
+            if (DT == 1) {
+                int vv = e >> 3, w = e & 7;
+                dst = qi * ld + (w >> 2) * (ld >> 1) + vv * 4 + (w & 3);
+            } else {
+                dst = i;
             }
-            float acc[kGemvRows][NQ + 1];
-#pragma unroll
-            for (int j = 0; j < kGemvRows; ++j)
-#pragma unroll
-                for (int x = 0; x <= NQ; ++x) acc[j][x] = 0.0f;
+            qs[dst] = v;
+        }
+        uint64_t thr[NQ], ubk[NQ];
+        int cnt[NQ];
+        float qinv[NQ];
+    #pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            thr[qi] = 0; cnt[qi] = 0;
+            ubk[qi] = (a.ub && qi < nq_here) ? a.ub[qid[qi]] : ~0ull;
+            qinv[qi] = (qi < nq_here) ? a.qinv[qid[qi]] : 0.0f;
+        }
+        __syncthreads();
 
-            for (int v0 = 0; v0 < nvec; v0 += kWarp * kGemvVecs) {
-                uint4 d[kGemvRows][kGemvVecs];
-#pragma unroll
-                for (int c = 0; c < kGemvVecs; ++c) {
-                    int v = v0 + c * kWarp + lane;
-                    bool ok = v < nvec;
-#pragma unroll
-                    for (int j = 0; j < kGemvRows; ++j) {
-                        if (ok && j < nr) d[j][c] = ldg_stream(base + size_t(r[j]) * row_bytes + size_t(v) * 16);
-                        else d[j][c] = make_uint4(0, 0, 0, 0);
-                    }
+        const int64_t nwords = (a.n + 31) >> 5;
+        const int64_t W = int64_t(gridDim.x) * kGemvWarps;
+        const char* base = reinterpret_cast<const char*>(a.rows);
+        const size_t row_bytes = size_t(ld) * (DT == 1 ? 2 : 4);
+
+        int64_t w = int64_t(blockIdx.x) * kGemvWarps + warp;
+        uint32_t m_next = (w < nwords) ? __ldg(a.mask + w) : 0u;
+        for (; w < nwords; w += W) {
+            uint32_t m = m_next;
+            m_next = (w + W < nwords) ? __ldg(a.mask + w + W) : 0u;
+            while (m) {
+                uint32_t r[kGemvRows];
+                int nr = 0;
+    #pragma unroll
+                for (int j = 0; j < kGemvRows; ++j) {
+                    if (m) { int b = __ffs(m) - 1; m &= m - 1; r[j] = uint32_t(w * 32 + b); ++nr; }
+                    else r[j] = r[0];
                 }
-#pragma unroll
-                for (int c = 0; c < kGemvVecs; ++c) {
-                    int v = v0 + c * kWarp + lane;
-                    if (v < nvec) {
-                        float x[kGemvRows][E];
-#pragma unroll
+                float acc[kGemvRows][NQ + 1];
+    #pragma unroll
+                for (int j = 0; j < kGemvRows; ++j)
+    #pragma unroll
+                    for (int x = 0; x <= NQ; ++x) acc[j][x] = 0.0f;
+
+                for (int v0 = 0; v0 < nvec; v0 += kWarp * kGemvVecs) {
+                    uint4 d[kGemvRows][kGemvVecs];
+    #pragma unroll
+                    for (int c = 0; c < kGemvVecs; ++c) {
+                        int v = v0 + c * kWarp + lane;
+                        bool ok = v < nvec;
+    #pragma unroll
                         for (int j = 0; j < kGemvRows; ++j) {
-                            if (DT == 1) {
-                                x[j][0] = bf16lo(d[j][c].x); x[j][1] = bf16hi(d[j][c].x);
-                                x[j][2] = bf16lo(d[j][c].y); x[j][3] = bf16hi(d[j][c].y);
-                                x[j][4 % E] = bf16lo(d[j][c].z); x[j][5 % E] = bf16hi(d[j][c].z);
-                                x[j][6 % E] = bf16lo(d[j][c].w); x[j][7 % E] = bf16hi(d[j][c].w);
-                            } else {
-                                x[j][0] = __uint_as_float(d[j][c].x); x[j][1] = __uint_as_float(d[j][c].y);
-                                x[j][2] = __uint_as_float(d[j][c].z); x[j][3] = __uint_as_float(d[j][c].w);
-                            }
-#pragma unroll
-                            for (int e = 0; e < E; ++e) acc[j][NQ] = fmaf(x[j][e], x[j][e], acc[j][NQ]);
+                            if (ok && j < nr) d[j][c] = ldg_stream(base + size_t(r[j]) * row_bytes + size_t(v) * 16);
+                            else d[j][c] = make_uint4(0, 0, 0, 0);
                         }
-#pragma unroll
-                        for (int qi = 0; qi < NQ; ++qi) {
-                            float qv[E];
-                            const float4 q0v = *reinterpret_cast<const float4*>(qs + qi * ld + v * 4);
-                            qv[0] = q0v.x; qv[1] = q0v.y; qv[2] = q0v.z; qv[3] = q0v.w;
-                            if (DT == 1) {
-                                const float4 q1v = *reinterpret_cast<const float4*>(qs + qi * ld + (ld >> 1) + v * 4);
-                                qv[4 % E] = q1v.x; qv[5 % E] = q1v.y; qv[6 % E] = q1v.z; qv[7 % E] = q1v.w;
+                    }
+    #pragma unroll
+                    for (int c = 0; c < kGemvVecs; ++c) {
+                        int v = v0 + c * kWarp + lane;
+                        if (v < nvec) {
+                            float x[kGemvRows][E];
+    #pragma unroll
+                            for (int j = 0; j < kGemvRows; ++j) {
+                                if (DT == 1) {
+                                    x[j][0] = bf16lo(d[j][c].x); x[j][1] = bf16hi(d[j][c].x);
+                                    x[j][2] = bf16lo(d[j][c].y); x[j][3] = bf16hi(d[j][c].y);
+                                    x[j][4 % E] = bf16lo(d[j][c].z); x[j][5 % E] = bf16hi(d[j][c].z);
+                                    x[j][6 % E] = bf16lo(d[j][c].w); x[j][7 % E] = bf16hi(d[j][c].w);
+                                } else {
+                                    x[j][0] = __uint_as_float(d[j][c].x); x[j][1] = __uint_as_float(d[j][c].y);
+                                    x[j][2] = __uint_as_float(d[j][c].z); x[j][3] = __uint_as_float(d[j][c].w);
+                                }
+    #pragma unroll
+                                for (int e = 0; e < E; ++e) acc[j][NQ] = fmaf(x[j][e], x[j][e], acc[j][NQ]);
                             }
-#pragma unroll
-                            for (int j = 0; j < kGemvRows; ++j)
-#pragma unroll
-                                for (int e = 0; e < E; ++e) acc[j][qi] = fmaf(x[j][e], qv[e], acc[j][qi]);
+    #pragma unroll
+                            for (int qi = 0; qi < NQ; ++qi) {
+                                float qv[E];
+                                const float4 q0v = *reinterpret_cast<const float4*>(qs + qi * ld + v * 4);
+                                qv[0] = q0v.x; qv[1] = q0v.y; qv[2] = q0v.z; qv[3] = q0v.w;
+                                if (DT == 1) {
+                                    const float4 q1v = *reinterpret_cast<const float4*>(qs + qi * ld + (ld >> 1) + v * 4);
+                                    qv[4 % E] = q1v.x; qv[5 % E] = q1v.y; qv[6 % E] = q1v.z; qv[7 % E] = q1v.w;
+                                }
+    #pragma unroll
+                                for (int j = 0; j < kGemvRows; ++j)
+    #pragma unroll
+                                    for (int e = 0; e < E; ++e) acc[j][qi] = fmaf(x[j][e], qv[e], acc[j][qi]);
+                            }
                         }
                     }
                 }
-            }
-            // ---- finish the sums: every lane ends up with every total
-#pragma unroll
-            for (int j = 0; j < kGemvRows; ++j)
-#pragma unroll
-                for (int x = 0; x <= NQ; ++x) acc[j][x] = warp_sum(acc[j][x]);
+                // ---- finish the sums: every lane ends up with every total
+    #pragma unroll
+                for (int j = 0; j < kGemvRows; ++j)
+    #pragma unroll
+                    for (int x = 0; x <= NQ; ++x) acc[j][x] = warp_sum(acc[j][x]);
 
-            // ---- normalise and select (warp uniform)
-#pragma unroll
-            for (int j = 0; j < kGemvRows; ++j) {
-                if (j >= nr) break;
-                const float nx = acc[j][NQ];
-                if (!(nx > 0.0f)) continue;             // zero-norm row: similarity is NaN (NaN tail pass)
-                const float inv = rsqrtf(nx);
-#pragma unroll
-                for (int qi = 0; qi < NQ; ++qi) {
-                    if (qi >= a.nq) break;
-                    const float s = acc[j][qi] * inv * qinv[qi];
-                    if (!(s == s)) continue;            // zero-norm query
-                    const uint64_t key = make_key(s, r[j]);
-                    if (key > thr[qi] && key < ubk[qi]) {
-                        uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
-                        if (lane == 0) b[cnt[qi]] = key;
-                        if (++cnt[qi] == cap) {
-                            __syncwarp();
-                            warp_sort_desc(b, cap, lane);
-                            cnt[qi] = a.k;
-                            thr[qi] = b[a.k - 1];
+                // ---- normalise and select (warp uniform)
+    #pragma unroll
+                for (int j = 0; j < kGemvRows; ++j) {
+                    if (j >= nr) break;
+                    const float nx = acc[j][NQ];
+                    if (!(nx > 0.0f)) continue;             // zero-norm row: similarity is NaN (NaN tail pass)
+                    const float inv = rsqrtf(nx);
+    #pragma unroll
+                    for (int qi = 0; qi < NQ; ++qi) {
+                        if (qi >= nq_here) break;
+                        const float s = acc[j][qi] * inv * qinv[qi];
+                        if (!(s == s)) continue;            // zero-norm query
+                        const uint64_t key = make_key(s, r[j]);
+                        if (key > thr[qi] && key < ubk[qi]) {
+                            uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
+                            if (lane == 0) b[cnt[qi]] = key;
+                            if (++cnt[qi] == cap) {
+                                __syncwarp();
+                                warp_sort_desc(b, cap, lane);
+                                cnt[qi] = a.k;
+                                thr[qi] = b[a.k - 1];
+                            }
                         }
                     }
                 }
             }
         }
-    }
 
-    // ---- block merge: clear the unused tail of every warp buffer, sort the block's buffers together
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-        uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
-        for (int i = cnt[qi] + lane; i < cap; i += kWarp) b[i] = 0;
-    }
-    __syncthreads();
-    for (int qi = 0; qi < a.nq; ++qi) {
-        uint64_t* b = bufs + size_t(qi) * kGemvWarps * cap;
-        block_sort_desc(b, kGemvWarps * cap);
-        uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
-        for (int i = tid; i < a.kp; i += kGemvThreads) out[i] = (i < a.k) ? b[i] : 0ull;
+        // ---- block merge: clear the unused tail of every warp buffer, sort the block's buffers together
+    #pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
+            for (int i = cnt[qi] + lane; i < cap; i += kWarp) b[i] = 0;
+        }
+        __syncthreads();
+        for (int qi = 0; qi < nq_here; ++qi) {
+            uint64_t* b = bufs + size_t(qi) * kGemvWarps * cap;
+            block_sort_desc(b, kGemvWarps * cap);
+            uint64_t* out = a.part + (size_t(qid[qi]) * a.P + blockIdx.x) * a.kp;
+            for (int i = tid; i < a.kp; i += kGemvThreads) out[i] = (i < a.k) ? b[i] : 0ull;
+        }
     }
 }
 

@@ -33,6 +33,9 @@ struct MergeArgs {
     // each; block (q, g) writes the sorted top-k keys of its group to part_out[q][g][kp] and nothing else
     uint64_t* part_out;
     int Pg;
+    // exact-fallback mode: block b serves query qlist[b] and exits if b >= *qcount
+    const int* qlist;
+    const int* qcount;
 };
 
 // One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
@@ -41,7 +44,9 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     __shared__ uint64_t s[kMergeSlots];
     __shared__ unsigned long long s_T;
     __shared__ int s_cnt;
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    if (a.qlist && int(blockIdx.x) >= *a.qcount) return;
+    const int q = a.qlist ? a.qlist[blockIdx.x] : int(blockIdx.x);
     const int p_lo = a.part_out ? int(blockIdx.y) * a.Pg : 0;
     const int P = a.part_out ? min(a.Pg, a.P - p_lo) : a.P;
     const uint64_t* base = a.part + (size_t(q) * a.P + p_lo) * a.kp;

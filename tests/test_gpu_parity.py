@@ -552,3 +552,100 @@ def test_mma_threshold_sampling_pass(oracle):
     env = dict(os.environ, MRAG_SAMPLE_MIN_TILES="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "SAMPLING-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# large batches: 128-query candidate scan (fp16 queries x bf16 rows / bf16 shadow) + exact rescoring
+# with certificate + exact rescan of uncertified queries.  Results must be EXACT, not approximate.
+# ---------------------------------------------------------------------------------------------
+def _fallbacks():
+    return int(N.load().mrag_debug_fallback_count())
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (30000, 768, 130, 10), (5000, 96, 70, 32), (64, 64, 5, 10), (63, 64, 9, 1), (20000, 768, 256, 10),
+    (4097, 100, 129, 7), (100000, 768, 200, 10), (300, 768, 140, 20),
+])
+def test_mma128_rescore_exact(oracle, dtype, n, dim, nq, k):
+    X, valid = synth.make_corpus(n, dim, seed=n + dim + 2, null_frac=3e-3)
+    Q = synth.make_queries(X, nq, seed=k + 2)
+    idx = Index(dim, dtype, 0, n + 5)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA128)
+    assert idx.last_scan_kind() == "mma128"
+    check_all(oracle, stored(oracle, X, dtype), Q, valid.astype(bool), k, s, r, c, dtype)
+    assert 0 <= _fallbacks() <= nq
+    idx.close()
+
+
+def test_mma128_default_dispatch(oracle):
+    n, dim = 8000, 768
+    X, valid = synth.make_corpus(n, dim, seed=5)
+    for dtype, nq, want in (("f32", 4, "gemv"), ("f32", 5, "mma128"), ("bf16", 64, "mma"), ("bf16", 65, "mma128")):
+        idx = Index(dim, dtype, 0, n)
+        idx.append(X, make_meta(n, valid=valid))
+        Q = synth.make_queries(X, nq, seed=6)
+        s, r, c = idx.search(Q, 10)
+        assert idx.last_scan_kind() == want, (dtype, nq)
+        check_all(oracle, stored(oracle, X, dtype), Q, valid.astype(bool), 10, s, r, c, dtype)
+        s, r, c = idx.search(Q, 33)                    # k > 32: the exact kernels
+        assert idx.last_scan_kind() != "mma128"
+        with pytest.raises(N.MragError):
+            idx.search(Q, 33, options=N.OPT_FORCE_MMA128)
+        idx.close()
+    idx = Index(1536, "bf16", 0, 100)                  # dim > 768: no tensor-core path
+    idx.append(np.ones((10, 1536), np.float32))
+    with pytest.raises(N.MragError):
+        idx.search(np.ones((1, 1536), np.float32), 5, options=N.OPT_FORCE_MMA128)
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_mma128_certificate_failure_goes_to_exact_rescan(oracle, dtype, monkeypatch):
+    """A huge eps makes every certificate fail: all queries take the exact CUDA-core rescan, and the
+    answer must not change.  With the real eps on data full of near-duplicates some queries fail."""
+    n, dim, nq, k = 20000, 128, 70, 10
+    X, valid = synth.make_corpus(n, dim, seed=9, null_frac=2e-3)
+    # 300 near-copies of one row (spread 1e-4): more near-ties than k + 32 candidates can hold
+    rng = np.random.default_rng(1)
+    X[5000:5300] = X[77] * (1.0 + 1e-4 * rng.standard_normal((300, 1)).astype(np.float32)) \
+        + 1e-4 * rng.standard_normal((300, dim)).astype(np.float32)
+    Q = synth.make_queries(X, nq, seed=10)
+    Q[0] = X[77] + 1e-3 * rng.standard_normal(dim).astype(np.float32)
+    idx = Index(dim, dtype, 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    Xs = stored(oracle, X, dtype)
+    s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA128)
+    check_all(oracle, Xs, Q, valid.astype(bool), k, s, r, c, dtype)
+    assert _fallbacks() >= 1                           # query 0 sits in the dense cluster
+    monkeypatch.setenv("MRAG_APPROX_EPS_SCALE", "1e6")
+    s2, r2, c2 = idx.search(Q, k, options=N.OPT_FORCE_MMA128)
+    assert _fallbacks() == nq
+    check_all(oracle, Xs, Q, valid.astype(bool), k, s2, r2, c2, dtype)
+    idx.close()
+
+
+def test_mma128_with_filters_ties_and_nan(oracle):
+    n, dim, nq, k = 30000, 256, 150, 10
+    X, valid = synth.make_corpus(n, dim, seed=21, null_frac=5e-3)
+    X[100:110] = 0.0                                   # zero-norm rows: NaN similarity, sort last
+    X[2000:2040] = X[1999]                             # exact duplicates: ties by row
+    meta, doc_tags, info = synth.make_metadata(n, seed=22, rows_per_doc=32, valid=valid)
+    Q = synth.make_queries(X, nq, seed=23)
+    Q[3] = 0.0                                         # zero query: every similarity NaN
+    Q[4] = X[1999]
+    for dtype in ("f32", "bf16"):
+        idx = Index(dim, dtype, 0, n)
+        idx.append(X, meta)
+        idx.set_doc_tags(0, doc_tags)
+        Xs = stored(oracle, X, dtype)
+        for flt, m in (
+            (None, valid.astype(bool)),
+            (Filter().state_eq(synth.STATES.index("FL")), valid.astype(bool) & (meta["state"] == synth.STATES.index("FL"))),
+            (Filter().doc_pool(np.arange(0, info["n_docs"], 37)), valid.astype(bool) & (info["doc_of_row"] % 37 == 0)),
+            (Filter().doc_eq(3), valid.astype(bool) & (info["doc_of_row"] == 3)),       # fewer rows than k + 32
+        ):
+            s, r, c = idx.search(Q, k, flt, options=N.OPT_FORCE_MMA128)
+            check_all(oracle, Xs, Q, m, k, s, r, c, dtype)
+        idx.close()
