@@ -669,14 +669,16 @@ static int approx_min_nq() {
     return v;
 }
 
+template <int KREG>
 static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute(scan_mma128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(scan_mma128_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
+    if (KREG > 0) a.cap = 0;
     const size_t fixed = mma128_smem_bytes(0, a.cap);
     if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma128: candidate buffers do not fit");
     a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
@@ -684,7 +686,7 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
     for (int q0 = 0; q0 < nq; q0 += kMma128Queries) {
         a.q0 = q0;
         a.nq = std::min(kMma128Queries, nq - q0);
-        scan_mma128_kernel<<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        scan_mma128_kernel<KREG><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
         LAUNCHED();
     }
     return MRAG_OK;
@@ -717,7 +719,34 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
     a.part = w->part.p; a.k = kc; a.kp = kpc; a.P = grid; a.cap = kc + kMma128Slack;
     a.gthr = w->gthr.p; a.tile_mul = 1; a.sleep_ns = mma_sleep_ns();
-    int rc = launch_scan_mma128(x, a, nq, grid, s);
+    if (getenv("MRAG_SCAN_STATS")) {
+        if (w->stats.reserve(40)) return MRAG_ERR_OOM;
+        CU(cudaMemsetAsync(w->stats.p, 0, 40 * 8, s));
+        a.stats = w->stats.p;
+        t_stats_ptr = w->stats.p;
+    }
+    int rc;
+    const int64_t tiles = ceil_div(n, kMmaTileRows);
+    if (tiles >= sample_min_tiles(x->num_sms)) {
+        // admission bound from a strided sample (4 tiles per CTA), same arithmetic, register top-16 per CTA: the
+        // K'-th best of the union of the per-CTA lists is reached by K' known rows, so the full pass may skip
+        // anything below it (a CTA holds 1/#CTAs of the sample: its top 16 almost never truncate the sample's top K')
+        MmaArgs sa = a;
+        sa.stats = nullptr;
+        sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(4) * x->num_sms)));
+        const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
+        sa.P = sgrid;
+        sa.k = std::min(kc, kMmaRegK);
+        sa.kp = kMmaRegK;
+        rc = launch_scan_mma128<kMmaRegK>(x, sa, nq, sgrid, s);
+        if (rc != MRAG_OK) return rc;
+        MergeArgs sm{};
+        sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kc; sm.lk = sa.k; sm.k_total = kc;
+        sm.gthr_out = w->gthr.p;     // (overwrites the looser per-CTA bounds the sampling launches left there)
+        merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
+        LAUNCHED();
+    }
+    rc = launch_scan_mma128<0>(x, a, nq, grid, s);
     if (rc != MRAG_OK) return rc;
     CU(cudaEventRecord(ev.e[2], s));
     // nominees per query, by approximate score

@@ -22,7 +22,7 @@
 namespace mrag {
 
 constexpr int kMma128Queries = 128;
-constexpr int kMma128InvSlots = 4;
+constexpr int kMma128InvSlots = 8;
 constexpr int kMma128Slack = 32;          // candidate buffer = K' + slack keys per query
 
 inline size_t mma128_smem_bytes(int stages, int cap) {
@@ -36,8 +36,78 @@ MRAG_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64
                  : "memory");
 }
 
+// rank sort like warp_rank_select, with the per-lane work bounded by the lanes actually in use
+MRAG_DEVINL void warp_rank_select_n(uint64_t* buf, int n, int keep, int lane) {
+    uint64_t key[kRankPerLane];
+    int rank[kRankPerLane];
+    const int ne = (n + 31) >> 5;             // warp uniform
+#pragma unroll
+    for (int e = 0; e < kRankPerLane; ++e) {
+        const int i = lane + 32 * e;
+        key[e] = (i < n) ? buf[i] : 0ull;
+        rank[e] = 0;
+    }
+    for (int j = 0; j < n; ++j) {
+        const uint64_t kj = buf[j];           // broadcast read
+#pragma unroll
+        for (int e = 0; e < kRankPerLane; ++e)
+            if (e < ne) rank[e] += (kj > key[e]) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kRankPerLane; ++e) {
+        const int i = lane + 32 * e;
+        if (i < n && rank[e] < keep) buf[rank[e]] = key[e];
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ SelState select_compact128(SelState st, unsigned full, uint64_t* cand_warp, int cap, int k, int lane) {
+    while (full) {
+        const int L = __ffs(full) - 1;
+        full &= full - 1;
+        __syncwarp();
+        uint64_t* b = cand_warp + size_t(L) * cap;
+        warp_rank_select_n(b, cap, k, lane);
+        const uint64_t kth = b[k - 1];
+        if (lane == L) { st.cnt = k; st.thr_s = key_score(kth); }
+    }
+    return st;
+}
+
+// rows 8G .. 8G+7 of the tile: append what beats the threshold; a full buffer is compacted and the walk resumes.
+// (a function template so that every index into sc[] is a compile-time constant: the array must stay in registers)
+template <int G>
+MRAG_DEVINL void walk_group(const float (&sc)[64], float& thr, SelState& st, uint64_t* mybuf, uint64_t* cand_warp, int cap,
+                            int k, int lane, int64_t r0, uint32_t* gslot, unsigned& n_keys, unsigned& n_compact) {
+    const int cnt0 = st.cnt;
+    int c_start = 0;
+    for (;;) {
+        int ovf = 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_start && sc[8 * G + c] > thr) {
+                if (st.cnt < cap) mybuf[st.cnt++] = make_key(sc[8 * G + c], uint32_t(r0 + 8 * G + c));
+                else ovf = min(ovf, c);
+            }
+        }
+        const unsigned full = __ballot_sync(kFull, st.cnt == cap);
+        if (!full) { n_keys += st.cnt - cnt0; break; }
+        n_compact += __popc(full);
+        st = select_compact128(st, full, cand_warp, cap, k, lane);
+        if ((full >> lane) & 1u) atomicMax(gslot, f2ord(st.thr_s));
+        thr = fmaxf(thr, st.thr_s);
+        c_start = ovf;
+        if (!__any_sync(kFull, ovf < 8)) break;
+    }
+}
+
 // a.q: fp32 queries; a.qinv: 1/|q|; a.k = K' (candidates wanted), a.kp = pow2 >= K', a.cap = K' + slack.
-// a.stats / a.ub are ignored.
+// a.ub is ignored.
+// KREG = 0: per-query shared-memory buffers of `cap` keys (the full pass).
+// KREG > 0: every thread keeps the sorted top-KREG of its query in registers (a.k <= KREG, cap = 0): the
+//           sampling pass, where a buffer would be compacted over and over before any bound exists.
+template <int KREG>
 __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
@@ -186,6 +256,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
         st.cnt = 0;
         st.thr_s = (live && !isinf(qinv)) ? -CUDART_INF_F : CUDART_INF_F;
         uint32_t* gslot = a.gthr + a.q0 + (live ? qi : 0);
+        unsigned n_tiles = 0, n_groups = 0, n_keys = 0, n_compact = 0;
+        // KREG mode: only SCORES are kept (the pass exists to produce a bound, rows do not matter): sorted
+        // orderable scores, the k live slots are the LAST k of top[] (sentinels before them), so the k-th best
+        // is always top[KREG-1]; every index is a compile-time constant (the array must stay in registers)
+        uint32_t top[KREG > 0 ? KREG : 1];
+        const int top_off = (KREG > 0 ? KREG : 1) - a.k;
+#pragma unroll
+        for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = (i < top_off) ? ~0u : 0u;
 
         uint2 m = tile_mask(t_first);
         for (int64_t t = t_first; t < num_tiles; t += G) {
@@ -193,7 +271,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
             if ((m.x | m.y) != 0u) {
                 const int64_t r0 = t * kMmaTileRows;
                 float sc[64];
-                float best = -CUDART_INF_F;
+                float bestg[8];                                      // max of each group of 8 rows
                 uint32_t gord;
                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gord) : "l"(gslot) : "memory");
                 mbar_wait(&ifull_bar[is], iph, slp);
@@ -227,7 +305,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) best = fmaxf(best, sc[c]);
+                    for (int g = 0; g < 8; ++g) {
+                        const float m01 = fmaxf(sc[8 * g + 0], sc[8 * g + 1]), m23 = fmaxf(sc[8 * g + 2], sc[8 * g + 3]);
+                        const float m45 = fmaxf(sc[8 * g + 4], sc[8 * g + 5]), m67 = fmaxf(sc[8 * g + 6], sc[8 * g + 7]);
+                        bestg[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));      // fmaxf drops NaN
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);
@@ -237,42 +319,71 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
                 if (++is == kMma128InvSlots) { is = 0; iph ^= 1u; }
                 if (warp_live) {
                     float thr = fmaxf(st.thr_s, gord ? ord2f(gord - 1u) : -CUDART_INF_F);
-                    if (__any_sync(kFull, best > thr)) {
-                        int c_start = 0;
-                        for (;;) {
-                            int ovf = 64;
+                    // the warp walks only the groups of 8 rows in which some query admits a row
+                    // (warp-uniform votes: in steady state a tile has no such group, or one)
+                    ++n_tiles;
+                    if constexpr (KREG > 0) {
+                        const float thr_in = st.thr_s;
 #pragma unroll
-                            for (int c = 0; c < 64; ++c) {
-                                if (c >= c_start && sc[c] > thr) {
-                                    if (st.cnt < cap) mybuf[st.cnt++] = make_key(sc[c], uint32_t(r0 + c));
-                                    else ovf = min(ovf, c);
+                        for (int c = 0; c < 64; ++c) {
+                            const bool ins = sc[c] > thr;
+                            if (__any_sync(kFull, ins)) {                        // warp-uniform
+                                uint32_t key = ins ? f2ord(sc[c]) : 0u;
+#pragma unroll
+                                for (int i = 0; i < KREG; ++i) {                 // sorted insertion, a zero key falls through
+                                    const uint32_t hi = max(key, top[i]);
+                                    key = min(key, top[i]);
+                                    top[i] = hi;
                                 }
+                                const uint32_t kth = top[KREG - 1];
+                                if (kth) { st.thr_s = ord2f(kth); thr = fmaxf(thr, st.thr_s); }
                             }
-                            const unsigned full = __ballot_sync(kFull, st.cnt == cap);
-                            if (!full) break;
-                            st = select_compact(st, full, cand_warp, cap, a.k, lane);
-                            if ((full >> lane) & 1u) atomicMax(gslot, f2ord(st.thr_s));
-                            thr = fmaxf(thr, st.thr_s);
-                            c_start = ovf;
-                            if (!__any_sync(kFull, ovf < 64)) break;
                         }
+                        if (st.thr_s > thr_in) atomicMax(gslot, f2ord(st.thr_s));
+                    } else {
+#define MRAG_WALK_GROUP(G)                                                                                        \
+                    if (__any_sync(kFull, bestg[G] > thr)) {                                                      \
+                        ++n_groups;                                                                               \
+                        walk_group<G>(sc, thr, st, mybuf, cand_warp, cap, a.k, lane, r0, gslot, n_keys, n_compact); \
+                    }
+                    MRAG_WALK_GROUP(0) MRAG_WALK_GROUP(1) MRAG_WALK_GROUP(2) MRAG_WALK_GROUP(3)
+                    MRAG_WALK_GROUP(4) MRAG_WALK_GROUP(5) MRAG_WALK_GROUP(6) MRAG_WALK_GROUP(7)
+#undef MRAG_WALK_GROUP
                     }
                 }
             }
             m = mn;
         }
 
+        if (a.stats) {
+            // [0] tiles (per select warp), [1] groups of 8 rows walked, [2] keys appended (uncompacted tiles only),
+            // [3] buffer compactions
+            if (lane == 0) { atomicAdd(a.stats + 0, (unsigned long long)n_tiles); atomicAdd(a.stats + 1, (unsigned long long)n_groups);
+                             atomicAdd(a.stats + 3, (unsigned long long)n_compact); }
+            if (n_keys) atomicAdd(a.stats + 2, (unsigned long long)n_keys);
+        }
         // ---- this CTA's sorted candidate list per query
         __syncwarp();
-        for (int L = 0; L < 32; ++L) {
-            const int qL = quarter * 32 + L;
-            if (qL >= a.nq) break;
-            const int n = __shfl_sync(kFull, st.cnt, L);
-            uint64_t* b = cand_warp + size_t(L) * a.cap;
-            warp_rank_select(b, n, a.kp, lane);
-            uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
-            const int have = n < a.k ? n : a.k;
-            for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
+        if constexpr (KREG > 0) {
+            if (live) {
+                uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
+                // keys stay unique across CTAs and slots (the merge's radix select relies on it); 0 = empty
+#pragma unroll
+                for (int i = 0; i < KREG; ++i)
+                    if (i >= top_off) out[i - top_off] = top[i] ? (uint64_t(top[i]) << 32) | uint64_t((blockIdx.x << 8) | unsigned(i)) : 0ull;
+                for (int i = a.k; i < a.kp; ++i) out[i] = 0ull;
+            }
+        } else {
+            for (int L = 0; L < 32; ++L) {
+                const int qL = quarter * 32 + L;
+                if (qL >= a.nq) break;
+                const int n = __shfl_sync(kFull, st.cnt, L);
+                uint64_t* b = cand_warp + size_t(L) * a.cap;
+                warp_rank_select_n(b, n, a.kp, lane);
+                uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
+                const int have = n < a.k ? n : a.k;
+                for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
+            }
         }
     }
 

@@ -38,10 +38,74 @@ struct MergeArgs {
     const int* qcount;
 };
 
+// Block-cooperative top-k of n UNIQUE non-zero keys in s[0..n): afterwards s[0..min(n,k)) holds the k largest,
+// descending; returns min(n, k).  A radix select (8 bits per pass from the top) finds the k-th largest key, the
+// k keys >= it are gathered and sorted -- ~10x cheaper than sorting thousands of keys to keep a few dozen.
+// k <= 128.  hist: 256 counters, small: 128 keys, misc: 4 ints (all shared memory).  All threads must call.
+MRAG_DEVINL int block_topk(uint64_t* s, int n, int k, unsigned* hist, uint64_t* small, int* misc) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (n > k) {
+        uint64_t prefix = 0;
+        int krem = k;
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            const uint64_t hi_mask = pass ? (~0ull << (shift + 8)) : 0ull;
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += nt) {
+                const uint64_t key = s[i];
+                if ((key & hi_mask) == prefix) atomicAdd(&hist[unsigned(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // lane l owns bins 255-8l .. 248-8l (descending); find the bin holding the krem-th largest
+                unsigned c[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * tid - j]; sum += c[j]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(kFull, incl, o);
+                    if (tid >= o) incl += v;
+                }
+                unsigned before = incl - sum;
+                if (before < unsigned(krem) && unsigned(krem) <= incl) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (before < unsigned(krem) && unsigned(krem) <= before + c[j]) { misc[0] = 255 - 8 * tid - j; misc[1] = krem - int(before); }
+                        before += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= uint64_t(unsigned(misc[0])) << shift;
+            krem = misc[1];
+        }
+        if (tid == 0) misc[2] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            const uint64_t key = s[i];
+            if (key >= prefix) small[atomicAdd(&misc[2], 1)] = key;       // exactly k keys (they are unique)
+        }
+        __syncthreads();
+        for (int i = tid; i < k; i += nt) s[i] = small[i];
+        n = k;
+        __syncthreads();
+    }
+    const int n2 = next_pow2(n < 2 ? 2 : n);
+    for (int i = n + tid; i < n2; i += nt) s[i] = 0;
+    __syncthreads();
+    block_sort_desc(s, n2);
+    return n;
+}
+
 // One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
 // alone already holds k keys >= T), so only the survivors are gathered and sorted.
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs a) {
     __shared__ uint64_t s[kMergeSlots];
+    __shared__ uint64_t s_small[128];
+    __shared__ unsigned s_hist[256];
+    __shared__ int s_misc[4];
     __shared__ unsigned long long s_T;
     __shared__ int s_cnt;
     const int tid = threadIdx.x;
@@ -67,14 +131,10 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     while (done < total) {
         int kept = s_cnt;                       // uniform: read between two barriers
         __syncthreads();
-        if (kept > kMergeSlots / 2) {           // make room: sort what we have, keep the best k
-            int n2 = next_pow2(kept);
-            for (int i = kept + tid; i < n2; i += kMergeThreads) s[i] = 0;
+        if (kept > kMergeSlots / 2) {           // make room: keep the best k of what we have
+            kept = block_topk(s, kept, a.k, s_hist, s_small, s_misc);
+            if (tid == 0) s_cnt = kept;
             __syncthreads();
-            block_sort_desc(s, n2);
-            if (tid == 0) s_cnt = a.k;
-            __syncthreads();
-            kept = a.k;
         }
         int room = kMergeSlots - kept;
         int take = total - done < room ? total - done : room;
@@ -85,12 +145,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
         done += take;
         __syncthreads();
     }
-    int kept = s_cnt;
-    int n2 = next_pow2(kept < 2 ? 2 : kept);
-    for (int i = kept + tid; i < n2; i += kMergeThreads) s[i] = 0;
-    __syncthreads();
-    block_sort_desc(s, n2);
-    const int got = kept < a.k ? kept : a.k;
+    const int got = block_topk(s, s_cnt, a.k, s_hist, s_small, s_misc);
     if (a.part_out) {
         uint64_t* out = a.part_out + (size_t(q) * gridDim.y + blockIdx.y) * a.kp;
         for (int i = tid; i < a.kp; i += kMergeThreads) out[i] = (i < got) ? s[i] : 0ull;
