@@ -209,22 +209,24 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
             m = mn;
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        int s = 0, as = 0;
-        uint32_t ph = 0, aph = 0;
-        const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
-        const uint32_t idesc = kMmaIdesc;
-        uint2 m = tile_mask(t_first);
-        for (int64_t t = t_first; t < num_tiles; t += G) {
-            const uint2 mn = tile_mask(t + G);
-            if ((m.x | m.y) != 0u) {
-                mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph, slp);
+        // ================= MMA issuer: ONE elected thread runs the whole loop =================
+        // (the issue loop is the critical path of the kernel -- ncu r1g: ~75 instructions per k-block with a
+        //  per-iteration election; a single-thread loop drops the election, the reconvergence and the warp syncs)
+        if (elect_one()) {
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
+            const uint32_t idesc = kMmaIdesc;
+            uint2 m = tile_mask(t_first);
+            for (int64_t t = t_first; t < num_tiles; t += G) {
+                const uint2 mn = tile_mask(t + G);
+                if ((m.x | m.y) != 0u) {
+                    mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
                     tc_fence_after();
-                    if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[s], ph, slp);
+                        tc_fence_after();
                         const uint64_t bdesc = bdesc0 + uint64_t(s) * (kMmaStageBytes >> 4);
                         const uint32_t a_tmem = tmem_base + uint32_t(kb * (kMmaKBlock / 2));
                         umma_ts_bf16(d_tmem, a_tmem, bdesc, idesc, kb != 0 ? 1u : 0u);
@@ -233,14 +235,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
                         umma_ts_bf16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
                         umma_commit(&empty_bar[s]);
                         if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+                        if (++s == a.stages) { s = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                    if (++as == 2) { as = 0; aph ^= 1u; }
                 }
-                if (++as == 2) { as = 0; aph ^= 1u; }
+                m = mn;
             }
-            m = mn;
         }
+        __syncwarp();
     } else {
         // ================= select (warps 2..5): thread = query =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
