@@ -269,6 +269,38 @@ __device__ __noinline__ SelState select_compact(SelState st, unsigned full, uint
     return st;
 }
 
+// rows 8G .. 8G+7 of the tile: append what beats the threshold; a full buffer is compacted and the walk resumes.
+// (a function template so that every index into sc[] is a compile-time constant: the array must stay in registers)
+template <int G>
+MRAG_DEVINL void walk_group64(const float (&sc)[64], float& thr, SelState& st, uint64_t* mybuf, uint64_t* cand_warp,
+                              int cap, int k, int lane, int64_t r0, uint32_t* gslot, uint64_t ubk,
+                              unsigned long long& n_keys, unsigned long long& n_compact, unsigned long long& n_retry) {
+    const int cnt_before = st.cnt;
+    int c_start = 0;
+    for (;;) {
+        int ovf = 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_start && sc[8 * G + c] > thr) {
+                const uint64_t key = make_key(sc[8 * G + c], uint32_t(r0 + 8 * G + c));
+                if (key < ubk) {
+                    if (st.cnt < cap) mybuf[st.cnt++] = key;
+                    else ovf = min(ovf, c);
+                }
+            }
+        }
+        const unsigned full = __ballot_sync(kFull, st.cnt == cap);
+        if (!full) { n_keys += st.cnt - cnt_before; break; }
+        n_compact += (full >> lane) & 1u;
+        ++n_retry;
+        st = select_compact(st, full, cand_warp, cap, k, lane);
+        if ((full >> lane) & 1u) atomicMax(gslot, f2ord(st.thr_s));
+        thr = fmaxf(thr, st.thr_s);
+        c_start = ovf;
+        if (!__any_sync(kFull, ovf < 8)) break;
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // KREG = 0: candidates go to per-query shared-memory buffers of k + 64 keys, compacted when full
 //           (k up to 128; large shards get their admission bound from a sampling pass first).
@@ -396,21 +428,23 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         }
         stamp(3);
     } else if (warp == 1) {
-        // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
-        int s = 0, as = 0;
-        uint32_t ph = 0, aph = 0;
-        const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
-        uint2 m = tile_mask(t_first);
-        for (int64_t t = t_first; t < num_tiles; t += G) {
-            const uint2 mn = tile_mask(t + G);
-            if ((m.x | m.y) != 0u) {
-                mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph, slp);
+        // ================= MMA issuer: ONE elected thread runs the whole loop =================
+        // (the issue loop is the critical path of the kernel -- ncu r1g: ~75 instructions per k-block with a
+        //  per-iteration election; a single-thread loop drops the election, the reconvergence and the warp syncs)
+        if (elect_one()) {
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
+            uint2 m = tile_mask(t_first);
+            for (int64_t t = t_first; t < num_tiles; t += G) {
+                const uint2 mn = tile_mask(t + G);
+                if ((m.x | m.y) != 0u) {
+                    mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
                     tc_fence_after();
-                    if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[s], ph, slp);
+                        tc_fence_after();
                         const uint64_t bdesc = bdesc0 + uint64_t(s) * (kMmaStageBytes >> 4);
                         const uint32_t a_tmem = tmem_base + uint32_t(kb * (kMmaKBlock / 2));
                         // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of the swizzled B rows
@@ -420,14 +454,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                         umma_ts_bf16(d_tmem, a_tmem + 24, bdesc + 6, kMmaIdesc, 1u);
                         umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
                         if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);   // accumulator ready
+                        if (++s == a.stages) { s = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                    if (++as == 2) { as = 0; aph ^= 1u; }
                 }
-                if (++as == 2) { as = 0; aph ^= 1u; }
+                m = mn;
             }
-            m = mn;
         }
+        __syncwarp();
         stamp(4);
     } else if (!hi_part) {
         // ================= lo epilogue (warps 4,5): TMEM lanes 0..63 -> exchange buffer =================
@@ -503,7 +537,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             if ((m.x | m.y) != 0u) {
                 const int64_t r0 = t * kMmaTileRows;
                 float sc[64];
-                float best = -CUDART_INF_F;
+                float bestg[8];                                      // max of each group of 8 rows
+#pragma unroll
+                for (int g = 0; g < 8; ++g) bestg[g] = -CUDART_INF_F;
                 uint32_t gord;
                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gord) : "l"(gslot) : "memory");
                 mbar_wait(&tfull_bar[as], aph, slp);
@@ -528,7 +564,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                                 const int c = h * 32 + c4 * 4 + i;
                                 const float dot = __uint_as_float(d[c4 * 4 + i]) + xb[c * 64 + qi];
                                 sc[c] = dot * ivv[i] * qinv;
-                                best = fmaxf(best, sc[c]);                       // fmaxf drops NaN
+                                bestg[c >> 3] = fmaxf(bestg[c >> 3], sc[c]);     // fmaxf drops NaN
                             }
                         }
                     }
@@ -542,6 +578,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                     //      only scores strictly above the threshold can enter
                     float thr = fmaxf(st.thr_s, gord ? ord2f(gord - 1u) : -CUDART_INF_F);
                     ++n_tiles;
+                    const float best = fmaxf(fmaxf(fmaxf(bestg[0], bestg[1]), fmaxf(bestg[2], bestg[3])),
+                                             fmaxf(fmaxf(bestg[4], bestg[5]), fmaxf(bestg[6], bestg[7])));
                     if (__any_sync(kFull, best > thr)) {
                         ++n_slow;
                         if constexpr (KREG > 0) {
@@ -573,30 +611,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                             }
                             if (st.thr_s > thr_in) atomicMax(gslot, f2ord(st.thr_s));
                         } else {
-                        const int cnt_before = st.cnt;
-                        int c_start = 0;
-                        for (;;) {
-                            int ovf = 64;
-#pragma unroll
-                            for (int c = 0; c < 64; ++c) {
-                                if (c >= c_start && sc[c] > thr) {
-                                    const uint64_t key = make_key(sc[c], uint32_t(r0 + c));
-                                    if (key < ubk) {
-                                        if (st.cnt < cap) mybuf[st.cnt++] = key;
-                                        else ovf = min(ovf, c);
-                                    }
-                                }
-                            }
-                            const unsigned full = __ballot_sync(kFull, st.cnt == cap);
-                            if (!full) { n_keys += st.cnt - cnt_before; break; }
-                            n_compact += (full >> lane) & 1u;
-                            ++n_retry;
-                            st = select_compact(st, full, cand_warp, cap, a.k, lane);
-                            if ((full >> lane) & 1u) atomicMax(gslot, f2ord(st.thr_s));
-                            thr = fmaxf(thr, st.thr_s);
-                            c_start = ovf;
-                            if (!__any_sync(kFull, ovf < 64)) break;
-                        }
+                        // the warp walks only the groups of 8 rows in which some query admits a row
+#define MRAG_WALK_GROUP(G)                                                                                          \
+                        if (__any_sync(kFull, bestg[G] > thr))                                                      \
+                            walk_group64<G>(sc, thr, st, mybuf, cand_warp, cap, a.k, lane, r0, gslot, ubk, n_keys, n_compact, n_retry);
+                        MRAG_WALK_GROUP(0) MRAG_WALK_GROUP(1) MRAG_WALK_GROUP(2) MRAG_WALK_GROUP(3)
+                        MRAG_WALK_GROUP(4) MRAG_WALK_GROUP(5) MRAG_WALK_GROUP(6) MRAG_WALK_GROUP(7)
+#undef MRAG_WALK_GROUP
                         }
                     }
                 } else {
