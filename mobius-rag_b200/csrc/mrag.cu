@@ -590,13 +590,13 @@ static int mma_stages_for(int cap) {
     return int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
 }
 
-template <int KREG>
+template <int KREG, bool SO = false>
 static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute(scan_mma_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute((scan_mma_kernel<KREG, SO>), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
     if (KREG > 0) a.cap = 0;                   // candidates live in registers: no shared-memory buffers
@@ -605,7 +605,7 @@ static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStrea
     for (int q0 = 0; q0 < nq; q0 += kMmaQueries) {
         a.q0 = q0;
         a.nq = std::min(kMmaQueries, nq - q0);
-        scan_mma_kernel<KREG><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        scan_mma_kernel<KREG, SO><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
         LAUNCHED();
     }
     return MRAG_OK;
@@ -901,13 +901,13 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 MmaArgs sa = a;
                 sa.stats = nullptr;
                 sa.tstamps = ts_sample;
-                const int per_cta = kr <= kMmaRegK ? 2 : (kr <= 64 ? 4 : 8);
+                const int per_cta = kr <= 64 ? 4 : 8;
                 sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
                 const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
                 sa.P = sgrid;
                 sa.k = std::min(kr, kMmaRegK);
                 sa.kp = kMmaRegK;
-                int rc = run_scan_mma(x, sa, nq, sgrid, /*reg_topk=*/true, s);
+                int rc = launch_scan_mma<kMmaRegK, true>(x, sa, nq, sgrid, s);     // scores only
                 if (rc != MRAG_OK) return rc;
                 MergeArgs sm{};
                 sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kr; sm.lk = sa.k; sm.k_total = k; sm.k_off = k_off;

@@ -309,7 +309,9 @@ MRAG_DEVINL void walk_group64(const float (&sc)[64], float& thr, SelState& st, u
 //           ~k ln(n/k) insertions per query and CTA, no buffers, no compaction, no sampling pass.
 constexpr int kMmaRegK = 16;
 
-template <int KREG>
+// SO (score only, KREG > 0): the sampling pass needs a bound, not rows: 32-bit orderable scores in the
+//           registers (half the insertion work); the lists it writes carry synthetic unique low words.
+template <int KREG, bool SO = false>
 __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     // SWIZZLE_128B tiles need 1024-byte alignment; stay in the shared address space (no integer casts)
@@ -521,10 +523,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         // register-resident sorted top-k (KREG mode): the k live slots are the LAST k of top[], the
         // slots before them hold an unbeatable sentinel, so the k-th best is always top[KREG-1]
         // (every index stays a compile-time constant: the array must not fall into local memory)
-        uint64_t top[KREG > 0 ? KREG : 1];
+        uint64_t top[(KREG > 0 && !SO) ? KREG : 1];
+        uint32_t tops[(KREG > 0 && SO) ? KREG : 1];
         const int top_off = (KREG > 0 ? KREG : 1) - a.k;
 #pragma unroll
-        for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) top[i] = (i < top_off) ? ~0ull : 0ull;
+        for (int i = 0; i < ((KREG > 0 && !SO) ? KREG : 1); ++i) top[i] = (i < top_off) ? ~0ull : 0ull;
+#pragma unroll
+        for (int i = 0; i < ((KREG > 0 && SO) ? KREG : 1); ++i) tops[i] = (i < top_off) ? ~0u : 0u;
+        const uint32_t ub_ord = uint32_t(ubk >> 32);            // SO: rows scoring >= the bound's score are left out
         // Cross-CTA bound: once ANY CTA holds k keys with score >= g, a row scoring below g cannot be
         // in the global top-k.  Rows scoring exactly g may still win a tie by row index, so the bound
         // admits s >= g, i.e. s > prev(g).  Read relaxed once per tile, raised after each compaction.
@@ -582,7 +588,26 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                                              fmaxf(fmaxf(bestg[4], bestg[5]), fmaxf(bestg[6], bestg[7])));
                     if (__any_sync(kFull, best > thr)) {
                         ++n_slow;
-                        if constexpr (KREG > 0) {
+                        if constexpr (KREG > 0 && SO) {
+                            const float thr_in = st.thr_s;
+#pragma unroll
+                            for (int c = 0; c < 64; ++c) {
+                                const bool ins = sc[c] > thr;
+                                if (__any_sync(kFull, ins)) {                    // warp-uniform
+                                    uint32_t key = ins ? f2ord(sc[c]) : 0u;
+                                    if (key >= ub_ord) key = 0u;
+#pragma unroll
+                                    for (int i = 0; i < KREG; ++i) {             // sorted insertion, a zero key falls through
+                                        const uint32_t hi = max(key, tops[i]);
+                                        key = min(key, tops[i]);
+                                        tops[i] = hi;
+                                    }
+                                    const uint32_t kth = tops[KREG - 1];
+                                    if (kth) { st.thr_s = ord2f(kth); thr = fmaxf(thr, st.thr_s); }
+                                }
+                            }
+                            if (st.thr_s > thr_in) atomicMax(gslot, f2ord(st.thr_s));
+                        } else if constexpr (KREG > 0) {
                             const float thr_in = st.thr_s;
 #pragma unroll
                             for (int c = 0; c < 64; ++c) {
@@ -639,9 +664,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         if constexpr (KREG > 0) {
             if (live) {
                 uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
+                if constexpr (SO) {
+                    // keys stay unique across CTAs and slots (the merge's radix select relies on it); 0 = empty
 #pragma unroll
-                for (int i = 0; i < KREG; ++i)
-                    if (i >= top_off) out[i - top_off] = top[i];
+                    for (int i = 0; i < KREG; ++i)
+                        if (i >= top_off) out[i - top_off] = tops[i] ? (uint64_t(tops[i]) << 32) | uint64_t((blockIdx.x << 8) | unsigned(i)) : 0ull;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KREG; ++i)
+                        if (i >= top_off) out[i - top_off] = top[i];
+                }
                 for (int i = a.k; i < a.kp; ++i) out[i] = 0ull;
             }
         } else {
