@@ -841,7 +841,9 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     //                  + exact rescoring with certificate (k <= 32)
     const bool can_mma = x->has_tmap && x->dtype == MRAG_BF16 && n > 0;
     const bool can_mma128 = x->has_tmap && n > 0 && k <= 32;
-    bool use_mma = can_mma && nq >= 2;
+    // a single query also goes to the tensor-core scan (it streams faster than the CUDA-core kernel) unless a
+    // filter is active: the CUDA-core scan skips masked rows one by one, the tensor-core scan only 64-row tiles
+    bool use_mma = can_mma && (nq >= 2 || !(filter && filter->flags));
     bool use_mma128 = can_mma128 && (x->dtype == MRAG_BF16 ? nq > kMmaQueries : nq >= approx_min_nq());
     if (options & MRAG_OPT_FORCE_GEMV) use_mma = use_mma128 = false;
     if (options & MRAG_OPT_FORCE_MMA) {

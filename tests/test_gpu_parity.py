@@ -469,7 +469,9 @@ def test_mma_default_dispatch_and_limits(oracle):
     idx.search(Q, 10)
     assert idx.last_scan_kind() == "mma"          # batches go to the tensor cores
     idx.search(Q[:1], 10)
-    assert idx.last_scan_kind() == "gemv"         # a single query stays on the streaming CUDA-core scan
+    assert idx.last_scan_kind() == "mma"          # an unfiltered single query too (it streams faster there)
+    idx.search(Q[:1], 10, Filter().doc_eq(3))
+    assert idx.last_scan_kind() == "gemv"         # a filtered single query: the CUDA-core scan skips rows one by one
     idx.close()
     for dtype, dim in (("f32", 768), ("bf16", 1536)):       # outside the tensor-core scan's envelope
         idx = Index(dim, dtype, 0, 100)
