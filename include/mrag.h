@@ -183,6 +183,70 @@ enum {
 int mrag_search(mrag_index* idx, const float* q, int nq, int k, const mrag_filter* filter,
                 float* scores, int64_t* rows, int32_t* counts, uint32_t options, void* stream);
 
+/* --- hybrid rerank (config 5): rerank score fused into the scan --------------------------------
+ *
+ * Replaces, for ONE arm (vector) over ALL rows that pass the filter, the per-candidate loop of
+ * `_rerank` (app/services/corpus_search.py:1909-2297) with `_best_arm_sim` (:1787-1814):
+ *
+ *   sim'  = max(0, (clamp01(cos) - 0.5) * 2)                                   (:1802-1814, :1569)
+ *   cov   = sum_i w_i [phrase_i present] / sum_i w_i                           (:2041-2086)
+ *           present = doc carries the phrase's j-code  OR  phrase in body/meta haystack
+ *   jpd   = min(1, sum_c qcat_c * ccat_c / sum_c qcat_c)                       (:324-377)
+ *   score = (w_sim sim' + w_auth auth + w_len len + w_jpd jpd + w_cov cov) / max_weight   (:2113-2118)
+ *   score *= boost  if a d: phrase code is among the chunk's chunk_d_tags      (:2120-2137)
+ *   drop if cov < floor unless promoted / contact-exact / d-tag matched        (:2183-2247)
+ *
+ * Everything that needs TEXT (substring tests, regexes, lengths) is evaluated once per row by the
+ * host shim when the row is inserted and shipped here as mrag_chunkfeat; the kernels see bits.
+ */
+#define MRAG_PHRASE_WORDS 2     /* phrase dictionary of <= 128 phrases (the query bank's required phrases) */
+#define MRAG_JPD_CATS 11        /* non-empty categories of _JPD_PATTERNS, corpus_search.py:233-309 */
+#define MRAG_JTAG_WORDS 4       /* document j: tag codes < 256 */
+#define MRAG_HYB_MAX_PHRASES 16
+
+typedef struct mrag_chunkfeat {
+    uint64_t phrase_bits[MRAG_PHRASE_WORDS]; /* bit p: dictionary phrase p occurs in the body or meta haystack (:1844-1906) */
+    uint8_t  jpd_hits[MRAG_JPD_CATS];        /* patterns of category c found in the body haystack (:339-349)        */
+    uint8_t  flags;                          /* MRAG_CF_* */
+    float    length_score;                   /* _length_score(text), :1779-1784                                      */
+    uint16_t dtags[4];                       /* codes (>= 1) of the keys of chunk_d_tags, 0 = empty slot, models.py:278-280 */
+} mrag_chunkfeat;                            /* 40 bytes */
+
+enum {
+    MRAG_CF_SHORT_TEXT    = 1u << 0,  /* body haystack has <= 20 words: _classify_jpd scores hits / sqrt(n) (:336-347) */
+    MRAG_CF_CONTACT_VALUE = 1u << 1,  /* _CONTACT_VALUE_RE matches the text (:676-683, :2219-2222)                      */
+    MRAG_CF_PROMOTED      = 1u << 2   /* promoted neighbour / bm25_inherited: exempt from the coverage floor (:2205-2208) */
+};
+
+typedef struct mrag_hybrid_query {
+    int32_t  n_phrases;                              /* required phrases, 0 = no coverage term and no floor       */
+    float    phrase_weight[MRAG_HYB_MAX_PHRASES];    /* selectivity weights (>= 0), :1977-1985                    */
+    int16_t  phrase_bit[MRAG_HYB_MAX_PHRASES];       /* dictionary index of the phrase, -1 = occurs nowhere       */
+    int16_t  phrase_jbit[MRAG_HYB_MAX_PHRASES];      /* doc j-tag bit that gives binary credit, -1 = none (:2055-2063) */
+    uint16_t phrase_dcode[MRAG_HYB_MAX_PHRASES];     /* chunk d-tag code (>= 1) of a d: phrase code, 0 = none (:2124-2133) */
+    float    qcat[MRAG_JPD_CATS];                    /* _classify_jpd(query); all zero = no jpd term (:1952-1953) */
+    float    auth_score[32];                         /* authority code -> _authority_score (:1773-1776); [31] = NULL / unknown */
+    float    w_sim, w_auth, w_len, w_jpd, w_cov;     /* 0.25, 0.10, 0.05, 0.20 | 0, 0.55 | 0  (:2006-2011)        */
+    float    boost;                                  /* CHUNK_TAG_BOOST (config.py:129)                            */
+    float    floor;                                  /* _TAG_COVERAGE_FLOOR (:604)                                 */
+    uint32_t contact_query;                          /* _CONTACT_QUERY_RE matched the query (:1959)                */
+    /* restrict this query to rows whose source_type code is in the set (bit 255 = NULL); all zero = no restriction.
+     * The per-(arm, source_type) decay of :2258-2285 needs each category's own best, so the shim asks for the top
+     * rows of every category separately (one query slot per category) and merges after decaying.                */
+    uint64_t source_type_any[MRAG_SMALL_WORDS];
+} mrag_hybrid_query;
+
+/* per-row text features of rows [first_row, first_row + n) (HOST array) */
+int mrag_set_chunk_features(mrag_index* idx, int64_t first_row, const mrag_chunkfeat* feat, int64_t n);
+/* document j: tag sets as bitsets, n_docs * MRAG_JTAG_WORDS u64 (HOST), like mrag_set_doc_tags */
+int mrag_set_doc_jtags(mrag_index* idx, int64_t first_doc, const uint64_t* bits, int64_t n_docs);
+/* The fused scan: like mrag_search, ordered by rerank score DESC (ties by ascending row) over the rows that
+ * pass `filter` and the coverage floor.  hq: nq entries (HOST).  scores = rerank scores; cos_out (may be NULL)
+ * = clamp01(similarity) of each returned row.  Host buffers only (options: FORCE_* ignored). k <= MRAG_FUSED_K. */
+int mrag_search_hybrid(mrag_index* idx, const float* q, int nq, int k, const mrag_filter* filter,
+                       const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows, int32_t* counts,
+                       void* stream);
+
 /* Global row id offset added to every returned row (shard base for row-sharded corpora). */
 int mrag_set_row_base(mrag_index* idx, int64_t row_base);
 

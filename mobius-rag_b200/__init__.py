@@ -10,6 +10,7 @@ Layout
   table.py         PublishedTable: host half of rag_published_embeddings (ids, text, vocabularies)
   vector_store.py  VectorStore ABC + B200VectorStore + get_vector_store()  (reference: vector_store.py)
   corpus_search.py vector_arm / _vector_arm                                (reference: corpus_search.py:1427)
+  hybrid.py        hybrid rerank fused with the scan (reference: corpus_search.py:1909-2297)
   sharded.py       row-sharded search across GPUs (allgather + k-way merge)
   synth.py         deterministic synthetic corpora / metadata / queries
 """
@@ -17,5 +18,6 @@ from .vector_store import B200VectorStore, NoopVectorStore, VectorStore, get_vec
 from .corpus_search import CorpusFilters, LexiconExpansion, _vector_arm, vector_arm  # noqa: F401
 from .table import PublishedTable  # noqa: F401
 from .index import Filter, Index, make_meta, merge_topk  # noqa: F401
+from .hybrid import HybridTable, hybrid_rerank  # noqa: F401
 
 __version__ = "0.1.0"

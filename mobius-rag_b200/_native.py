@@ -19,6 +19,8 @@ MRAG_CODE_NONE = 0xFFFF
 F_PAYER, F_STATE, F_PROGRAM, F_AUTHORITY, F_SOURCE_TYPE = 1, 2, 4, 8, 16
 F_DOC_EQ, F_DOC_POOL, F_TAG_STRICT, F_TAG_RELAXED = 32, 64, 128, 256
 OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC, OPT_FORCE_MMA128 = 1, 2, 4, 8, 16
+MRAG_PHRASE_WORDS, MRAG_JPD_CATS, MRAG_JTAG_WORDS, MRAG_HYB_MAX_PHRASES = 2, 11, 4, 16
+CF_SHORT_TEXT, CF_CONTACT_VALUE, CF_PROMOTED = 1, 2, 4
 
 EXPORTS = [
     "mrag_create", "mrag_destroy", "mrag_append", "mrag_append_device", "mrag_set_doc_tags",
@@ -26,6 +28,7 @@ EXPORTS = [
     "mrag_search", "mrag_set_row_base", "mrag_merge_topk", "mrag_filter_mask", "mrag_last_kernel_ms",
     "mrag_profile_begin", "mrag_profile_read", "mrag_launch_count", "mrag_last_scan_kind",
     "mrag_last_error", "mrag_version",
+    "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid",
 ]
 
 
@@ -51,6 +54,30 @@ class FilterStruct(C.Structure):
         ("tag_program_any", C.c_uint64 * MRAG_SMALL_WORDS),
         ("tag_payer_any", C.c_uint64 * MRAG_PAYER_WORDS),
         ("tag_any", C.c_uint64 * MRAG_TAG_WORDS),
+    ]
+
+
+class ChunkFeat(C.Structure):
+    """mrag_chunkfeat (40 bytes)."""
+    _fields_ = [
+        ("phrase_bits", C.c_uint64 * MRAG_PHRASE_WORDS), ("jpd_hits", C.c_uint8 * MRAG_JPD_CATS), ("flags", C.c_uint8),
+        ("length_score", C.c_float), ("dtags", C.c_uint16 * 4),
+    ]
+
+
+class HybridQuery(C.Structure):
+    """mrag_hybrid_query."""
+    _fields_ = [
+        ("n_phrases", C.c_int32),
+        ("phrase_weight", C.c_float * MRAG_HYB_MAX_PHRASES),
+        ("phrase_bit", C.c_int16 * MRAG_HYB_MAX_PHRASES),
+        ("phrase_jbit", C.c_int16 * MRAG_HYB_MAX_PHRASES),
+        ("phrase_dcode", C.c_uint16 * MRAG_HYB_MAX_PHRASES),
+        ("qcat", C.c_float * MRAG_JPD_CATS),
+        ("auth_score", C.c_float * 32),
+        ("w_sim", C.c_float), ("w_auth", C.c_float), ("w_len", C.c_float), ("w_jpd", C.c_float), ("w_cov", C.c_float),
+        ("boost", C.c_float), ("floor", C.c_float), ("contact_query", C.c_uint32),
+        ("source_type_any", C.c_uint64 * MRAG_SMALL_WORDS),
     ]
 
 
@@ -117,6 +144,12 @@ def load(build_if_missing: bool = True):
     lib.mrag_profile_read.argtypes = [i32, f32p, i32]
     lib.mrag_launch_count.restype = i64
     lib.mrag_launch_count.argtypes = []
+    lib.mrag_set_chunk_features.restype = i32
+    lib.mrag_set_chunk_features.argtypes = [vp, i64, vp, i64]
+    lib.mrag_set_doc_jtags.restype = i32
+    lib.mrag_set_doc_jtags.argtypes = [vp, i64, vp, i64]
+    lib.mrag_search_hybrid.restype = i32
+    lib.mrag_search_hybrid.argtypes = [vp, vp, i32, i32, C.POINTER(FilterStruct), vp, vp, vp, vp, vp, vp]
     for name in ("mrag_last_scan_kind", "mrag_last_error", "mrag_version"):
         getattr(lib, name).restype = C.c_char_p
         getattr(lib, name).argtypes = []

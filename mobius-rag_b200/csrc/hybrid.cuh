@@ -1,0 +1,133 @@
+// hybrid.cuh -- K5: the rerank score of `_rerank` (app/services/corpus_search.py:1909-2297) fused into the scan.
+//
+// The reference scores <= ~3k candidates per query in a Python loop (substring tests per phrase per chunk).
+// Here every text-dependent test is a bit computed once per row at insert (mrag_chunkfeat), so the score of a
+// (row, query) pair is a few dozen integer / fp32 instructions and can be taken over ALL rows:
+//   hybrid_mask_kernel   the coverage floor (:2183-2247) AND the WHERE mask, per query -> one bitmap per query;
+//                        with required phrases only the few rows that cover them all survive, and the scan
+//                        (scan_gemv.cuh, HYB mode) loads nothing else.
+//   hybrid_score()       sim' / authority / length / jpd / coverage mix and the chunk d-tag boost (:2020-2137),
+//                        called from the scan's epilogue instead of the plain cosine.
+#pragma once
+#include "common.cuh"
+#include "../../include/mrag.h"
+#include <math_constants.h>
+
+namespace mrag {
+
+// number of patterns per category of _JPD_PATTERNS (corpus_search.py:233-309), in dictionary order, empty
+// category ("other_important") left out
+__constant__ float kJpdPatterns[MRAG_JPD_CATS] = {20.f, 13.f, 12.f, 13.f, 8.f, 16.f, 11.f, 6.f, 9.f, 4.f, 19.f};
+
+struct DevHyb {
+    mrag_hybrid_query q;
+    float total_weight;          // sum of phrase weights, or 1 (:1986)
+    float max_weight;            // w_sim + w_auth + w_len + w_jpd + w_cov (:2011)
+    float qcat_sum;              // sum of qcat
+    uint64_t need[MRAG_PHRASE_WORDS];   // dictionary bits of the phrases that can only be present through their bit
+    uint32_t impossible;         // some phrase has neither a dictionary bit nor a j-code: coverage can never be complete
+    uint32_t has_dcodes;         // some phrase carries a d: code (chunk d-tag boost / exemption possible)
+    uint32_t src_restrict;       // source_type_any is not empty
+};
+
+struct HybEval {
+    float cov;
+    bool dtag_match;
+};
+
+MRAG_DEVINL bool has_dtag(const mrag_chunkfeat& f, uint32_t code) {
+    return f.dtags[0] == code || f.dtags[1] == code || f.dtags[2] == code || f.dtags[3] == code;
+}
+
+// coverage and chunk d-tag match of one (row, query) pair.  jt: the document's j-tag words or nullptr.
+MRAG_DEVINL HybEval hybrid_eval(const DevHyb& h, const mrag_chunkfeat& f, const uint64_t* jt) {
+    HybEval e;
+    e.cov = 0.0f;
+    e.dtag_match = false;
+    float acc = 0.0f;
+    for (int i = 0; i < h.q.n_phrases; ++i) {
+        bool present = false;
+        const int jb = h.q.phrase_jbit[i];
+        if (jb >= 0 && jt) present = (jt[jb >> 6] >> (jb & 63)) & 1ull;
+        if (!present) {
+            const int pb = h.q.phrase_bit[i];
+            if (pb >= 0) present = (f.phrase_bits[pb >> 6] >> (pb & 63)) & 1ull;
+        }
+        if (present) acc += h.q.phrase_weight[i];          // same order as the reference's sum: complete coverage is exactly 1
+        const uint32_t dc = h.q.phrase_dcode[i];
+        if (dc != 0u) e.dtag_match = e.dtag_match || has_dtag(f, dc);
+    }
+    if (h.q.n_phrases > 0) e.cov = acc / h.total_weight;
+    return e;
+}
+
+MRAG_DEVINL bool hybrid_keep(const DevHyb& h, const mrag_chunkfeat& f, const HybEval& e) {
+    if (h.q.n_phrases == 0) return true;
+    if (!(e.cov < h.q.floor)) return true;
+    if (f.flags & MRAG_CF_PROMOTED) return true;
+    if (h.q.contact_query && (f.flags & MRAG_CF_CONTACT_VALUE)) return true;
+    return e.dtag_match;
+}
+
+MRAG_DEVINL float hybrid_score(const DevHyb& h, const mrag_chunkfeat& f, const HybEval& e, float cos, uint32_t auth_code) {
+    const float c01 = fminf(1.0f, fmaxf(0.0f, cos));                       // _vector_arm clamp (:1569)
+    const float sim = fmaxf(0.0f, (c01 - 0.5f) * 2.0f);                    // _best_arm_sim (:1808-1810)
+    const float auth = h.q.auth_score[auth_code < 31u ? auth_code : 31u];
+    float jpd = 0.0f;
+    if (h.q.w_jpd > 0.0f) {
+        float num = 0.0f;
+#pragma unroll
+        for (int c = 0; c < MRAG_JPD_CATS; ++c) {
+            const float hits = float(f.jpd_hits[c]);
+            const float den = (f.flags & MRAG_CF_SHORT_TEXT) ? sqrtf(kJpdPatterns[c]) : kJpdPatterns[c];
+            num += h.q.qcat[c] * fminf(1.0f, hits / den);
+        }
+        jpd = fminf(1.0f, num / h.qcat_sum);
+    }
+    const float raw = h.q.w_sim * sim + h.q.w_auth * auth + h.q.w_len * f.length_score + h.q.w_jpd * jpd + h.q.w_cov * e.cov;
+    float score = h.max_weight > 0.0f ? raw / h.max_weight : raw;
+    if (e.dtag_match) score *= h.q.boost;
+    return score;
+}
+
+// One thread per row, all queries in a loop (the row's features are read once).  Bit (q, r) = row r passes the
+// WHERE mask and query q's coverage floor.  hmask: [nq][nwords].
+__global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restrict__ hq, int nq, const mrag_chunkfeat* __restrict__ feat,
+                                                         const uint32_t* __restrict__ base_mask, const uint32_t* __restrict__ doc_idx,
+                                                         const uint8_t* __restrict__ source_type,
+                                                         const uint64_t* __restrict__ doc_jtags, int64_t n_jtag_docs, int64_t n,
+                                                         uint32_t* __restrict__ hmask, int64_t nwords) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = r < n;
+    bool base = false;
+    mrag_chunkfeat f;
+    const uint64_t* jt = nullptr;
+    uint32_t src = 0xFFu;
+    if (in_range) {
+        base = (base_mask[r >> 5] >> (r & 31)) & 1u;
+        if (base) {
+            f = feat[r];
+            src = source_type[r];
+            const uint32_t d = doc_idx[r];
+            if (doc_jtags && int64_t(d) < n_jtag_docs) jt = doc_jtags + size_t(d) * MRAG_JTAG_WORDS;
+        }
+    }
+    const bool maybe_exempt = base && ((f.flags & (MRAG_CF_PROMOTED | MRAG_CF_CONTACT_VALUE)) ||
+                                       (f.dtags[0] | f.dtags[1] | f.dtags[2] | f.dtags[3]) != 0u);
+    for (int q = 0; q < nq; ++q) {
+        const DevHyb& h = hq[q];
+        bool keep = base;
+        if (keep && h.src_restrict) keep = (h.q.source_type_any[src >> 6] >> (src & 63)) & 1ull;
+        if (keep && h.q.n_phrases > 0) {
+            // quick reject: a phrase that only its dictionary bit can satisfy is missing, and no exemption can apply
+            const bool bits_ok = !h.impossible && (f.phrase_bits[0] & h.need[0]) == h.need[0] && (f.phrase_bits[1] & h.need[1]) == h.need[1];
+            if (!bits_ok && !maybe_exempt) keep = false;
+            else keep = hybrid_keep(h, f, hybrid_eval(h, f, jt));
+        }
+        const uint32_t word = __ballot_sync(kFull, keep);
+        if (lane == 0 && (r >> 5) < nwords) hmask[size_t(q) * nwords + (r >> 5)] = word;
+    }
+}
+
+}  // namespace mrag

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -115,12 +116,14 @@ struct Workspace {
     DevBuf<float> cscores;
     DevBuf<uint64_t> ckeys;
     DevBuf<int> fb;                 // [0] count, [1..] query list of the exact fallback
+    DevBuf<DevHyb> hyb;             // hybrid search: per-query parameters
+    DevBuf<uint32_t> hmask;         // hybrid search: per-query row bitmaps
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); ub.release();
-        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); flags.release(); npass.release(); stats.release();
+        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -140,6 +143,9 @@ struct mrag_index {
     MetaCols cols{};
     uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
     int64_t n_tag_docs = 0, tag_docs_cap = 0;
+    mrag_chunkfeat* feat = nullptr;     // [capacity] text features of the hybrid rerank (allocated on first use, zero = none)
+    uint64_t* doc_jtags = nullptr;      // [jtag_docs_cap][MRAG_JTAG_WORDS]
+    int64_t n_jtag_docs = 0, jtag_docs_cap = 0;
     CUtensorMap tmap;                   // bf16 rows (or the shadow) as a 2-D tensor, 64x64 boxes, SWIZZLE_128B
     bool has_tmap = false;
     cudaStream_t wstream = nullptr;     // write-side stream
@@ -285,6 +291,8 @@ extern "C" int mrag_destroy(mrag_index* x) {
     if (x->cols.source_type) cudaFree(x->cols.source_type);
     if (x->cols.valid) cudaFree(x->cols.valid);
     if (x->doc_tags) cudaFree(x->doc_tags);
+    if (x->feat) cudaFree(x->feat);
+    if (x->doc_jtags) cudaFree(x->doc_jtags);
     if (x->wstream) cudaStreamDestroy(x->wstream);
     t_last_valid = false;
     delete x;
@@ -541,27 +549,27 @@ static int build_mask(mrag_index* x, Workspace* w, const mrag_filter* f, int64_t
 // ------------------------------------------------------------------------------------------
 static const int kMaxSmem = 232448;   // 227 KB
 
-template <int DT, int NQ>
+template <int DT, int NQ, int HYB = 0>
 static int launch_gemv(const ScanArgs& a, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = gemv_smem_bytes(NQ, a.ld, a.kp);
+    const size_t smem = gemv_smem_bytes(NQ, a.ld, a.kp, HYB != 0);
     if (smem > size_t(kMaxSmem))
         return fail(MRAG_ERR_ARG, "scan: %zu B of shared memory needed (dim too large for k)", smem);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute(scan_gemv_kernel<DT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute((scan_gemv_kernel<DT, NQ, HYB>), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
-    scan_gemv_kernel<DT, NQ><<<grid, kGemvThreads, smem, s>>>(a);
+    scan_gemv_kernel<DT, NQ, HYB><<<grid, kGemvThreads, smem, s>>>(a);
     LAUNCHED();
     return MRAG_OK;
 }
 
-static int gemv_nq_for(int nq, int ld, int kp) {
+static int gemv_nq_for(int nq, int ld, int kp, bool hyb = false) {
     // widest query group whose buffers fit in shared memory
     for (int g : {4, 2, 1})
-        if ((nq >= g || g == 1) && gemv_smem_bytes(g, ld, kp) <= size_t(kMaxSmem)) return g;
+        if ((nq >= g || g == 1) && gemv_smem_bytes(g, ld, kp, hyb) <= size_t(kMaxSmem)) return g;
     return 1;
 }
 
@@ -1005,6 +1013,199 @@ extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const m
     t_last_ev = *ev;
     t_last_valid = (rc == MRAG_OK);
     release_ws(x, w, (rc == MRAG_OK && no_sync) ? s : nullptr);
+    return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// hybrid rerank (K5)
+// ------------------------------------------------------------------------------------------
+extern "C" int mrag_set_chunk_features(mrag_index* x, int64_t first_row, const mrag_chunkfeat* feat, int64_t n) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_chunk_features: null index");
+    if (first_row < 0 || n < 0) return fail(MRAG_ERR_ARG, "mrag_set_chunk_features: negative range");
+    if (n == 0) return MRAG_OK;
+    if (!feat) return fail(MRAG_ERR_ARG, "mrag_set_chunk_features: feat is null");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    if (first_row + n > x->size) return fail(MRAG_ERR_ARG, "mrag_set_chunk_features: rows [%lld, %lld) beyond size %lld",
+                                             (long long)first_row, (long long)(first_row + n), (long long)x->size);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_set_chunk_features: cudaSetDevice failed");
+    if (!x->feat) {
+        const int64_t cap32 = ceil_div(x->capacity, 32) * 32;
+        CU(cudaMalloc(&x->feat, size_t(cap32) * sizeof(mrag_chunkfeat)));
+        CU(cudaMemsetAsync(x->feat, 0, size_t(cap32) * sizeof(mrag_chunkfeat), x->wstream));   // all-zero = no features
+    }
+    CU(cudaMemcpyAsync(x->feat + first_row, feat, size_t(n) * sizeof(mrag_chunkfeat), cudaMemcpyHostToDevice, x->wstream));
+    CU(cudaStreamSynchronize(x->wstream));
+    return MRAG_OK;
+}
+
+extern "C" int mrag_set_doc_jtags(mrag_index* x, int64_t first_doc, const uint64_t* bits, int64_t n_docs) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_doc_jtags: null index");
+    if (first_doc < 0 || n_docs < 0) return fail(MRAG_ERR_ARG, "mrag_set_doc_jtags: negative range");
+    if (n_docs == 0) return MRAG_OK;
+    if (!bits) return fail(MRAG_ERR_ARG, "mrag_set_doc_jtags: bits is null");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_set_doc_jtags: cudaSetDevice failed");
+    const int64_t need = first_doc + n_docs;
+    if (need > x->jtag_docs_cap) {
+        int64_t cap = std::max<int64_t>(need + need / 2, 1024);
+        uint64_t* p = nullptr;
+        CU(cudaMalloc(&p, size_t(cap) * MRAG_JTAG_WORDS * 8));
+        CU(cudaMemsetAsync(p, 0, size_t(cap) * MRAG_JTAG_WORDS * 8, x->wstream));
+        if (x->doc_jtags) {
+            CU(cudaMemcpyAsync(p, x->doc_jtags, size_t(x->n_jtag_docs) * MRAG_JTAG_WORDS * 8, cudaMemcpyDeviceToDevice, x->wstream));
+            CU(cudaStreamSynchronize(x->wstream));
+            cudaFree(x->doc_jtags);
+        }
+        x->doc_jtags = p;
+        x->jtag_docs_cap = cap;
+    }
+    CU(cudaMemcpyAsync(x->doc_jtags + size_t(first_doc) * MRAG_JTAG_WORDS, bits, size_t(n_docs) * MRAG_JTAG_WORDS * 8,
+                       cudaMemcpyHostToDevice, x->wstream));
+    CU(cudaStreamSynchronize(x->wstream));
+    x->n_jtag_docs = std::max(x->n_jtag_docs, need);
+    return MRAG_OK;
+}
+
+static void derive_hyb(const mrag_hybrid_query& q, DevHyb* d) {
+    memset(d, 0, sizeof *d);
+    d->q = q;
+    const int np = std::max(0, std::min<int>(q.n_phrases, MRAG_HYB_MAX_PHRASES));
+    d->q.n_phrases = np;
+    float tw = 0.0f;
+    for (int i = 0; i < np; ++i) {
+        tw += q.phrase_weight[i];                       // same left-to-right order as the kernel's partial sums
+        if (q.phrase_dcode[i] != 0) d->has_dcodes = 1;
+        if (q.phrase_weight[i] > 0.0f && q.phrase_jbit[i] < 0) {
+            const int pb = q.phrase_bit[i];
+            if (pb >= 0 && pb < MRAG_PHRASE_WORDS * 64) d->need[pb >> 6] |= 1ull << (pb & 63);
+            else d->impossible = 1;
+        }
+    }
+    d->total_weight = tw != 0.0f ? tw : 1.0f;           // `sum(phrase_weights) or 1.0`
+    d->max_weight = q.w_sim + q.w_auth + q.w_len + q.w_jpd + q.w_cov;
+    float qs = 0.0f;
+    for (int c = 0; c < MRAG_JPD_CATS; ++c) qs += q.qcat[c];
+    d->qcat_sum = qs;
+    if (!(qs > 0.0f)) d->q.w_jpd = 0.0f;
+    for (int i = 0; i < MRAG_SMALL_WORDS; ++i) if (q.source_type_any[i]) d->src_restrict = 1;
+}
+
+static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float* q, int nq, int k, const mrag_filter* filter,
+                         const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows, int32_t* counts,
+                         cudaStream_t s) {
+    const int64_t n = x->size;
+    const int ld = x->ld;
+    const size_t nk = size_t(nq) * k;
+    CU(cudaEventRecord(ev.e[0], s));
+    if (w->qraw.reserve(size_t(nq) * x->dim) || w->qpad.reserve(size_t(nq) * ld) || w->qinv.reserve(size_t(nq)) ||
+        w->flags.reserve(4) || w->counts.reserve(size_t(nq)) || w->scores.reserve(nk) || w->rows.reserve(nk) ||
+        w->cscores.reserve(nk) || w->hyb.reserve(size_t(nq)))
+        return MRAG_ERR_OOM;
+    CU(cudaMemcpyAsync(w->qraw.p, q, size_t(nq) * x->dim * 4, cudaMemcpyHostToDevice, s));
+    query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(w->qraw.p, nq, x->dim, ld, w->qpad.p, w->qinv.p, nullptr, nq);
+    LAUNCHED();
+    std::vector<DevHyb> dh;
+    dh.resize(size_t(nq));
+    for (int i = 0; i < nq; ++i) derive_hyb(hq[i], &dh[size_t(i)]);
+    CU(cudaMemcpyAsync(w->hyb.p, dh.data(), size_t(nq) * sizeof(DevHyb), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));                      // dh is a stack-lifetime host buffer
+    const int kp = std::max(8, host_next_pow2(k));
+    const int64_t nwords = ceil_div(n, 32);
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
+    if (w->part.reserve(size_t(nq) * grid * kp)) return MRAG_ERR_OOM;
+    if (n > 0) {
+        const uint32_t* mask = x->cols.valid;
+        if (filter && filter->flags) {
+            if (w->mask.reserve(size_t(nwords) + 1)) return MRAG_ERR_OOM;
+            int rc = build_mask(x, w, filter, n, w->mask.p, nullptr, s);
+            if (rc != MRAG_OK) return rc;
+            mask = w->mask.p;
+        }
+        if (w->hmask.reserve(size_t(nq) * nwords)) return MRAG_ERR_OOM;
+        hybrid_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(w->hyb.p, nq, x->feat, mask, x->cols.doc_idx, x->cols.source_type, x->doc_jtags,
+                                                                              x->n_jtag_docs, n, w->hmask.p, nwords);
+        LAUNCHED();
+        CU(cudaEventRecord(ev.e[1], s));
+        ScanArgs a{};
+        a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p; a.ub = nullptr;
+        a.part = w->part.p; a.k = k; a.kp = kp; a.P = grid;
+        a.hmask = w->hmask.p; a.hwords = nwords; a.feat = x->feat; a.hyb = w->hyb.p; a.doc_idx = x->cols.doc_idx;
+        a.authority = x->cols.authority; a.doc_jtags = x->doc_jtags; a.n_jtag_docs = x->n_jtag_docs;
+        int q0 = 0;
+        while (q0 < nq) {
+            const int left = nq - q0;
+            const int g = gemv_nq_for(left >= 3 ? 4 : left, ld, kp, true);
+            a.q0 = q0; a.nq = std::min(g, left);
+            a.hyb = w->hyb.p;
+            int rc;
+            if (x->dtype == MRAG_BF16)
+                rc = g == 4 ? launch_gemv<1, 4, 1>(a, grid, s) : g == 2 ? launch_gemv<1, 2, 1>(a, grid, s) : launch_gemv<1, 1, 1>(a, grid, s);
+            else
+                rc = g == 4 ? launch_gemv<0, 4, 1>(a, grid, s) : g == 2 ? launch_gemv<0, 2, 1>(a, grid, s) : launch_gemv<0, 1, 1>(a, grid, s);
+            if (rc != MRAG_OK) return rc;
+            q0 += a.nq;
+        }
+    } else {
+        CU(cudaMemsetAsync(w->part.p, 0, size_t(nq) * grid * kp * 8, s));
+        CU(cudaEventRecord(ev.e[1], s));
+    }
+    CU(cudaEventRecord(ev.e[2], s));
+    MergeArgs m{};
+    m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = k; m.k_total = k; m.k_off = 0;
+    m.scores = w->scores.p; m.rows = w->rows.p; m.counts = w->counts.p; m.row_base = x->row_base; m.no_clamp = 1;
+    int rc = launch_merge(w, m, nq, s);
+    if (rc != MRAG_OK) return rc;
+    if (n > 0) {
+        CosRowsArgs ca{};
+        ca.rows = x->rows; ca.ld = ld; ca.inv_norm = x->inv_norm; ca.q = w->qpad.p; ca.qinv = w->qinv.p;
+        ca.sel_rows = w->rows.p; ca.sel_counts = w->counts.p; ca.row_base = x->row_base; ca.nq = nq; ca.k = k; ca.cos_out = w->cscores.p;
+        const unsigned cb = unsigned(ceil_div(int64_t(nq) * k * 32, 256));
+        if (x->dtype == MRAG_BF16) cos_rows_kernel<1><<<cb, 256, 0, s>>>(ca);
+        else cos_rows_kernel<0><<<cb, 256, 0, s>>>(ca);
+        LAUNCHED();
+    }
+    CU(cudaMemcpyAsync(scores, w->scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(rows, w->rows.p, nk * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(counts, w->counts.p, size_t(nq) * 4, cudaMemcpyDeviceToHost, s));
+    if (cos_out && n > 0) CU(cudaMemcpyAsync(cos_out, w->cscores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ev.e[3], s));
+    ev.recorded = true;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_search_hybrid(mrag_index* x, const float* q, int nq, int k, const mrag_filter* filter,
+                                  const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows,
+                                  int32_t* counts, void* stream) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_search_hybrid: null index");
+    if (nq < 0) return fail(MRAG_ERR_ARG, "mrag_search_hybrid: nq < 0");
+    if (nq == 0) return MRAG_OK;
+    if (nq > 65535) return fail(MRAG_ERR_ARG, "mrag_search_hybrid: nq %d > 65535", nq);
+    if (k < 1 || k > MRAG_FUSED_K) return fail(MRAG_ERR_ARG, "mrag_search_hybrid: k %d not in [1,%d]", k, MRAG_FUSED_K);
+    if (!q || !hq || !scores || !rows || !counts) return fail(MRAG_ERR_ARG, "mrag_search_hybrid: null buffer");
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    if (!x->feat && x->size > 0) return fail(MRAG_ERR_STATE, "mrag_search_hybrid: no chunk features set (mrag_set_chunk_features)");
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_search_hybrid: cudaSetDevice(%d) failed (no CPU path)", x->device);
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    Workspace* w = acquire_ws(x, user);
+    if (!w) return fail(MRAG_ERR_OOM, "mrag_search_hybrid: cannot create a workspace");
+    cudaStream_t s = user ? user : w->own_stream;
+    EventSet* ev = &w->ev;
+    if (t_ring_used < int(t_ring.size()) && t_ring_device == x->device) ev = &t_ring[size_t(t_ring_used++)];
+    int rc = hybrid_locked(x, w, *ev, q, nq, k, filter, hq, scores, cos_out, rows, counts, s);
+    if (ev != &w->ev) { cudaEventRecord(w->ev.e[3], s); w->ev.recorded = true; }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == MRAG_OK && e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_search_hybrid: %s", cudaGetErrorString(e));
+    if (rc != MRAG_OK) cudaGetLastError();
+    if (rc == MRAG_OK && x->size == 0 && cos_out)
+        for (size_t i = 0; i < size_t(nq) * k; ++i) cos_out[i] = NAN;
+    t_last_ev = *ev;
+    t_last_valid = (rc == MRAG_OK);
+    t_last_kind = "gemv_hybrid";
+    release_ws(x, w, nullptr);
     return rc;
 }
 

@@ -69,6 +69,56 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreArgs a) {
     }
 }
 
+// clamp01(cosine) of already selected rows (hybrid search: the rerank score is returned, the similarity beside it)
+struct CosRowsArgs {
+    const void* rows; int ld; const float* inv_norm; const float* q; const float* qinv;
+    const int64_t* sel_rows;     // [nq][k] global row ids (-1 = padding)
+    const int32_t* sel_counts;   // [nq]
+    int64_t row_base;
+    int nq, k;
+    float* cos_out;              // [nq][k]
+};
+
+template <int DT>
+__global__ void __launch_bounds__(256) cos_rows_kernel(const CosRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= int64_t(a.nq) * a.k) return;
+    const int q = int(wid / a.k), j = int(wid - int64_t(q) * a.k);
+    if (j >= a.sel_counts[q]) {
+        if (lane == 0) a.cos_out[wid] = CUDART_NAN_F;
+        return;
+    }
+    const int64_t row = a.sel_rows[wid] - a.row_base;
+    const float* qrow = a.q + size_t(q) * a.ld;
+    float acc = 0.0f;
+    if (DT == 1) {
+        const uint4* x = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.rows) + size_t(row) * a.ld);
+        for (int v = lane; v < a.ld / 8; v += 32) {
+            const uint4 d = __ldg(x + v);
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v);
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v + 1);
+            acc = fmaf(bf16lo(d.x), q0.x, acc); acc = fmaf(bf16hi(d.x), q0.y, acc);
+            acc = fmaf(bf16lo(d.y), q0.z, acc); acc = fmaf(bf16hi(d.y), q0.w, acc);
+            acc = fmaf(bf16lo(d.z), q1.x, acc); acc = fmaf(bf16hi(d.z), q1.y, acc);
+            acc = fmaf(bf16lo(d.w), q1.z, acc); acc = fmaf(bf16hi(d.w), q1.w, acc);
+        }
+    } else {
+        const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.rows) + size_t(row) * a.ld);
+        for (int v = lane; v < a.ld / 4; v += 32) {
+            const float4 d = __ldg(x + v);
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + v);
+            acc = fmaf(d.x, q0.x, acc); acc = fmaf(d.y, q0.y, acc);
+            acc = fmaf(d.z, q0.z, acc); acc = fmaf(d.w, q0.w, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float s = acc * a.inv_norm[row] * a.qinv[q];
+        a.cos_out[wid] = (s == s) ? fminf(1.0f, fmaxf(0.0f, s)) : 1.0f;      // corpus_search.py:1569 (NaN -> 1.0)
+    }
+}
+
 struct FinalizeArgs {
     const uint64_t* keys;        // [nq][kc] exact keys
     const float* cand_scores;    // [nq][kc] approximate scores, descending

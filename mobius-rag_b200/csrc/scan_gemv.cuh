@@ -15,6 +15,7 @@
 // keys per (query, block) -- no N-sized score array ever exists.
 #pragma once
 #include "common.cuh"
+#include "hybrid.cuh"
 
 namespace mrag {
 
@@ -39,10 +40,20 @@ struct ScanArgs {
     // one full pass per group; *qcount == 0 makes the launch a no-op.  q0 / nq are ignored.
     const int* qlist;
     const int* qcount;
+    // hybrid mode (HYB = 1, hybrid.cuh): per-query row bitmaps hmask[query][hwords] replace `mask`, and the
+    // candidate key is built from the rerank score of (row, query) instead of the cosine
+    const uint32_t* hmask;
+    int64_t hwords;
+    const mrag_chunkfeat* feat;
+    const DevHyb* hyb;
+    const uint32_t* doc_idx;
+    const uint8_t* authority;
+    const uint64_t* doc_jtags;
+    int64_t n_jtag_docs;
 };
 
-inline size_t gemv_smem_bytes(int nq_tpl, int ld, int kp) {
-    return size_t(nq_tpl) * ld * 4 + size_t(nq_tpl) * kGemvWarps * (2 * kp) * 8;
+inline size_t gemv_smem_bytes(int nq_tpl, int ld, int kp, bool hyb = false) {
+    return size_t(nq_tpl) * ld * 4 + size_t(nq_tpl) * kGemvWarps * (2 * kp) * 8 + (hyb ? size_t(nq_tpl) * sizeof(DevHyb) : 0);
 }
 
 // element j (0..E-1) of 16-byte vector v lives at  qs[plane(j)][v][j%4]
@@ -50,12 +61,13 @@ template <int DT> struct VecTraits;
 template <> struct VecTraits<0> { static constexpr int E = 4; };   // fp32: 4 elements / 16 B
 template <> struct VecTraits<1> { static constexpr int E = 8; };   // bf16: 8 elements / 16 B
 
-template <int DT, int NQ>
+template <int DT, int NQ, int HYB = 0>
 __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanArgs a) {
     constexpr int E = VecTraits<DT>::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* qs = reinterpret_cast<float*>(smem_raw);
     uint64_t* bufs = reinterpret_cast<uint64_t*>(smem_raw + size_t(NQ) * a.ld * 4);
+    DevHyb* hq = reinterpret_cast<DevHyb*>(smem_raw + size_t(NQ) * a.ld * 4 + size_t(NQ) * kGemvWarps * (2 * a.kp) * 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld;
@@ -85,10 +97,22 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
             }
             qs[dst] = v;
         }
+        if (HYB) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.hyb);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(hq);
+            constexpr int W32 = sizeof(DevHyb) / 4;
+            for (int i = tid; i < nq_here * W32; i += kGemvThreads) {
+                const int qi = i / W32;
+                int src_q = 0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) src_q = (qi == j) ? qid[j] : src_q;
+                dst[i] = src[size_t(src_q) * W32 + (i - qi * W32)];
+            }
+        }
         uint64_t thr[NQ], ubk[NQ];
         int cnt[NQ];
         float qinv[NQ];
-    #pragma unroll
+#pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
             thr[qi] = 0; cnt[qi] = 0;
             ubk[qi] = (a.ub && qi < nq_here) ? a.ub[qid[qi]] : ~0ull;
@@ -101,43 +125,56 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
         const char* base = reinterpret_cast<const char*>(a.rows);
         const size_t row_bytes = size_t(ld) * (DT == 1 ? 2 : 4);
 
+        // row bitmap word w: the WHERE mask, or (hybrid) the union of the group's per-query bitmaps
+        auto load_mask = [&](int64_t ww) -> uint32_t {
+            if (ww >= nwords) return 0u;
+            if (!HYB) return __ldg(a.mask + ww);
+            uint32_t u = 0u;
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi)
+                if (qi < nq_here) u |= __ldg(a.hmask + size_t(qid[qi]) * a.hwords + ww);
+            return u;
+        };
         int64_t w = int64_t(blockIdx.x) * kGemvWarps + warp;
-        uint32_t m_next = (w < nwords) ? __ldg(a.mask + w) : 0u;
+        uint32_t m_next = load_mask(w);
         for (; w < nwords; w += W) {
             uint32_t m = m_next;
-            m_next = (w + W < nwords) ? __ldg(a.mask + w + W) : 0u;
+            m_next = load_mask(w + W);
+            uint32_t mq[NQ];                       // hybrid: this word of every query's own bitmap
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) mq[qi] = (HYB && qi < nq_here && m) ? __ldg(a.hmask + size_t(qid[qi]) * a.hwords + w) : 0u;
             while (m) {
                 uint32_t r[kGemvRows];
                 int nr = 0;
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < kGemvRows; ++j) {
                     if (m) { int b = __ffs(m) - 1; m &= m - 1; r[j] = uint32_t(w * 32 + b); ++nr; }
                     else r[j] = r[0];
                 }
                 float acc[kGemvRows][NQ + 1];
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < kGemvRows; ++j)
-    #pragma unroll
+#pragma unroll
                     for (int x = 0; x <= NQ; ++x) acc[j][x] = 0.0f;
 
                 for (int v0 = 0; v0 < nvec; v0 += kWarp * kGemvVecs) {
                     uint4 d[kGemvRows][kGemvVecs];
-    #pragma unroll
+#pragma unroll
                     for (int c = 0; c < kGemvVecs; ++c) {
                         int v = v0 + c * kWarp + lane;
                         bool ok = v < nvec;
-    #pragma unroll
+#pragma unroll
                         for (int j = 0; j < kGemvRows; ++j) {
                             if (ok && j < nr) d[j][c] = ldg_stream(base + size_t(r[j]) * row_bytes + size_t(v) * 16);
                             else d[j][c] = make_uint4(0, 0, 0, 0);
                         }
                     }
-    #pragma unroll
+#pragma unroll
                     for (int c = 0; c < kGemvVecs; ++c) {
                         int v = v0 + c * kWarp + lane;
                         if (v < nvec) {
                             float x[kGemvRows][E];
-    #pragma unroll
+#pragma unroll
                             for (int j = 0; j < kGemvRows; ++j) {
                                 if (DT == 1) {
                                     x[j][0] = bf16lo(d[j][c].x); x[j][1] = bf16hi(d[j][c].x);
@@ -148,10 +185,10 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
                                     x[j][0] = __uint_as_float(d[j][c].x); x[j][1] = __uint_as_float(d[j][c].y);
                                     x[j][2] = __uint_as_float(d[j][c].z); x[j][3] = __uint_as_float(d[j][c].w);
                                 }
-    #pragma unroll
+#pragma unroll
                                 for (int e = 0; e < E; ++e) acc[j][NQ] = fmaf(x[j][e], x[j][e], acc[j][NQ]);
                             }
-    #pragma unroll
+#pragma unroll
                             for (int qi = 0; qi < NQ; ++qi) {
                                 float qv[E];
                                 const float4 q0v = *reinterpret_cast<const float4*>(qs + qi * ld + v * 4);
@@ -160,31 +197,46 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
                                     const float4 q1v = *reinterpret_cast<const float4*>(qs + qi * ld + (ld >> 1) + v * 4);
                                     qv[4 % E] = q1v.x; qv[5 % E] = q1v.y; qv[6 % E] = q1v.z; qv[7 % E] = q1v.w;
                                 }
-    #pragma unroll
+#pragma unroll
                                 for (int j = 0; j < kGemvRows; ++j)
-    #pragma unroll
+#pragma unroll
                                     for (int e = 0; e < E; ++e) acc[j][qi] = fmaf(x[j][e], qv[e], acc[j][qi]);
                             }
                         }
                     }
                 }
                 // ---- finish the sums: every lane ends up with every total
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < kGemvRows; ++j)
-    #pragma unroll
+#pragma unroll
                     for (int x = 0; x <= NQ; ++x) acc[j][x] = warp_sum(acc[j][x]);
 
                 // ---- normalise and select (warp uniform)
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < kGemvRows; ++j) {
                     if (j >= nr) break;
                     const float nx = acc[j][NQ];
-                    if (!(nx > 0.0f)) continue;             // zero-norm row: similarity is NaN (NaN tail pass)
+                    if (!HYB && !(nx > 0.0f)) continue;     // zero-norm row: similarity is NaN (NaN tail pass)
                     const float inv = rsqrtf(nx);
-    #pragma unroll
+                    mrag_chunkfeat f;
+                    const uint64_t* jt = nullptr;
+                    uint32_t auth_code = 31u;
+                    if (HYB) {
+                        f = a.feat[r[j]];
+                        auth_code = a.authority[r[j]];
+                        const uint32_t d = a.doc_idx[r[j]];
+                        if (a.doc_jtags && int64_t(d) < a.n_jtag_docs) jt = a.doc_jtags + size_t(d) * MRAG_JTAG_WORDS;
+                    }
+#pragma unroll
                     for (int qi = 0; qi < NQ; ++qi) {
                         if (qi >= nq_here) break;
-                        const float s = acc[j][qi] * inv * qinv[qi];
+                        float s = (nx > 0.0f) ? acc[j][qi] * inv * qinv[qi] : CUDART_NAN_F;
+                        if (HYB) {
+                            if (!((mq[qi] >> (r[j] & 31u)) & 1u)) continue;       // filtered out or below this query's coverage floor
+                            // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
+                            const float c01 = (s == s) ? s : 1.0f;
+                            s = hybrid_score(hq[qi], f, hybrid_eval(hq[qi], f, jt), c01, auth_code);
+                        }
                         if (!(s == s)) continue;            // zero-norm query
                         const uint64_t key = make_key(s, r[j]);
                         if (key > thr[qi] && key < ubk[qi]) {
@@ -203,7 +255,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
         }
 
         // ---- block merge: clear the unused tail of every warp buffer, sort the block's buffers together
-    #pragma unroll
+#pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
             uint64_t* b = bufs + size_t(qi * kGemvWarps + warp) * cap;
             for (int i = cnt[qi] + lane; i < cap; i += kWarp) b[i] = 0;

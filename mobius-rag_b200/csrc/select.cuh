@@ -36,6 +36,7 @@ struct MergeArgs {
     // exact-fallback mode: block b serves query qlist[b] and exits if b >= *qcount
     const int* qlist;
     const int* qcount;
+    int no_clamp;           // hybrid rerank scores are not cosines: do not clamp them to [-1, 1]
 };
 
 // Block-cooperative top-k of n UNIQUE non-zero keys in s[0..n): afterwards s[0..min(n,k)) holds the k largest,
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
         if (i < got) {
             uint64_t key = s[i];
             float sc = key_score(key);
-            sc = fminf(1.0f, fmaxf(-1.0f, sc));          // pgvector "keep in range"
+            if (!a.no_clamp) sc = fminf(1.0f, fmaxf(-1.0f, sc));          // pgvector "keep in range"
             a.scores[o] = sc;
             a.rows[o] = int64_t(key_row(key)) + a.row_base;
         } else {

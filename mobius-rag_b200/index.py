@@ -12,6 +12,12 @@ import numpy as np
 
 from . import _native as N
 
+FEAT_DTYPE = np.dtype([
+    ("phrase_bits", "<u8", (N.MRAG_PHRASE_WORDS,)), ("jpd_hits", "u1", (N.MRAG_JPD_CATS,)), ("flags", "u1"),
+    ("length_score", "<f4"), ("dtags", "<u2", (4,)),
+])
+assert FEAT_DTYPE.itemsize == C.sizeof(N.ChunkFeat) == 40
+
 META_DTYPE = np.dtype([
     ("doc_idx", "<u4"), ("payer", "<u2"), ("state", "u1"), ("program", "u1"),
     ("authority", "u1"), ("source_type", "u1"), ("valid", "u1"), ("reserved", "u1"),
@@ -190,6 +196,37 @@ class Index:
         if bits.ndim != 2 or bits.shape[1] != N.MRAG_TAG_WORDS:
             raise ValueError(f"bits must be [n_docs, {N.MRAG_TAG_WORDS}] uint64")
         N.check(self._lib.mrag_set_doc_tags(self._h, int(first_doc), bits.ctypes.data, bits.shape[0]))
+
+    def set_chunk_features(self, first_row: int, feat: np.ndarray) -> None:
+        """Per-row text features of the hybrid rerank (FEAT_DTYPE array)."""
+        feat = np.ascontiguousarray(feat)
+        if feat.dtype != FEAT_DTYPE or feat.ndim != 1:
+            raise ValueError("feat must be a 1-D FEAT_DTYPE array")
+        N.check(self._lib.mrag_set_chunk_features(self._h, int(first_row), feat.ctypes.data, feat.shape[0]))
+
+    def set_doc_jtags(self, first_doc: int, bits: np.ndarray) -> None:
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        if bits.ndim != 2 or bits.shape[1] != N.MRAG_JTAG_WORDS:
+            raise ValueError(f"bits must be [n_docs, {N.MRAG_JTAG_WORDS}] uint64")
+        N.check(self._lib.mrag_set_doc_jtags(self._h, int(first_doc), bits.ctypes.data, bits.shape[0]))
+
+    def search_hybrid(self, Q: np.ndarray, k: int, hq, flt: "Filter | None" = None):
+        """Fused hybrid rerank.  hq: ctypes array of N.HybridQuery (one per query).
+        Returns (rerank scores f32 [nq,k], clamp01(cos) f32 [nq,k], rows i64 [nq,k], counts i32 [nq])."""
+        Q = np.ascontiguousarray(np.atleast_2d(np.asarray(Q, dtype=np.float32)))
+        if Q.shape[1] != self.dim:
+            raise ValueError(f"query dim {Q.shape[1]} != index dim {self.dim}")
+        nq = Q.shape[0]
+        if len(hq) != nq:
+            raise ValueError("one HybridQuery per query")
+        scores = np.empty((nq, k), dtype=np.float32)
+        cos = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        counts = np.zeros(nq, dtype=np.int32)
+        N.check(self._lib.mrag_search_hybrid(self._h, Q.ctypes.data, nq, int(k), flt.ref() if flt is not None else None,
+                                             C.addressof(hq), scores.ctypes.data, cos.ctypes.data, rows.ctypes.data,
+                                             counts.ctypes.data, None))
+        return scores, cos, rows, counts
 
     def tombstone_doc(self, doc_idx: int) -> int:
         n = C.c_int64(0)

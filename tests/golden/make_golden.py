@@ -21,6 +21,7 @@ dict shape.  tests/test_golden.py replays them against the oracle (CPU) and the 
 from __future__ import annotations
 
 import asyncio
+import gzip
 import json
 import os
 import sys
@@ -34,6 +35,12 @@ REF = "/root/reference"
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, HERE)
+
+
+def dump_json(obj, name):
+    """Fixtures are gzip-compressed JSON (mtime 0 so regeneration is byte-stable)."""
+    with gzip.GzipFile(os.path.join(HERE, name + ".gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(obj, separators=(",", ":")).encode())
 
 
 def install_stubs():
@@ -86,6 +93,143 @@ class FakeSession:
 
     async def __aexit__(self, *a):
         return False
+
+
+PHRASE_POOL = [
+    "prior authorization", "sunshine health", "timely filing", "appeal", "medical records", "molina healthcare",
+    "behavioral health", "provider services", "claims submission", "credentialing", "telehealth", "phone",
+    "peer support", "targeted case management", "florida medicaid", "denial",
+]
+FILLER = ("the plan requires that providers follow the documented process for each covered service and retain "
+          "supporting notes for review by the health plan within the stated period of time").split()
+
+
+def hybrid_table(n=900, dim=32, seed=5):
+    """A small text-rich table for the `_rerank` fixtures: bodies assembled from filler words and pool
+    phrases, varied lengths, some phone numbers, chunk d-tags, document d/j/p tags."""
+    rng = np.random.default_rng(seed)
+    n_docs = 60
+    doc_of = np.sort(rng.integers(0, n_docs, size=n))
+    payers = ["Sunshine Health", "Molina Healthcare", "AHCA", "Aetna", None]
+    auths = ["contract_source_of_truth", "payer_website", "operational_suggested", "payer_policy", "fyi_not_citable", None, "Mystery"]
+    dkeys = ["utilization_management.prior_authorization", "claims.timely_filing", "claims.appeals", "benefits.behavioral_health"]
+    jkeys = ["payor.sunshine_health", "payor.molina_healthcare", "state.fl", "program.medicaid"]
+    docs = []
+    for d in range(n_docs):
+        payer = payers[int(rng.integers(0, len(payers)))]
+        docs.append({
+            "document_id": f"00000000-0000-4000-8000-{d:012d}",
+            "document_payer": payer, "document_state": ["FL", "TX", None][int(rng.integers(0, 3))],
+            "document_program": ["Medicaid", "Medicare Advantage", None][int(rng.integers(0, 3))],
+            "document_authority_level": auths[int(rng.integers(0, len(auths)))],
+            "document_display_name": ["", f"{payer or 'General'} Provider Manual {d}", "Timely Filing and Appeals Guide"][int(rng.integers(0, 3))],
+            "document_filename": [f"FL_SunshineHealth_Caid_PAReq_{d}.pdf", f"molina-healthcare_behavioral-health_{d}.pdf", f"doc_{d}.pdf"][int(rng.integers(0, 3))],
+            "d_tags": [k for k in dkeys if rng.random() < 0.25], "j_tags": [k for k in jkeys if rng.random() < 0.3],
+            "p_tags": ["process.claims_submission"] if rng.random() < 0.2 else [],
+            "has_tags_row": bool(rng.random() < 0.8),
+        })
+    rows = []
+    X = rng.standard_normal((n, dim)).astype(np.float32) * np.exp(0.25 * rng.standard_normal((n, 1))).astype(np.float32)
+    X[7] = 0.0                                            # zero-norm row: similarity NaN -> reports 1.0
+    X[40:46] = X[39]                                      # duplicate cluster
+    for i in range(n):
+        d = docs[int(doc_of[i])]
+        words = []
+        for _ in range(int(rng.integers(1, 90))):
+            if rng.random() < 0.12:
+                words.append(PHRASE_POOL[int(rng.integers(0, len(PHRASE_POOL)))])
+            else:
+                words.append(FILLER[int(rng.integers(0, len(FILLER)))])
+        if rng.random() < 0.05:
+            words.append(["call 1-800-555-1234", "fax (305) 555-0100", "dial 813.555.0199"][int(rng.integers(0, 3))])
+        text = " ".join(words)
+        if rng.random() < 0.1:
+            text = text.upper()
+        cd = {}
+        if rng.random() < 0.08:
+            cd[dkeys[int(rng.integers(0, len(dkeys)))]] = 1
+        rows.append({
+            "id": f"11111111-0000-4000-8000-{i:012d}", "document_id": d["document_id"],
+            "source_type": ["hierarchical", "fact", None][int(rng.integers(0, 3))], "source_id": f"src-{i}",
+            "text": text if rng.random() > 0.01 else None,
+            "page_number": int(i % 30) + 1, "paragraph_index": int(i % 9),
+            "section_path": ["", "Claims/Timely_Filing", "Utilization-Management/Prior_Authorization", None][int(rng.integers(0, 4))],
+            "chapter_path": [None, "Provider.Services/Contact"][int(rng.integers(0, 2))],
+            "summary": [None, "how to appeal a denial"][int(rng.random() < 0.1)],
+            "content_sha": f"{i:040x}",
+            "document_display_name": d["document_display_name"], "document_filename": d["document_filename"],
+            "document_authority_level": d["document_authority_level"], "document_payer": d["document_payer"],
+            "document_state": d["document_state"], "document_program": d["document_program"],
+            "chunk_d_tags": cd or None, "chunk_p_tags": None, "chunk_j_tags": None,
+            "has_vec": bool(rng.random() > 0.01),
+        })
+    promoted = sorted(int(x) for x in rng.choice(n, 6, replace=False))
+    return docs, rows, X, promoted
+
+
+def make_rerank_golden(oracle, ref_cs):
+    """Runs the reference's own `_rerank` over ALL rows of a small table (vector arm only)."""
+    cfg = types.ModuleType("app.config")
+    cfg.CHUNK_TAG_BOOST = 1.5                         # app/config.py:129 (the module itself needs DATABASE_URL + dotenv)
+    sys.modules["app.config"] = cfg
+    docs, rows, X, promoted = hybrid_table()
+    doc_by_id = {d["document_id"]: d for d in docs}
+    rng = np.random.default_rng(77)
+    dim = X.shape[1]
+    cases = [
+        dict(query="sunshine health prior authorization requirements", phrases=["Sunshine Health", "prior authorization"],
+             weights=[0.93, 0.79], codes=["j:payor.sunshine_health", "d:utilization_management.prior_authorization"]),
+        dict(query="what is the appeal process for a denial", phrases=None, weights=None, codes=None),
+        dict(query="sunshine health provider services phone number", phrases=["sunshine health", "phone"],
+             weights=[0.9, 0.7], codes=["j:payor.sunshine_health", None]),
+        dict(query="timely filing deadline", phrases=["timely filing"], weights=[0.8], codes=["d:claims.timely_filing"]),
+        dict(query="timely filing deadline for corrected claim", phrases=["timely filing", "appeal"], weights=None, codes=None),
+        dict(query="unicorn coverage", phrases=["unicorn rides"], weights=[1.0], codes=[None]),
+        dict(query="", phrases=["molina healthcare", "behavioral health", "credentialing"], weights=[0.9, 0.8, 0.0],
+             codes=["j:payor.molina_healthcare", "d:benefits.behavioral_health", None]),
+        dict(query="telehealth medical records documentation required", phrases=["medical records"], weights=[0.0], codes=[None]),
+        dict(query="prior authorization", phrases=["prior authorization", "florida medicaid"], weights=[0.7, 0.95],
+             codes=["d:utilization_management.prior_authorization", "j:state.fl"], payer="AHCA"),   # not an FL-MCO payer: plain equality (:524-535)
+        dict(query="peer support claims submission", phrases=["peer support", "claims submission", "denial", "appeal"],
+             weights=[0.9, 0.8, 0.7, 0.6], codes=[None, "p:process.claims_submission", None, "d:claims.appeals"]),
+    ]
+    out_cases = []
+    for ci, kw in enumerate(cases):
+        q = (X[int(rng.integers(0, len(rows)))].astype(np.float64) + 0.1 * rng.standard_normal(dim)).tolist() if ci % 2 == 0 \
+            else rng.standard_normal(dim).tolist()
+        qv = np.asarray([np.float32(x) for x in q], dtype=np.float32)
+        with np.errstate(all="ignore"):
+            dist = oracle.cosine_distance_c(np.ascontiguousarray(X), qv)
+        cands = []
+        for i, r in enumerate(rows):
+            if not r["has_vec"]:
+                continue
+            if kw.get("payer") and r["document_payer"] != kw["payer"]:
+                continue
+            sim = 1.0 - float(dist[i])
+            cosine_sim = max(0.0, min(1.0, float(sim or 0.0)))           # _vector_arm, corpus_search.py:1569
+            c = ref_cs._row_to_base_dict(r)
+            c["similarity"] = cosine_sim
+            c["match_score"] = cosine_sim
+            c["_arm"] = "vector"
+            c["arm_scores"] = {"vector": cosine_sim}                     # _rrf_merge keeps the raw per-arm score
+            c["retrieval_arms"] = ["vector"]
+            d = doc_by_id[r["document_id"]]
+            if d["has_tags_row"]:                                        # _attach_inherited_doc_tags, :2802-2807
+                c["_doc_d_tags"] = list(d["d_tags"]); c["_doc_j_tags"] = list(d["j_tags"]); c["_doc_p_tags"] = list(d["p_tags"])
+            if i in promoted:
+                c["_promoted_from_seed"] = "seed"
+            cands.append(c)
+        ranked = ref_cs._rerank(cands, "", kw["query"], kw["phrases"], kw["weights"], kw["codes"])
+        out_cases.append({
+            "case": kw, "query_embedding": q, "n_candidates": len(cands), "n_ranked": len(ranked),
+            "top": [{"id": c["id"], "rerank_score": c["rerank_score"], "similarity": c["similarity"],
+                     "source_type": c["source_type"]} for c in ranked[:50]],
+        })
+    np.savez_compressed(os.path.join(HERE, "hybrid_vectors.npz"), X=X)
+    dump_json({"docs": docs, "rows": rows, "promoted": promoted, "phrase_pool": PHRASE_POOL}, "hybrid_table.json")
+    dump_json(out_cases, "rerank.json")
+    print("rerank cases:", [(c["n_candidates"], c["n_ranked"]) for c in out_cases])
 
 
 def main():
@@ -198,6 +342,8 @@ def main():
         got = asyncio.run(store.asearch(q, kw["k"], kw.get("document_id"), kw.get("filters")))
         store_out.append({"case": kw, "query": q, "statements": list(store_log), "result": got})
 
+    make_rerank_golden(oracle, ref_cs)
+
     # ---- write fixtures
     np.savez_compressed(os.path.join(HERE, "table_vectors.npz"), X=Xf, has_vec=np.asarray(ot.has_vec, dtype=np.uint8))
     table_json = {
@@ -208,9 +354,9 @@ def main():
         "doc_d_tags": {k: sorted(v) for k, v in ot.doc_d_tags.items()},
         "doc_p_tags": {k: sorted(v) for k, v in ot.doc_p_tags.items()},
     }
-    json.dump(table_json, open(os.path.join(HERE, "table.json"), "w"), separators=(",", ":"))
-    json.dump(arm_out, open(os.path.join(HERE, "vector_arm.json"), "w"), separators=(",", ":"))
-    json.dump(store_out, open(os.path.join(HERE, "store_search.json"), "w"), separators=(",", ":"))
+    dump_json(table_json, "table.json")
+    dump_json(arm_out, "vector_arm.json")
+    dump_json(store_out, "store_search.json")
     print(f"wrote {len(arm_out)} _vector_arm cases, {len(store_out)} PgVectorStore cases; "
           f"result sizes {[len(c['result']) for c in arm_out]}")
     print("statements per case:", [len(c["statements"]) for c in arm_out])

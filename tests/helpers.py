@@ -87,12 +87,20 @@ def build_tables(oracle, n: int, dim: int, seed: int = 7, dtype: str = "f32", nu
 GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
 
 
+def load_golden_json(name: str):
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(GOLDEN_DIR, name + ".gz"), "rb") as f:
+        return json.loads(f.read().decode())
+
+
 def load_golden_table(oracle, with_product: bool = False, dtype: str = "f32", device: int = 0):
     """The table the golden fixtures were generated on (tests/golden/make_golden.py), rebuilt from the
     committed files -- NOT from synth, so generator changes cannot silently move the fixtures."""
     import json
     import os
-    tj = json.load(open(os.path.join(GOLDEN_DIR, "table.json")))
+    tj = load_golden_json("table.json")
     vz = np.load(os.path.join(GOLDEN_DIR, "table_vectors.npz"))
     X, has_vec = vz["X"], vz["has_vec"].astype(bool)
     c = tj["columns"]

@@ -52,6 +52,18 @@ def test_struct_layouts_match_c(tmp_path):
     assert got == [C.sizeof(N.FilterStruct), C.sizeof(N.RowMeta), N.FilterStruct.doc_pool.offset,
                    N.FilterStruct.tag_any.offset, N.FilterStruct.alt_state.offset, N.RowMeta.valid.offset]
     assert META_DTYPE.itemsize == 12 and META_DTYPE.fields["valid"][1] == N.RowMeta.valid.offset
+    src.write_text('#include "mrag.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mrag_chunkfeat), sizeof(mrag_hybrid_query),'
+                   'offsetof(mrag_chunkfeat, length_score), offsetof(mrag_chunkfeat, dtags), offsetof(mrag_hybrid_query, qcat),'
+                   'offsetof(mrag_hybrid_query, auth_score), offsetof(mrag_hybrid_query, contact_query),'
+                   'offsetof(mrag_hybrid_query, source_type_any));return 0;}')
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    from mrag_b200.index import FEAT_DTYPE
+    assert got == [C.sizeof(N.ChunkFeat), C.sizeof(N.HybridQuery), N.ChunkFeat.length_score.offset, N.ChunkFeat.dtags.offset,
+                   N.HybridQuery.qcat.offset, N.HybridQuery.auth_score.offset, N.HybridQuery.contact_query.offset,
+                   N.HybridQuery.source_type_any.offset]
+    assert FEAT_DTYPE.itemsize == 40 and FEAT_DTYPE.fields["dtags"][1] == N.ChunkFeat.dtags.offset
 
 
 def test_no_device_fails_loudly_not_silently():
