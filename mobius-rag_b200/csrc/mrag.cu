@@ -642,12 +642,13 @@ static uint32_t mma_sleep_ns() {
 }
 
 static int64_t sample_min_tiles(int num_sms) {
-    // default: shards of >= 64 tiles per SM (~600k rows); MRAG_SAMPLE_MIN_TILES overrides (tests)
+    // default: shards of >= 8 tiles per SM (~76k rows) -- measured (r1h): from there on the sampled buffer kernel
+    // beats the register top-k kernel by 2x .. 3.5x; MRAG_SAMPLE_MIN_TILES overrides (tests)
     static const int64_t env = [] {
         const char* e = getenv("MRAG_SAMPLE_MIN_TILES");
         return (e && *e) ? std::max<int64_t>(1, atoll(e)) : int64_t(0);
     }();
-    return env ? env : int64_t(64) * num_sms;
+    return env ? env : int64_t(8) * num_sms;
 }
 
 
@@ -741,7 +742,8 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         // anything below it (a CTA holds 1/#CTAs of the sample: its top 16 almost never truncate the sample's top K')
         MmaArgs sa = a;
         sa.stats = nullptr;
-        sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(4) * x->num_sms)));
+        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(4, tiles / (4 * int64_t(x->num_sms)))));
+        sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
         const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
         sa.P = sgrid;
         sa.k = std::min(kc, kMmaRegK);
@@ -911,7 +913,8 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 MmaArgs sa = a;
                 sa.stats = nullptr;
                 sa.tstamps = ts_sample;
-                const int per_cta = kr <= 64 ? 4 : 8;
+                // 4 (k <= 64) or 8 tiles per CTA, at most a quarter of the shard
+                const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kr <= 64 ? 4 : 8, tiles / (4 * int64_t(x->num_sms)))));
                 sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
                 const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
                 sa.P = sgrid;
