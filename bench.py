@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 METRIC = "QPS exact cosine top-10, 10Mx768 corpus"
 DEFAULT_BATCH = 64         # queries per step (see DESIGN.md "Measurement")
-CHUNK = 1 << 18            # rows generated per chunk; shard cuts fall on chunk boundaries
+CHUNK = 1 << 16            # rows generated per chunk; shard cuts fall on chunk boundaries (fine enough to balance 8 ranks within 1 %)
 
 
 def parse_args():
@@ -52,7 +52,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tag-filter", type=int, default=0, metavar="M",
                     help="document-tag filter passing every M-th document (0 = no filter); C2 uses 10")
-    ap.add_argument("--workload", default="", choices=["", "c2", "c3", "c5"],
+    ap.add_argument("--payer-filter", type=int, default=0, metavar="M",
+                    help="payor bitset filter passing the documents of 1 payer out of M (0 = none); C4 uses 13")
+    ap.add_argument("--workload", default="", choices=["", "c2", "c3", "c4", "c5"],
                     help="shortcut: c2 = 1Mx768 fp32, batch 256, top-10, tag filter 10%%; c3 = 10Mx768 bf16 top-100; "
                          "c5 = hybrid rerank over 10M chunks, 22-query bank, top-50")
     return ap.parse_args()
@@ -187,7 +189,8 @@ def workload_config(args, batch):
     return {
         "workload": f"{args.rows}x{args.dim} {args.dtype} corpus, top-{args.k}, query batch {batch}, row-sharded",
         "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "accumulate": "f32", "k": args.k, "batch": batch,
-        "filter": ("embedding_vec IS NOT NULL only" if not args.tag_filter else
+        "filter": (f"payor bitset passing 1/{args.payer_filter} of the documents" if args.payer_filter else
+                   "embedding_vec IS NOT NULL only" if not args.tag_filter else
                    f"document tag filter (relaxed, 1 tag) passing 1/{args.tag_filter} of the documents"), "l2": "inputs larger than L2 (no flush needed)",
         "parallelism": f"rowshard{args.gpus}",
     }
@@ -296,6 +299,9 @@ def main():
         args.sweep = ""
     elif args.workload == "c3":
         args.rows, args.dim, args.dtype, args.k = 10_000_000, 768, "bf16", 100
+    elif args.workload == "c4":
+        # one GPU's share of 50M x 1536 bf16 sharded over 8 (6.25M rows, 19.2 GB), per-payor bitset, top-10, single queries
+        args.rows, args.dim, args.dtype, args.k, args.batch, args.payer_filter, args.sweep = 6_250_000, 1536, "bf16", 10, 1, 13, "4"
     elif args.workload == "c5":
         args.rows, args.dim, args.dtype, args.k, args.batch, args.sweep = 10_000_000, 768, "bf16", 50, 22, ""
     if args.impl == "reference":
@@ -339,7 +345,8 @@ def main():
         if first >= hi:
             break
         m = X.shape[0]
-        meta = mi.make_meta(m, doc_idx=(np.arange(first, first + m) // 64).astype(np.uint32))
+        docs = (np.arange(first, first + m) // 64).astype(np.uint32)
+        meta = mi.make_meta(m, doc_idx=docs, payer=(docs % max(args.payer_filter, 1)).astype(np.uint16) if args.payer_filter else None)
         idx.append_device(X, meta)
     flt = None
     pass_frac = 1.0
@@ -350,6 +357,9 @@ def main():
         idx.set_doc_tags(0, bits)
         flt = mi.Filter().tag_relaxed([0])
         pass_frac = float(np.ceil(n_docs / args.tag_filter) / n_docs)
+    if args.payer_filter:
+        flt = (flt or mi.Filter()).payer_in([3 % args.payer_filter])
+        pass_frac *= 1.0 / args.payer_filter
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     assert len(idx) == n_local

@@ -247,6 +247,14 @@ int mrag_search_hybrid(mrag_index* idx, const float* q, int nq, int k, const mra
                        const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows, int32_t* counts,
                        void* stream);
 
+/* The d-tag arm's WHERE (`_dtag_arm`, corpus_search.py:1605-1701): rows that pass `filter` -- evaluated over every
+ * live row: that statement has no "embedding_vec IS NOT NULL" -- and whose chunk_d_tags hold any of `dcodes`
+ * (n_codes <= 32).  host_mask_out: ceil(size/32) words (HOST); counts (HOST, n_codes + 1): [0] = rows passing the
+ * filter (the IDF count's n_total, :1649-1653), [1+i] = of those, rows holding code i.  The shim orders the matches
+ * by (authority tier, id) and applies LIMIT k (:1674-1680). */
+int mrag_dtag_mask(mrag_index* idx, const mrag_filter* filter, const uint16_t* dcodes, int n_codes,
+                   uint32_t* host_mask_out, int64_t* counts);
+
 /* Global row id offset added to every returned row (shard base for row-sharded corpora). */
 int mrag_set_row_base(mrag_index* idx, int64_t row_base);
 

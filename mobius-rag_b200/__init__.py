@@ -18,6 +18,6 @@ from .vector_store import B200VectorStore, NoopVectorStore, VectorStore, get_vec
 from .corpus_search import CorpusFilters, LexiconExpansion, _vector_arm, vector_arm  # noqa: F401
 from .table import PublishedTable  # noqa: F401
 from .index import Filter, Index, make_meta, merge_topk  # noqa: F401
-from .hybrid import HybridTable, hybrid_rerank  # noqa: F401
+from .hybrid import HybridTable, dtag_arm, hybrid_rerank, rrf_merge  # noqa: F401
 
 __version__ = "0.1.0"

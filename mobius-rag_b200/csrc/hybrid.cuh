@@ -130,4 +130,34 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
     }
 }
 
+// The d-tag arm's WHERE (corpus_search.py:1632-1640, 1667-1672): row passes the base mask (filters over LIVE rows --
+// that statement has no "embedding_vec IS NOT NULL") and chunk_d_tags holds any of the codes.
+// counts[0] = rows passing the base mask ("n_total" of the IDF count, :1649-1653), counts[1+i] = of those, rows
+// holding code i.
+__global__ void __launch_bounds__(256) dtag_mask_kernel(const mrag_chunkfeat* __restrict__ feat, const uint32_t* __restrict__ base_mask,
+                                                       int64_t n, const uint16_t* __restrict__ codes, int n_codes,
+                                                       uint32_t* __restrict__ mask_out, unsigned long long* __restrict__ counts) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool base = false, any = false;
+    uint32_t has = 0;                       // bit i: the row holds code i
+    if (r < n) {
+        base = (base_mask[r >> 5] >> (r & 31)) & 1u;
+        if (base) {
+            const mrag_chunkfeat f = feat[r];
+            for (int i = 0; i < n_codes; ++i)
+                if (has_dtag(f, codes[i])) has |= 1u << i;
+            any = has != 0u;
+        }
+    }
+    const uint32_t word = __ballot_sync(kFull, any);
+    const uint32_t bword = __ballot_sync(kFull, base);
+    if (lane == 0 && r < ((n + 31) & ~int64_t(31))) mask_out[r >> 5] = word;
+    if (lane == 0 && bword) atomicAdd(counts, (unsigned long long)__popc(bword));
+    for (int i = 0; i < n_codes; ++i) {
+        const uint32_t w = __ballot_sync(kFull, (has >> i) & 1u);
+        if (lane == 0 && w) atomicAdd(counts + 1 + i, (unsigned long long)__popc(w));
+    }
+}
+
 }  // namespace mrag

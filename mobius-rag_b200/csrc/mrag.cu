@@ -118,12 +118,13 @@ struct Workspace {
     DevBuf<int> fb;                 // [0] count, [1..] query list of the exact fallback
     DevBuf<DevHyb> hyb;             // hybrid search: per-query parameters
     DevBuf<uint32_t> hmask;         // hybrid search: per-query row bitmaps
+    DevBuf<uint16_t> codes;         // d-tag arm: the codes asked for
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); ub.release();
-        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); flags.release(); npass.release(); stats.release();
+        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -244,6 +245,8 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.source_type, size_t(cap32));
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.valid, size_t(cap32 / 32 + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(x->cols.valid, 0, size_t(cap32 / 32 + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&x->cols.live, size_t(cap32 / 32 + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemset(x->cols.live, 0, size_t(cap32 / 32 + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32 + 64) * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->wstream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -290,6 +293,7 @@ extern "C" int mrag_destroy(mrag_index* x) {
     if (x->cols.authority) cudaFree(x->cols.authority);
     if (x->cols.source_type) cudaFree(x->cols.source_type);
     if (x->cols.valid) cudaFree(x->cols.valid);
+    if (x->cols.live) cudaFree(x->cols.live);
     if (x->doc_tags) cudaFree(x->doc_tags);
     if (x->feat) cudaFree(x->feat);
     if (x->doc_jtags) cudaFree(x->doc_jtags);
@@ -454,7 +458,7 @@ extern "C" int mrag_tombstone_doc(mrag_index* x, uint32_t doc_idx, int64_t* n_ro
     CU(cudaMalloc(&d_hit, 8));
     CU(cudaMemsetAsync(d_hit, 0, 8, x->wstream));
     tombstone_kernel<<<unsigned(ceil_div(x->size, 256)), 256, 0, x->wstream>>>(x->cols.doc_idx, x->size, doc_idx,
-                                                                              x->cols.valid, d_hit);
+                                                                              x->cols.valid, x->cols.live, d_hit);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     unsigned long long hit = 0;
     cudaError_t e = cudaMemcpyAsync(&hit, d_hit, 8, cudaMemcpyDeviceToHost, x->wstream);
@@ -518,7 +522,7 @@ static void to_dev_filter(const mrag_filter* f, DevFilter* d) {
 
 // builds the row bitmap for `f` into `mask_out` (ceil(n/32) words) on stream s
 static int build_mask(mrag_index* x, Workspace* w, const mrag_filter* f, int64_t n, uint32_t* mask_out,
-                      unsigned long long* d_npass, cudaStream_t s) {
+                      unsigned long long* d_npass, cudaStream_t s, bool include_null_vec = false) {
     DevFilter df;
     to_dev_filter(f, &df);
     const uint32_t* pool_bits = nullptr;
@@ -539,7 +543,7 @@ static int build_mask(mrag_index* x, Workspace* w, const mrag_filter* f, int64_t
     }
     const int64_t n32 = ceil_div(n, 32) * 32;
     filter_mask_kernel<<<unsigned(ceil_div(n32, 256)), 256, 0, s>>>(df, x->cols, n, pool_bits, x->doc_tags,
-                                                                   x->n_tag_docs, mask_out, d_npass);
+                                                                   x->n_tag_docs, mask_out, d_npass, include_null_vec ? 1 : 0);
     LAUNCHED();
     return MRAG_OK;
 }
@@ -1208,6 +1212,48 @@ extern "C" int mrag_search_hybrid(mrag_index* x, const float* q, int nq, int k, 
     t_last_ev = *ev;
     t_last_valid = (rc == MRAG_OK);
     t_last_kind = "gemv_hybrid";
+    release_ws(x, w, nullptr);
+    return rc;
+}
+
+
+// The d-tag arm (corpus_search.py:1605-1701): WHERE over live rows + "chunk_d_tags ? key" for any key.  The row
+// bitmap comes back to the HOST (the shim orders the matches by (authority tier, id) and cuts to k, :1674-1680).
+extern "C" int mrag_dtag_mask(mrag_index* x, const mrag_filter* filter, const uint16_t* dcodes, int n_codes,
+                              uint32_t* host_mask_out, int64_t* counts) {
+    if (!x || !host_mask_out || !counts) return fail(MRAG_ERR_ARG, "mrag_dtag_mask: null argument");
+    if (n_codes < 0 || n_codes > 32 || (n_codes > 0 && !dcodes)) return fail(MRAG_ERR_ARG, "mrag_dtag_mask: 0 <= n_codes <= 32");
+    for (int i = 0; i <= n_codes; ++i) counts[i] = 0;
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    const int64_t n = x->size;
+    if (n == 0) return MRAG_OK;
+    if (!x->feat) return fail(MRAG_ERR_STATE, "mrag_dtag_mask: no chunk features set (mrag_set_chunk_features)");
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_dtag_mask: cudaSetDevice failed (no CPU path)");
+    Workspace* w = acquire_ws(x, nullptr);
+    if (!w) return fail(MRAG_ERR_OOM, "mrag_dtag_mask: cannot create a workspace");
+    cudaStream_t s = w->own_stream;
+    const int64_t nwords = ceil_div(n, 32);
+    int rc = MRAG_OK;
+    mrag_filter none;
+    memset(&none, 0, sizeof none);
+    if (w->mask.reserve(size_t(nwords) + 1) || w->hmask.reserve(size_t(nwords) + 1) || w->stats.reserve(40) || w->codes.reserve(32))
+        rc = MRAG_ERR_OOM;
+    if (rc == MRAG_OK) rc = build_mask(x, w, filter ? filter : &none, n, w->mask.p, nullptr, s, /*include_null_vec=*/true);
+    if (rc == MRAG_OK) {
+        unsigned long long hc[40];
+        cudaMemsetAsync(w->stats.p, 0, 40 * 8, s);
+        if (n_codes) cudaMemcpyAsync(w->codes.p, dcodes, size_t(n_codes) * 2, cudaMemcpyHostToDevice, s);
+        dtag_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(x->feat, w->mask.p, n, w->codes.p, n_codes, w->hmask.p, w->stats.p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaMemcpyAsync(host_mask_out, w->hmask.p, size_t(nwords) * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(hc, w->stats.p, size_t(n_codes + 1) * 8, cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_dtag_mask: %s", cudaGetErrorString(e));
+        else for (int i = 0; i <= n_codes; ++i) counts[i] = int64_t(hc[i]);
+    } else {
+        cudaStreamSynchronize(s);
+    }
     release_ws(x, w, nullptr);
     return rc;
 }

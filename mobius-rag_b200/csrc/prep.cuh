@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) store_rows_kernel(const float* __restrict
 struct MetaCols {
     uint32_t* doc_idx; uint16_t* payer; uint8_t* state; uint8_t* program; uint8_t* authority;
     uint8_t* source_type; uint32_t* valid;
+    uint32_t* live;      // row exists (inserted and not deleted), whether or not it has a vector
 };
 
 __global__ void __launch_bounds__(256) scatter_meta_kernel(const mrag_rowmeta* __restrict__ m, int64_t n,
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) scatter_meta_kernel(const mrag_rowmeta* _
     c.doc_idx[r] = x.doc_idx; c.payer[r] = x.payer; c.state[r] = x.state; c.program[r] = x.program;
     c.authority[r] = x.authority; c.source_type[r] = x.source_type;
     if (x.valid) atomicOr(&c.valid[r >> 5], 1u << (r & 31));
+    atomicOr(&c.live[r >> 5], 1u << (r & 31));
 }
 
 // device copy of mrag_filter without the host pointer
@@ -81,11 +83,12 @@ __global__ void __launch_bounds__(256) filter_mask_kernel(const __grid_constant_
                                                          const uint32_t* __restrict__ pool_bits,
                                                          const uint64_t* __restrict__ doc_tags, int64_t n_tag_docs,
                                                          uint32_t* __restrict__ mask_out,
-                                                         unsigned long long* __restrict__ n_pass) {
+                                                         unsigned long long* __restrict__ n_pass, int include_null_vec) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     bool ok = false;
     if (r < n) {
-        ok = (c.valid[r >> 5] >> (r & 31)) & 1u;              // embedding_vec IS NOT NULL
+        // embedding_vec IS NOT NULL -- or, for statements without that clause (the d-tag arm), any live row
+        ok = ((include_null_vec ? c.live : c.valid)[r >> 5] >> (r & 31)) & 1u;
         if (ok && f.flags) {
             const uint32_t payer = c.payer[r], state = c.state[r];
             if (f.flags & MRAG_F_PAYER)
@@ -129,11 +132,12 @@ __global__ void pool_bitmap_kernel(const uint32_t* __restrict__ pool, int64_t n_
 }
 
 __global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n, uint32_t doc, uint32_t* valid,
-                                 unsigned long long* n_hit) {
+                                 uint32_t* live, unsigned long long* n_hit) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= n) return;
     if (doc_idx[r] == doc) {
         uint32_t old = atomicAnd(&valid[r >> 5], ~(1u << (r & 31)));
+        atomicAnd(&live[r >> 5], ~(1u << (r & 31)));
         if ((old >> (r & 31)) & 1u) atomicAdd(n_hit, 1ull);
     }
 }

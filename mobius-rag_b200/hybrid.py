@@ -352,3 +352,94 @@ def hybrid_rerank(ht: HybridTable, query_embedding: Sequence[float], k: int, que
         c["confidence_label"] = confidence_label(sc)
         res.append(c)
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# the d-tag arm and reciprocal rank fusion (corpus_search.py:1605-1766)
+# ---------------------------------------------------------------------------------------------
+RRF_K = 60                        # corpus_search.py:394
+
+
+def _authority_tier(level: str | None) -> int:
+    """ORDER BY CASE document_authority_level ... of the d-tag arm (corpus_search.py:1674-1678)."""
+    return 0 if level == "contract_source_of_truth" else 1 if level == "operational" else 2
+
+
+def dtag_arm(ht: "HybridTable", dtag_keys: Sequence[str], k: int, filters: Any = None,
+             include_document_ids: Sequence[str] | None = None, search_id: str = "", idf_mode: bool = False) -> list[dict]:
+    """`_dtag_arm`: chunks whose chunk_d_tags hold any of the keys, ordered by (authority tier, id), LIMIT k;
+    similarity is the constant 0.5; with ``idf_mode`` each chunk carries ``_dtag_idf`` = ln(n_total / pool_size)
+    of its highest-IDF key.  The WHERE and the counts run on the GPU (dtag_mask_kernel); ordering k rows by
+    (tier, id) is done here over the matches."""
+    if not dtag_keys:
+        return []
+    t = ht.table
+    try:
+        ht.build_features()
+        keys = list(dtag_keys)
+        if len(keys) > 32:
+            raise ValueError("at most 32 d-tag keys")
+        codes = (C.c_uint16 * max(1, len(keys)))(*[ht.dcodes.get(key, 0xFFFF) for key in keys])   # 0xFFFF: a key no chunk has
+        flt: Filter = t.filter_corpus(filters, include_document_ids)
+        n = len(t)
+        mask = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        counts = (C.c_int64 * (len(keys) + 1))()
+        N.check(t.index._lib.mrag_dtag_mask(t.index._h, flt.ref() if flt.active else None, codes, len(keys),
+                                            mask.ctypes.data, counts))
+        rows = np.flatnonzero(np.unpackbits(mask.view(np.uint8), bitorder="little")[:n])
+        idf_weights: dict[str, float] = {}
+        if idf_mode:
+            n_total = max(1, int(counts[0]) or 1)
+            for i, key in enumerate(keys):
+                idf_weights[key] = math.log(n_total / max(1, int(counts[1 + i]) or 1))
+        order = sorted(rows.tolist(), key=lambda r: (_authority_tier(t.document_authority_level[r]), t.id[r]))[:max(0, int(k))]
+    except Exception as exc:                       # fail-soft like the reference (:1684-1686)
+        import logging
+        logging.getLogger(__name__).warning("corpus_search dtag arm failed: %s", exc)
+        return []
+    out = []
+    for r in order:
+        c = _row_to_base_dict(t, r)
+        c["similarity"] = 0.5
+        c["match_score"] = 0.5
+        c["_arm"] = "dtag"
+        if idf_mode and idf_weights:
+            chunk_dtags = c.get("chunk_d_tags") or {}
+            c["_dtag_idf"] = max((idf_weights[key] for key in keys if key in chunk_dtags), default=1.0)
+        out.append(c)
+    return out
+
+
+def rrf_merge(arms: dict[str, list[dict]], k: int = RRF_K, search_id: str = "") -> list[dict]:
+    """`_rrf_merge` (corpus_search.py:1708-1766): sum over arms of idf / (k + rank), first arm's dict wins,
+    blanks filled from later arms, ordered by (-rrf, best rank); `similarity` becomes the RRF score."""
+    fused: dict[str, dict] = {}
+    for arm_name, ranked in arms.items():
+        for rank0, chunk in enumerate(ranked):
+            cid = chunk.get("id") or ""
+            if not cid:
+                continue
+            rank1 = rank0 + 1
+            contribution = float(chunk.get("_dtag_idf") or 1.0) / (k + rank1)
+            f = fused.get(cid)
+            if f is None:
+                f = fused[cid] = dict(chunk)
+                f["retrieval_arms"] = [arm_name]
+                f["arm_ranks"] = {arm_name: rank1}
+                f["arm_scores"] = {arm_name: float(chunk.get("similarity", 0.0))}
+                f["rrf_score"] = contribution
+            else:
+                for key, val in chunk.items():
+                    if key in ("retrieval_arms", "arm_ranks", "arm_scores", "rrf_score"):
+                        continue
+                    if f.get(key) in (None, "", []) and val not in (None, "", []):
+                        f[key] = val
+                if arm_name not in f["retrieval_arms"]:
+                    f["retrieval_arms"].append(arm_name)
+                f["arm_ranks"][arm_name] = rank1
+                f["arm_scores"][arm_name] = float(chunk.get("similarity", 0.0))
+                f["rrf_score"] += contribution
+    out = sorted(fused.values(), key=lambda c: (-float(c.get("rrf_score", 0.0)), min(c.get("arm_ranks", {}).values() or [999])))
+    for c in out:
+        c["similarity"] = float(c.get("rrf_score", 0.0))
+    return out

@@ -74,6 +74,9 @@ class FakeResult:
     def all(self):
         return self._rows
 
+    def one_or_none(self):
+        return self._rows[0] if self._rows else None
+
 
 class FakeSession:
     """Stands in for AsyncSession / AsyncSessionLocal(): records every statement, answers through mini_pg."""
@@ -86,7 +89,7 @@ class FakeSession:
         sql = str(stmt)
         self.log.append({"sql": " ".join(sql.split()),
                          "params": {k: v for k, v in params.items() if k != "query_vec"}})
-        return FakeResult(mini_pg.execute(self.table_rows, self.X, sql, dict(params), self.cd))
+        return FakeResult(mini_pg.execute_any(self.table_rows, self.X, sql, dict(params), self.cd))
 
     async def __aenter__(self):
         return self
@@ -226,6 +229,48 @@ def make_rerank_golden(oracle, ref_cs):
             "top": [{"id": c["id"], "rerank_score": c["rerank_score"], "similarity": c["similarity"],
                      "source_type": c["source_type"]} for c in ranked[:50]],
         })
+    # ---- `_dtag_arm` (corpus_search.py:1605-1701) and `_rrf_merge` (:1708-1766) on the same table
+    table_rows = []
+    for r in rows:
+        tr = dict(r)
+        tr["embedding_vec"] = True if r["has_vec"] else None
+        table_rows.append(tr)
+    CF = ref_cs.CorpusFilters
+    dtag_cases = [
+        dict(keys=["claims.timely_filing"], k=10),
+        dict(keys=["claims.timely_filing", "claims.appeals", "no.such_key"], k=25, idf_mode=True),
+        dict(keys=["utilization_management.prior_authorization"], k=100, filters=dict(payer="AHCA"), idf_mode=True),
+        dict(keys=["benefits.behavioral_health"], k=5, include_document_ids=[docs[i]["document_id"] for i in range(0, 60, 3)], idf_mode=True),
+        dict(keys=["no.such_key"], k=10, idf_mode=True),
+        dict(keys=[], k=10),
+    ]
+    dtag_out = []
+    for kw in dtag_cases:
+        log = []
+        db = FakeSession(table_rows, X, None, log)
+        got = asyncio.run(ref_cs._dtag_arm(db, kw["keys"], kw["k"], CF(**kw["filters"]) if kw.get("filters") else None,
+                                           kw.get("include_document_ids"), "", kw.get("idf_mode", False)))
+        dtag_out.append({"case": kw, "statements": log, "result": got})
+    # RRF over three arms built from real outputs: vector order, a shuffled "bm25" list, the dtag arm with IDF
+    vec = [dict(c) for c in out_cases and []]
+    qv = np.asarray([np.float32(x) for x in out_cases[0]["query_embedding"]], dtype=np.float32)
+    with np.errstate(all="ignore"):
+        dist = oracle.cosine_distance_c(np.ascontiguousarray(X), qv)
+    order = [i for i in np.argsort(dist, kind="stable") if rows[i]["has_vec"] and not np.isnan(dist[i])][:40]
+    vec_arm = []
+    for i in order:
+        c = ref_cs._row_to_base_dict(rows[i]); c["similarity"] = 1.0 - float(dist[i]); c["_arm"] = "vector"; vec_arm.append(c)
+    bm_idx = [int(x) for x in rng.permutation(len(rows))[:30]] + order[5:12]
+    bm_arm = []
+    for j, i in enumerate(bm_idx):
+        c = ref_cs._row_to_base_dict(rows[i]); c["similarity"] = 0.9 - 0.01 * j; c["_arm"] = "bm25"
+        if j % 4 == 0:
+            c["summary"] = "bm25 summary"             # fills a blank of an earlier arm's dict
+        bm_arm.append(c)
+    arms = {"bm25": bm_arm, "vector": vec_arm, "dtag": dtag_out[1]["result"]}
+    fused = ref_cs._rrf_merge({a: [dict(c) for c in lst] for a, lst in arms.items()})
+    dump_json({"dtag": dtag_out, "rrf": {"arms": arms, "fused": fused}}, "dtag_rrf.json")
+    print("dtag results:", [len(c["result"]) for c in dtag_out], "rrf fused:", len(fused))
     np.savez_compressed(os.path.join(HERE, "hybrid_vectors.npz"), X=X)
     dump_json({"docs": docs, "rows": rows, "promoted": promoted, "phrase_pool": PHRASE_POOL}, "hybrid_table.json")
     dump_json(out_cases, "rerank.json")

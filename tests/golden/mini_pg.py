@@ -33,7 +33,8 @@ _TOKEN = re.compile(r"""
   | (?P<lpar>\() | (?P<rpar>\)) | (?P<comma>,)
   | (?P<str>'(?:[^']|'')*')
   | (?P<param>:[A-Za-z_][A-Za-z_0-9]*)
-  | (?P<op><=>|=|\[\])
+  | (?P<op><=>|=|\[\]|\?|\*)
+  | (?P<num>\d+)
   | (?P<word>[A-Za-z_][A-Za-z_0-9.]*)
 """, re.X)
 
@@ -111,10 +112,17 @@ class _Where:
             name = {"dt.d_tags": "_doc_d_tags", "dt.p_tags": "_doc_p_tags"}[col.lower()]
             # LEFT JOIN: no document_tags row -> dt.* is NULL -> jsonb_exists(NULL, k) is NULL
             return lambda r, name=name, key=key: r[name] is not None and key in r[name]
+        if kind == "num":                                   # WHERE 1=1
+            a = self.take()[1]; self.take("="); b = self.take()[1]
+            return lambda r, a=a, b=b: a == b
         if kind != "word":
             raise ValueError(f"mini_pg: unexpected token {v!r}")
         col = self.take()[1].split(".")[-1]
         nk, nv = self.peek()
+        if nv == "?":                                       # jsonb ? key  (NULL ? key is NULL)
+            self.take()
+            key = self.value()
+            return lambda r, col=col, key=key: r[col] is not None and key in r[col]
         if nv.upper() == "IS":
             self.take(); self.take("NOT"); self.take("NULL")
             return lambda r, col=col: r[col] is not None
@@ -178,3 +186,40 @@ def execute(table_rows: list[dict], X: np.ndarray, sql: str, params: dict, cosin
         r["similarity"] = float(sim)
         out.append(r)
     return out
+
+
+_DTAG_STMT = re.compile(
+    r"SELECT(?P<cols>.*?)0\.5\s+AS\s+similarity\s+FROM\s+rag_published_embeddings\s+WHERE(?P<where>.*?)"
+    r"ORDER\s+BY\s+CASE\s+document_authority_level\s+WHEN\s+'contract_source_of_truth'\s+THEN\s+0\s+"
+    r"WHEN\s+'operational'\s+THEN\s+1\s+ELSE\s+2\s+END\s*,\s*rag_published_embeddings\.id\s+LIMIT\s+:k\s*$", re.S | re.I)
+_COUNT_STMT = re.compile(r"SELECT\s+COUNT\(\*\)\s+AS\s+n_total\s*,(?P<filters>.*?)FROM\s+rag_published_embeddings\s+WHERE(?P<where>.*)$",
+                         re.S | re.I)
+_COUNT_ITEM = re.compile(r"COUNT\(\*\)\s+FILTER\s+\(WHERE\s+(?P<cond>.*?)\)\s+AS\s+(?P<name>cnt_\d+)", re.S | re.I)
+
+
+def execute_any(table_rows: list[dict], X, sql: str, params: dict, cosine_distance) -> list[dict]:
+    """Dispatch on the three statement shapes of the path: the vector statement, the d-tag arm's SELECT
+    (corpus_search.py:1664-1681) and its IDF COUNT (corpus_search.py:1644-1648)."""
+    text = sql.strip()
+    if "<=>" in text:
+        return execute(table_rows, X, sql, params, cosine_distance)
+    m = _COUNT_STMT.search(text)
+    if m and "COUNT(*)" in text.upper():
+        where = _Where(m.group("where"), params).parse()
+        passing = [r for r in table_rows if where(r)]
+        out = {"n_total": len(passing)}
+        for it in _COUNT_ITEM.finditer(m.group("filters")):
+            cond = _Where(it.group("cond"), params).parse()
+            out[it.group("name")] = sum(1 for r in passing if cond(r))
+        return [out]
+    m = _DTAG_STMT.search(text)
+    if not m:
+        raise ValueError("mini_pg: statement shape not recognised:\n" + sql)
+    where = _Where(m.group("where"), params).parse()
+    passing = [r for r in table_rows if where(r)]
+
+    def tier(r):
+        lvl = r["document_authority_level"]
+        return 0 if lvl == "contract_source_of_truth" else 1 if lvl == "operational" else 2
+    passing.sort(key=lambda r: (tier(r), r["id"]))          # uuid order == order of the canonical lowercase text
+    return [dict(r, similarity=0.5) for r in passing[: int(params["k"])]]
