@@ -110,7 +110,7 @@ struct Workspace {
     DevBuf<float> qraw, qpad, qinv, scores;
     DevBuf<__nv_bfloat16> qbf;
     DevBuf<uint32_t> mask, pool, pool_bits, gthr;
-    DevBuf<uint64_t> part, part2, ub;
+    DevBuf<uint64_t> part, part2, part3, ub, gcand;
     DevBuf<int64_t> rows, crows;
     DevBuf<int32_t> counts, ccounts;
     DevBuf<float> cscores;
@@ -123,7 +123,7 @@ struct Workspace {
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
-        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); ub.release();
+        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
         rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -658,12 +658,13 @@ static int64_t sample_min_tiles(int num_sms) {
 
 // ORDER BY .. LIMIT over the per-producer lists: one block per query, or two levels when the producer
 // set is wide (many blocks in flight sorting <= 2048 keys each, then one block per query)
+// (nblocks = queries served by this launch; the group lists are indexed by query id, so they are sized by m.nq)
 static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
     if (int64_t(m.P) * m.kp > kMergeSlots / 2 && !m.gthr_out) {
         MergeArgs m1 = m;
         m1.Pg = std::max(2, (kMergeSlots / 2) / m.kp);
         const int groups = int(ceil_div(m.P, m1.Pg));
-        if (w->part2.reserve(size_t(nq) * groups * m.kp)) return MRAG_ERR_OOM;
+        if (w->part2.reserve(size_t(std::max(nq, m.nq)) * groups * m.kp)) return MRAG_ERR_OOM;
         m1.part_out = w->part2.p;
         merge_kernel<<<dim3(unsigned(nq), unsigned(groups)), kMergeThreads, 0, s>>>(m1);
         LAUNCHED();
@@ -673,6 +674,9 @@ static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
     LAUNCHED();
     return MRAG_OK;
 }
+
+// largest k of the candidate-generating path: K' = 1.5 k nominees + 32 slack keys must fit a warp's rank sort (192 keys)
+static const int kMma128MaxK = 106;
 
 static int approx_min_nq() {
     static const int v = [] {
@@ -691,11 +695,12 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
         CU(cudaFuncSetAttribute(scan_mma128_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
-    if (KREG > 0) a.cap = 0;
-    const size_t fixed = mma128_smem_bytes(0, a.cap);
+    if (KREG > 0) { a.cap = 0; a.gcand = nullptr; }
+    const int smem_cap = a.gcand ? 0 : a.cap;           // candidate buffers in global memory take no shared memory
+    const size_t fixed = mma128_smem_bytes(0, smem_cap);
     if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma128: candidate buffers do not fit");
     a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
-    const size_t smem = mma128_smem_bytes(a.stages, a.cap);
+    const size_t smem = mma128_smem_bytes(a.stages, smem_cap);
     for (int q0 = 0; q0 < nq; q0 += kMma128Queries) {
         a.q0 = q0;
         a.nq = std::min(kMma128Queries, nq - q0);
@@ -712,7 +717,10 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
                                  float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t s) {
     const int64_t n = x->size;
     const int ld = x->ld;
-    const int kc = k + 32, kpc = host_next_pow2(kc);
+    // nominees per query: k + 32, or 1.5 k for large k (the number of rows within eps of the k-th best grows with k)
+    const int kc = std::max(k + 32, k + k / 2), kpc = host_next_pow2(kc);
+    const int cap = kc + kMma128Slack;
+    const bool global_cand = mma128_smem_bytes(12, cap) > size_t(kMaxSmem);      // keep >= 12 stages (96 KB) in flight
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))));
     const int64_t nwords = ceil_div(n, 32);
     const int ggrid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
@@ -730,8 +738,12 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
     MmaArgs a{};
     a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
-    a.part = w->part.p; a.k = kc; a.kp = kpc; a.P = grid; a.cap = kc + kMma128Slack;
+    a.part = w->part.p; a.k = kc; a.kp = kpc; a.P = grid; a.cap = cap;
     a.gthr = w->gthr.p; a.tile_mul = 1; a.sleep_ns = mma_sleep_ns();
+    if (global_cand) {
+        if (w->gcand.reserve(size_t(grid) * kMma128Queries * cap)) return MRAG_ERR_OOM;
+        a.gcand = w->gcand.p;
+    }
     if (getenv("MRAG_SCAN_STATS")) {
         if (w->stats.reserve(40)) return MRAG_ERR_OOM;
         CU(cudaMemsetAsync(w->stats.p, 0, 40 * 8, s));
@@ -746,7 +758,8 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         // anything below it (a CTA holds 1/#CTAs of the sample: its top 16 almost never truncate the sample's top K')
         MmaArgs sa = a;
         sa.stats = nullptr;
-        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(4, tiles / (4 * int64_t(x->num_sms)))));
+        // 4 tiles per CTA (16 for large k, whose bound must sit higher to keep the buffers quiet), at most a quarter of the shard
+        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kc > 64 ? 16 : 4, tiles / (4 * int64_t(x->num_sms)))));
         sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
         const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
         sa.P = sgrid;
@@ -780,25 +793,46 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     FinalizeArgs fa{};
     fa.keys = w->ckeys.p; fa.cand_scores = w->cscores.p; fa.cand_counts = w->ccounts.p; fa.nq = nq; fa.kc = kc; fa.k = k;
     fa.eps = eps; fa.scores = d_scores; fa.rows = d_rows; fa.counts = d_counts; fa.row_base = x->row_base;
-    fa.need_tail = w->flags.p; fa.fb_count = w->fb.p; fa.fb_list = w->fb.p + 1;
+    fa.need_tail = w->flags.p; fa.fb_count = w->fb.p; fa.fb_list = w->fb.p + 1; fa.gthr = w->gthr.p;
     finalize_kernel<<<nq, kFinalizeThreads, 0, s>>>(fa);
     LAUNCHED();
-    // exact rescan of the queries whose certificate failed (a no-op launch when there are none)
-    ScanArgs g{};
-    g.rows = x->rows; g.n = n; g.ld = ld; g.mask = mask; g.q = w->qpad.p; g.qinv = w->qinv.p; g.ub = nullptr;
-    g.part = w->part.p; g.k = k; g.kp = kp; g.P = ggrid; g.qlist = w->fb.p + 1; g.qcount = w->fb.p;
-    const int gq = gemv_nq_for(4, ld, kp);
-    if (x->dtype == MRAG_BF16)
-        rc = gq == 4 ? launch_gemv<1, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<1, 2>(g, ggrid, s) : launch_gemv<1, 1>(g, ggrid, s);
-    else
-        rc = gq == 4 ? launch_gemv<0, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<0, 2>(g, ggrid, s) : launch_gemv<0, 1>(g, ggrid, s);
-    if (rc != MRAG_OK) return rc;
-    MergeArgs fm{};
-    fm.part = w->part.p; fm.P = ggrid; fm.kp = kp; fm.nq = nq; fm.k = k; fm.k_total = k; fm.k_off = 0;
-    fm.scores = d_scores; fm.rows = d_rows; fm.counts = d_counts; fm.row_base = x->row_base;
-    fm.need_tail = w->flags.p; fm.qlist = w->fb.p + 1; fm.qcount = w->fb.p;
-    rc = launch_merge(w, fm, nq, s);
-    if (rc != MRAG_OK) return rc;
+    // exact rescan of the queries whose certificate failed (no-op launches when there are none): the first 64 of
+    // them in ONE pass of the exact tensor-core scan (bf16 shards), the rest -- and fp32 shards -- on the CUDA cores
+    const bool exact_mma = x->dtype == MRAG_BF16;
+    int gskip = 0;
+    if (exact_mma) {
+        MmaArgs e{};
+        e.n = n; e.ld = ld; e.mask = mask; e.inv_norm = x->inv_norm; e.q = w->qpad.p; e.qinv = w->qinv.p;
+        e.part = w->part.p; e.k = k; e.kp = kp; e.P = grid; e.cap = k + kMmaSlack; e.gthr = w->gthr.p; e.tile_mul = 1;
+        e.sleep_ns = mma_sleep_ns(); e.qlist = w->fb.p + 1; e.qcount = w->fb.p;
+        rc = launch_scan_mma<0>(x, e, /*nq=*/1, grid, s);        // one launch; the kernel reads the list length itself
+        if (rc != MRAG_OK) return rc;
+        MergeArgs em{};
+        em.part = w->part.p; em.P = grid; em.kp = kp; em.nq = nq; em.k = k; em.k_total = k; em.k_off = 0;
+        em.scores = d_scores; em.rows = d_rows; em.counts = d_counts; em.row_base = x->row_base;
+        em.need_tail = w->flags.p; em.qlist = w->fb.p + 1; em.qcount = w->fb.p; em.q_lo = 0; em.q_hi = kMmaQueries;
+        rc = launch_merge(w, em, std::min(nq, kMmaQueries), s);
+        if (rc != MRAG_OK) return rc;
+        gskip = kMmaQueries;
+    }
+    if (nq > gskip) {
+        if (w->part3.reserve(size_t(nq) * ggrid * kp)) return MRAG_ERR_OOM;
+        ScanArgs g{};
+        g.rows = x->rows; g.n = n; g.ld = ld; g.mask = mask; g.q = w->qpad.p; g.qinv = w->qinv.p; g.ub = nullptr;
+        g.part = w->part3.p; g.k = k; g.kp = kp; g.P = ggrid; g.qlist = w->fb.p + 1; g.qcount = w->fb.p; g.qskip = gskip;
+        const int gq = gemv_nq_for(4, ld, kp);
+        if (x->dtype == MRAG_BF16)
+            rc = gq == 4 ? launch_gemv<1, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<1, 2>(g, ggrid, s) : launch_gemv<1, 1>(g, ggrid, s);
+        else
+            rc = gq == 4 ? launch_gemv<0, 4>(g, ggrid, s) : gq == 2 ? launch_gemv<0, 2>(g, ggrid, s) : launch_gemv<0, 1>(g, ggrid, s);
+        if (rc != MRAG_OK) return rc;
+        MergeArgs fm{};
+        fm.part = w->part3.p; fm.P = ggrid; fm.kp = kp; fm.nq = nq; fm.k = k; fm.k_total = k; fm.k_off = 0;
+        fm.scores = d_scores; fm.rows = d_rows; fm.counts = d_counts; fm.row_base = x->row_base;
+        fm.need_tail = w->flags.p; fm.qlist = w->fb.p + 1; fm.qcount = w->fb.p; fm.q_lo = gskip; fm.q_hi = 0;
+        rc = launch_merge(w, fm, nq - gskip, s);
+        if (rc != MRAG_OK) return rc;
+    }
     t_fb_ptr = w->fb.p;
     return MRAG_OK;
 }
@@ -854,7 +888,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     //           mma128 tcgen05 candidate generation, 128 queries per pass over bf16 rows / the bf16 shadow,
     //                  + exact rescoring with certificate (k <= 32)
     const bool can_mma = x->has_tmap && x->dtype == MRAG_BF16 && n > 0;
-    const bool can_mma128 = x->has_tmap && n > 0 && k <= 32;
+    const bool can_mma128 = x->has_tmap && n > 0 && k <= kMma128MaxK;
     // a single query also goes to the tensor-core scan (it streams faster than the CUDA-core kernel) unless a
     // filter is active: the CUDA-core scan skips masked rows one by one, the tensor-core scan only 64-row tiles
     bool use_mma = can_mma && (nq >= 2 || !(filter && filter->flags));
@@ -866,7 +900,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     }
     if (options & MRAG_OPT_FORCE_MMA128) {
         if (!can_mma128)
-            return fail(MRAG_ERR_STATE, "mrag_search: the 128-query scan needs bf16 rows or a bf16 shadow, dim <= %d, k <= 32", kMmaMaxLd);
+            return fail(MRAG_ERR_STATE, "mrag_search: the 128-query scan needs bf16 rows or a bf16 shadow, dim <= %d, k <= %d", kMmaMaxLd, kMma128MaxK);
         use_mma128 = true;
     }
     if (use_mma128) {

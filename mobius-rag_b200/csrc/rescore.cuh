@@ -128,16 +128,17 @@ struct FinalizeArgs {
     float* scores; int64_t* rows; int32_t* counts; int64_t row_base;   // [nq][k] results
     int* need_tail;
     int* fb_list; int* fb_count; // queries that need the exact scan
+    uint32_t* gthr;              // [nq] admission bound handed to the exact rescan of a flagged query
 };
 
 constexpr int kFinalizeThreads = 128;
 
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const FinalizeArgs a) {
-    __shared__ uint64_t s[128];
+    __shared__ uint64_t s[256];
     const int q = blockIdx.x, tid = threadIdx.x;
-    const int n2 = next_pow2(a.kc < 2 ? 2 : a.kc);          // <= 128
+    const int n2 = next_pow2(a.kc < 2 ? 2 : a.kc);          // <= 256
     const int count = a.cand_counts[q];
-    if (tid < n2) s[tid] = (tid < count) ? a.keys[size_t(q) * a.kc + tid] : 0ull;
+    for (int i = tid; i < n2; i += kFinalizeThreads) s[i] = (i < count) ? a.keys[size_t(q) * a.kc + i] : 0ull;
     __syncthreads();
     block_sort_desc(s, n2);
     // keys can be 0 only past `count` (a nominated row always has a finite score)
@@ -160,7 +161,11 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
         if (count == a.kc) {
             const float a_min = a.cand_scores[size_t(q) * a.kc + count - 1];
             const float tau = key_score(s[a.k - 1]);
-            if (!(a_min + a.eps < tau)) a.fb_list[atomicAdd(a.fb_count, 1)] = q;
+            if (!(a_min + a.eps < tau)) {
+                a.fb_list[atomicAdd(a.fb_count, 1)] = q;
+                // kc rows have approx >= a_min, hence exact >= a_min - eps: the exact rescan may skip anything below
+                a.gthr[q] = f2ord(a_min - a.eps);
+            }
         }
     }
 }

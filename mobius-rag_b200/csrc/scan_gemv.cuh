@@ -40,6 +40,7 @@ struct ScanArgs {
     // one full pass per group; *qcount == 0 makes the launch a no-op.  q0 / nq are ignored.
     const int* qlist;
     const int* qcount;
+    int qskip;              // ... starting at list entry qskip (the first entries were served by another kernel)
     // hybrid mode (HYB = 1, hybrid.cuh): per-query row bitmaps hmask[query][hwords] replace `mask`, and the
     // candidate key is built from the rerank score of (row, query) instead of the cosine
     const uint32_t* hmask;
@@ -74,12 +75,12 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
     const int nvec = ld / E;               // 16-byte vectors per row
     const int cap = 2 * a.kp;
 
-    const int total = a.qlist ? *a.qcount : a.nq;
+    const int total = a.qlist ? max(0, *a.qcount - a.qskip) : a.nq;
     for (int g0 = 0; g0 < total; g0 += NQ) {
         const int nq_here = min(NQ, total - g0);
         int qid[NQ];
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) qid[qi] = qi < nq_here ? (a.qlist ? a.qlist[g0 + qi] : a.q0 + g0 + qi) : 0;
+        for (int qi = 0; qi < NQ; ++qi) qid[qi] = qi < nq_here ? (a.qlist ? a.qlist[a.qskip + g0 + qi] : a.q0 + g0 + qi) : 0;
         if (g0) __syncthreads();               // the previous group's buffers are still being read
         // ---- stage the queries: fp32, split in 4-float planes so every LDS.128 is conflict free
         for (int i = tid; i < NQ * ld; i += kGemvThreads) {

@@ -67,6 +67,12 @@ struct MmaArgs {
     unsigned long long* stats;   // optional counters: [0] tiles, [1] tiles with a candidate, [2] keys appended,
                                  // [3] compactions, [4] overflow retries  (summed over hi warps / lanes)
     int tile_mul;            // 1: every 64-row tile; m > 1: only tiles 0, m, 2m, ... (threshold sampling pass)
+    // exact-rescan mode (rescore.cuh): serve the queries qlist[0 .. min(64, *qcount)) instead of [q0, q0 + nq);
+    // *qcount == 0 makes the launch a no-op
+    const int* qlist;
+    const int* qcount;
+    uint64_t* gcand;         // scan_mma128, large k: candidate buffers in GLOBAL memory [gridDim][128][cap] (appends are
+                             // rare once a bound exists; the buffers of one CTA stay in its L1 / L2); nullptr = shared memory
     uint32_t sleep_ns;       // suspend-time hint of the barrier waits
     unsigned long long* tstamps;   // optional [16] %globaltimer stamps of CTA 0 (debugging aid)
 };
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t slp = a.sleep_ns;
+    const int nq_eff = a.qlist ? min(kMmaQueries, *a.qcount) : a.nq;
+    if (nq_eff == 0) return;                            // nothing to rescan (uniform over the grid: no barrier is pending)
 #if MRAG_STAMPS
     auto stamp = [&](int i) { if (a.tstamps && blockIdx.x == 0 && lane == 0) a.tstamps[i] = globaltimer_ns(); };
 #else
@@ -381,8 +389,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
 
     // ---- queries -> tensor memory (epilogue warps; lane of TMEM = thread)
     if (warp >= 2) {
-        const bool live = qi < a.nq;
-        const float* qrow = a.q + size_t(a.q0 + (live ? qi : 0)) * a.ld;
+        const bool live = qi < nq_eff;
+        const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
+        const float* qrow = a.q + size_t(qsrc) * a.ld;
         for (int c0 = 0; c0 < a.ld / 2; c0 += 32) {         // 32 columns = 64 elements per store
             uint32_t r[32];
 #pragma unroll
@@ -509,10 +518,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         int as = 0, xs = 0;
         uint32_t aph = 0, xph = 0;
-        const bool live = qi < a.nq;
-        const bool warp_live = (quarter & 1) * 32 < a.nq;       // any query in this warp at all?
-        const float qinv = live ? a.qinv[a.q0 + qi] : 0.0f;
-        const uint64_t ubk = (a.ub && live) ? a.ub[a.q0 + qi] : ~0ull;
+        const bool live = qi < nq_eff;
+        const bool warp_live = (quarter & 1) * 32 < nq_eff;     // any query in this warp at all?
+        const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
+        const float qinv = live ? a.qinv[qsrc] : 0.0f;
+        const uint64_t ubk = (a.ub && live) ? a.ub[qsrc] : ~0ull;
         uint64_t* cand_warp = cand + size_t((quarter & 1) * 32) * a.cap;
         uint64_t* mybuf = cand_warp + size_t(lane) * a.cap;
         const int cap = a.cap;
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         // Cross-CTA bound: once ANY CTA holds k keys with score >= g, a row scoring below g cannot be
         // in the global top-k.  Rows scoring exactly g may still win a tie by row index, so the bound
         // admits s >= g, i.e. s > prev(g).  Read relaxed once per tile, raised after each compaction.
-        uint32_t* gslot = a.gthr + a.q0 + (live ? qi : 0);
+        uint32_t* gslot = a.gthr + qsrc;
         unsigned long long n_tiles = 0, n_slow = 0, n_keys = 0, n_compact = 0, n_retry = 0;
 
         uint2 m = tile_mask(t_first);
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         __syncwarp();
         if constexpr (KREG > 0) {
             if (live) {
-                uint64_t* out = a.part + (size_t(a.q0 + qi) * a.P + blockIdx.x) * a.kp;
+                uint64_t* out = a.part + (size_t(qsrc) * a.P + blockIdx.x) * a.kp;
                 if constexpr (SO) {
                     // keys stay unique across CTAs and slots (the merge's radix select relies on it); 0 = empty
 #pragma unroll
@@ -679,11 +689,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         } else {
             for (int L = 0; L < 32; ++L) {
                 const int qL = (quarter & 1) * 32 + L;
-                if (qL >= a.nq) break;
+                if (qL >= nq_eff) break;
                 const int n = __shfl_sync(kFull, st.cnt, L);
                 uint64_t* b = cand_warp + size_t(L) * a.cap;
                 warp_rank_select(b, n, a.kp, lane);
-                uint64_t* out = a.part + (size_t(a.q0 + qL) * a.P + blockIdx.x) * a.kp;
+                uint64_t* out = a.part + (size_t(__shfl_sync(kFull, qsrc, L)) * a.P + blockIdx.x) * a.kp;
                 const int have = n < a.k ? n : a.k;
                 for (int i = lane; i < a.kp; i += 32) out[i] = (i < have) ? b[i] : 0ull;
             }

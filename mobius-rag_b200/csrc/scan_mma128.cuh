@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                                    // stages * 8 KB
     float* xinv = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [4][64] 1/|x| of a tile's rows
-    uint64_t* cand = reinterpret_cast<uint64_t*>(xinv + kMma128InvSlots * 64);           // [128 queries][cap]
-    uint64_t* bars = cand + size_t(kMma128Queries) * a.cap;
+    uint64_t* smem_cand = reinterpret_cast<uint64_t*>(xinv + kMma128InvSlots * 64);      // [128 queries][cap] unless a.gcand
+    uint64_t* cand = a.gcand ? a.gcand + size_t(blockIdx.x) * kMma128Queries * a.cap : smem_cand;
+    uint64_t* bars = smem_cand + (a.gcand ? size_t(0) : size_t(kMma128Queries) * a.cap);
     uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
     uint64_t* empty_bar = full_bar + a.stages;       // [stages]   MMA -> TMA
     uint64_t* tfull_bar = empty_bar + a.stages;      // [2]        MMA -> select

@@ -33,16 +33,17 @@ struct MergeArgs {
     // each; block (q, g) writes the sorted top-k keys of its group to part_out[q][g][kp] and nothing else
     uint64_t* part_out;
     int Pg;
-    // exact-fallback mode: block b serves query qlist[b] and exits if b >= *qcount
+    // exact-fallback mode: block b serves query qlist[q_lo + b] and exits if q_lo + b >= min(*qcount, q_hi)
     const int* qlist;
     const int* qcount;
+    int q_lo, q_hi;         // q_hi == 0 means no upper limit
     int no_clamp;           // hybrid rerank scores are not cosines: do not clamp them to [-1, 1]
 };
 
 // Block-cooperative top-k of n UNIQUE non-zero keys in s[0..n): afterwards s[0..min(n,k)) holds the k largest,
 // descending; returns min(n, k).  A radix select (8 bits per pass from the top) finds the k-th largest key, the
 // k keys >= it are gathered and sorted -- ~10x cheaper than sorting thousands of keys to keep a few dozen.
-// k <= 128.  hist: 256 counters, small: 128 keys, misc: 4 ints (all shared memory).  All threads must call.
+// k <= 256.  hist: 256 counters, small: 256 keys, misc: 4 ints (all shared memory).  All threads must call.
 MRAG_DEVINL int block_topk(uint64_t* s, int n, int k, unsigned* hist, uint64_t* small, int* misc) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (n > k) {
@@ -104,14 +105,17 @@ MRAG_DEVINL int block_topk(uint64_t* s, int n, int k, unsigned* hist, uint64_t* 
 // alone already holds k keys >= T), so only the survivors are gathered and sorted.
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs a) {
     __shared__ uint64_t s[kMergeSlots];
-    __shared__ uint64_t s_small[128];
+    __shared__ uint64_t s_small[256];
     __shared__ unsigned s_hist[256];
     __shared__ int s_misc[4];
     __shared__ unsigned long long s_T;
     __shared__ int s_cnt;
     const int tid = threadIdx.x;
-    if (a.qlist && int(blockIdx.x) >= *a.qcount) return;
-    const int q = a.qlist ? a.qlist[blockIdx.x] : int(blockIdx.x);
+    if (a.qlist) {
+        const int lim = a.q_hi > 0 ? min(*a.qcount, a.q_hi) : *a.qcount;
+        if (a.q_lo + int(blockIdx.x) >= lim) return;
+    }
+    const int q = a.qlist ? a.qlist[a.q_lo + blockIdx.x] : int(blockIdx.x);
     const int p_lo = a.part_out ? int(blockIdx.y) * a.Pg : 0;
     const int P = a.part_out ? min(a.Pg, a.P - p_lo) : a.P;
     const uint64_t* base = a.part + (size_t(q) * a.P + p_lo) * a.kp;

@@ -567,7 +567,8 @@ def _fallbacks():
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("n,dim,nq,k", [
     (30000, 768, 130, 10), (5000, 96, 70, 32), (64, 64, 5, 10), (63, 64, 9, 1), (20000, 768, 256, 10),
-    (4097, 100, 129, 7), (100000, 768, 200, 10), (300, 768, 140, 20),
+    (4097, 100, 129, 7), (100000, 768, 200, 10), (300, 768, 140, 20), (30000, 768, 130, 100), (9000, 128, 70, 64),
+    (20000, 256, 150, 106),
 ])
 def test_mma128_rescore_exact(oracle, dtype, n, dim, nq, k):
     X, valid = synth.make_corpus(n, dim, seed=n + dim + 2, null_frac=3e-3)
@@ -591,10 +592,10 @@ def test_mma128_default_dispatch(oracle):
         s, r, c = idx.search(Q, 10)
         assert idx.last_scan_kind() == want, (dtype, nq)
         check_all(oracle, stored(oracle, X, dtype), Q, valid.astype(bool), 10, s, r, c, dtype)
-        s, r, c = idx.search(Q, 33)                    # k > 32: the exact kernels
+        s, r, c = idx.search(Q, 107)                   # k > 106: the exact kernels
         assert idx.last_scan_kind() != "mma128"
         with pytest.raises(N.MragError):
-            idx.search(Q, 33, options=N.OPT_FORCE_MMA128)
+            idx.search(Q, 107, options=N.OPT_FORCE_MMA128)
         idx.close()
     idx = Index(1536, "bf16", 0, 100)                  # dim > 768: no tensor-core path
     idx.append(np.ones((10, 1536), np.float32))

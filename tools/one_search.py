@@ -30,3 +30,5 @@ for _ in range(reps):
     idx.search_device(Q, k)
 torch.cuda.synchronize()
 print("kind", idx.last_scan_kind(), "scan_ms", idx.last_kernel_ms(1), "total_ms", idx.last_kernel_ms(3))
+from mrag_b200 import _native as N
+print("fallbacks", N.load().mrag_debug_fallback_count())
