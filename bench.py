@@ -428,7 +428,7 @@ def main():
 
     def roofline_of(m, batch):
         kind = idx.last_scan_kind()
-        group = {"gemv": 4, "mma": 64, "mma128": 128}[kind]      # queries per scan launch
+        group = {"gemv": 4, "gemv_shadow": 4, "mma": 64, "mma128": 128}[kind]      # queries per scan launch
         scan_launches = (batch + group - 1) // group
         if not m["scan_ms"]:
             return None
@@ -437,9 +437,9 @@ def main():
         # bytes the scan kernel has to stream: the rows that pass the filter in the storage it reads (the
         # tensor-core kernels read bf16 rows -- for an fp32 corpus its bf16 shadow; the rows are 64-row tiles,
         # so with a document filter whole passing tiles are read), the mask, 1/|x|, queries in, lists out
-        scan_elem = 2 if kind in ("mma", "mma128") else elem
+        scan_elem = 2 if kind in ("mma", "mma128", "gemv_shadow") else elem
         n_pass = int(n_local * pass_frac)
-        bytes_launch = (n_pass * args.dim * scan_elem + (n_local + 7) // 8 + (n_pass * 4 if kind != "gemv" else 0)
+        bytes_launch = (n_pass * args.dim * scan_elem + (n_local + 7) // 8 + (n_pass * 4 if kind in ("mma", "mma128") else 0)
                         + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12)
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         traffic = load_traffic(f"scan_{idx.last_scan_kind()}", args, n_local, q_per_launch)
@@ -480,6 +480,17 @@ def main():
     if ss is None:
         assert torch.equal(hr, m["result"][1].cpu()), "e2e result differs from device-resident result"
 
+    # ---- where a sharded step spends its time: local search / allgather / k-way merge (rank 0's view)
+    shard_phases = None
+    if ss is not None:
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        barrier()
+        for i in range(args.steps):
+            ss.search(m["Q"], args.k, flt, events=evs[i])
+        barrier()
+        shard_phases = {name: float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs]))
+                        for j, name in enumerate(("local_search", "allgather", "kway_merge"))}
+
     # ---- brief sweep over other batch sizes (N=1 only, not the headline)
     sweep = []
     if world == 1 and args.sweep:
@@ -517,6 +528,8 @@ def main():
                           "merge": float(np.mean(m["merge_ms"])) if m["merge_ms"] else None},
             "rows_per_gpu": n_local, "build_s": t_build, "sweep": sweep,
         }
+        if shard_phases:
+            line["shard_phases_ms"] = shard_phases
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

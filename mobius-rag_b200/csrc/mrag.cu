@@ -259,8 +259,9 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
         return code;
     }
     const char* shadow_env = getenv("MRAG_F32_SHADOW");
-    if (dtype == MRAG_F32 && x->ld <= kMmaMaxLd && !(shadow_env && shadow_env[0] == '0')) {
-        // +50% memory buys the 128-queries-per-pass tensor-core scan for large batches
+    if (dtype == MRAG_F32 && !(shadow_env && shadow_env[0] == '0')) {
+        // +50% memory buys candidate scans at 2 B per element (tensor-core, 128 queries per pass, for dim <= 768;
+        // CUDA-core over the shadow otherwise) with exact rescoring
         cudaError_t es = cudaMalloc(&x->shadow, size_t(cap32) * x->ld * 2 + (2u << 20));
         if (es != cudaSuccess) { x->shadow = nullptr; cudaGetLastError(); }   // not fatal: exact scan only
     }
@@ -678,6 +679,15 @@ static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
 // largest k of the candidate-generating path: K' = 1.5 k nominees + 32 slack keys must fit a warp's rank sort (192 keys)
 static const int kMma128MaxK = 106;
 
+// fp32 shards: nominate from the bf16 shadow on the CUDA cores when the shard is big enough for the halved traffic to
+// pay for the extra launches (rescoring, finalize, no-op rescan): >= 128M elements (256 MB of shadow) by default;
+// MRAG_SHADOW_GEMV_MIN_ELEMS overrides (0 = always, tests; a huge value pins the exact fp32 scan).
+static bool shadow_gemv_wanted(int64_t n, int ld) {
+    const char* e = getenv("MRAG_SHADOW_GEMV_MIN_ELEMS");
+    const long long min_elems = (e && *e) ? atoll(e) : (128ll << 20);
+    return n * int64_t(ld) >= min_elems;
+}
+
 static int approx_min_nq() {
     static const int v = [] {
         const char* e = getenv("MRAG_APPROX_MIN_NQ");
@@ -713,8 +723,10 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
 // Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or
 // the bf16 shadow), exact rescoring of the K' = k + 32 nominees from the primary rows, certificate,
 // exact CUDA-core rescan of the queries that fail it.  Results are EXACT (same arithmetic as scan_gemv).
+// gen_gemv: nominate with the CUDA-core scan over the bf16 shadow instead (fp32 shards of any width, small batches):
+// half the bytes of the exact fp32 scan, eps = 2^-9 (the shadow's rounding; the query stays fp32).
 static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int nq, int k, const uint32_t* mask,
-                                 float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t s) {
+                                 float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t s, bool gen_gemv) {
     const int64_t n = x->size;
     const int ld = x->ld;
     // nominees per query: k + 32, or 1.5 k for large k (the number of rows within eps of the k-th best grows with k)
@@ -728,14 +740,29 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     const char* eps_env = getenv("MRAG_APPROX_EPS_SCALE");     // tests: a huge scale sends every query to the rescan
     const float eps_scale = (eps_env && *eps_env) ? float(atof(eps_env)) : 1.0f;
     // |approx - exact| <= 2^-9 (bf16 query) + 2^-9 (the shadow's rounding, fp32 corpora) + accumulation slop
-    const float eps = (0x1p-9f + (x->dtype == MRAG_F32 ? 0x1p-9f : 0.0f) + 5e-5f) * eps_scale;
+    const float eps = ((gen_gemv ? 0.0f : 0x1p-9f) + (x->dtype == MRAG_F32 ? 0x1p-9f : 0.0f) + 5e-5f) * eps_scale;
 
-    if (w->part.reserve(size_t(nq) * std::max(grid * kpc, ggrid * kp)) || w->gthr.reserve(size_t(nq)) ||
+    if (w->part.reserve(size_t(nq) * std::max(std::max(grid, ggrid) * kpc, ggrid * kp)) || w->gthr.reserve(size_t(nq)) ||
         w->cscores.reserve(size_t(nq) * kc) || w->crows.reserve(size_t(nq) * kc) || w->ccounts.reserve(size_t(nq)) ||
         w->ckeys.reserve(size_t(nq) * kc) || w->fb.reserve(size_t(nq) + 1))
         return MRAG_ERR_OOM;
     CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
     CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
+    int rc;
+    if (gen_gemv) {
+        ScanArgs ga{};
+        ga.rows = x->shadow; ga.n = n; ga.ld = ld; ga.mask = mask; ga.q = w->qpad.p; ga.qinv = w->qinv.p; ga.ub = nullptr;
+        ga.part = w->part.p; ga.k = kc; ga.kp = kpc; ga.P = ggrid;
+        int q0 = 0;
+        while (q0 < nq) {
+            const int left = nq - q0;
+            const int g = gemv_nq_for(left >= 3 ? 4 : left, ld, kpc);
+            ga.q0 = q0; ga.nq = std::min(g, left);
+            rc = g == 4 ? launch_gemv<1, 4>(ga, ggrid, s) : g == 2 ? launch_gemv<1, 2>(ga, ggrid, s) : launch_gemv<1, 1>(ga, ggrid, s);
+            if (rc != MRAG_OK) return rc;
+            q0 += ga.nq;
+        }
+    } else {
     MmaArgs a{};
     a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
     a.part = w->part.p; a.k = kc; a.kp = kpc; a.P = grid; a.cap = cap;
@@ -750,7 +777,6 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         a.stats = w->stats.p;
         t_stats_ptr = w->stats.p;
     }
-    int rc;
     const int64_t tiles = ceil_div(n, kMmaTileRows);
     if (tiles >= sample_min_tiles(x->num_sms)) {
         // admission bound from a strided sample (4 tiles per CTA), same arithmetic, register top-16 per CTA: the
@@ -775,10 +801,11 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     }
     rc = launch_scan_mma128<0>(x, a, nq, grid, s);
     if (rc != MRAG_OK) return rc;
+    }
     CU(cudaEventRecord(ev.e[2], s));
     // nominees per query, by approximate score
     MergeArgs m{};
-    m.part = w->part.p; m.P = grid; m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
+    m.part = w->part.p; m.P = gen_gemv ? ggrid : grid; m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
     m.scores = w->cscores.p; m.rows = w->crows.p; m.counts = w->ccounts.p; m.row_base = 0;
     rc = launch_merge(w, m, nq, s);
     if (rc != MRAG_OK) return rc;
@@ -798,7 +825,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     LAUNCHED();
     // exact rescan of the queries whose certificate failed (no-op launches when there are none): the first 64 of
     // them in ONE pass of the exact tensor-core scan (bf16 shards), the rest -- and fp32 shards -- on the CUDA cores
-    const bool exact_mma = x->dtype == MRAG_BF16;
+    const bool exact_mma = x->dtype == MRAG_BF16 && x->has_tmap;
     int gskip = 0;
     if (exact_mma) {
         MmaArgs e{};
@@ -903,19 +930,22 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             return fail(MRAG_ERR_STATE, "mrag_search: the 128-query scan needs bf16 rows or a bf16 shadow, dim <= %d, k <= %d", kMmaMaxLd, kMma128MaxK);
         use_mma128 = true;
     }
-    if (use_mma128) {
-        int rc = search_approx_rescore(x, w, ev, nq, k, mask, d_scores, d_rows, d_counts, s);
+    // fp32 shards that cannot (dim > 768) or should not (few queries) take the tensor-core candidate scan still
+    // halve their traffic by nominating from the bf16 shadow on the CUDA cores
+    const bool use_shadow_gemv = !use_mma128 && !use_mma && x->dtype == MRAG_F32 && x->shadow && n > 0 && k <= kMma128MaxK &&
+                                 !(options & (MRAG_OPT_FORCE_GEMV | MRAG_OPT_FORCE_MMA | MRAG_OPT_FORCE_MMA128)) && shadow_gemv_wanted(n, ld);
+    if (use_mma128 || use_shadow_gemv) {
+        int rc = search_approx_rescore(x, w, ev, nq, k, mask, d_scores, d_rows, d_counts, s, use_shadow_gemv);
         if (rc != MRAG_OK) return rc;
-        t_last_kind = "mma128";
+        t_last_kind = use_mma128 ? "mma128" : "gemv_shadow";
     }
     const int grid = use_mma
         ? int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))))
         : int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
     if (rounds > 1 && w->ub.reserve(size_t(nq))) return MRAG_ERR_OOM;
-    float scan_ms_dummy = 0; (void)scan_ms_dummy;
     // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
     // earlier rounds is attributed to the scan phase
-    for (int r = 0; r < rounds && !use_mma128; ++r) {
+    for (int r = 0; r < rounds && !use_mma128 && !use_shadow_gemv; ++r) {
         const int k_off = r * MRAG_FUSED_K;
         const int kr = std::min(MRAG_FUSED_K, k - k_off);
         const int kp = std::max(8, host_next_pow2(kr));

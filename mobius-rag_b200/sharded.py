@@ -94,12 +94,22 @@ class ShardedSearcher:
                           (lay["size"] // 4, lay["size"] // 8, lay["size"] // 4))
 
     # -- the search --------------------------------------------------------------------------
-    def search(self, q, k: int, flt=None):
+    def search(self, q, k: int, flt=None, events=None):
         """q: [nq, dim] float32 on this rank's device, identical on every rank.
-        Returns (scores [nq,k], rows [nq,k] global ids, counts [nq]) on every rank."""
+        Returns (scores [nq,k], rows [nq,k] global ids, counts [nq]) on every rank.
+        events: optional list of 4 torch.cuda.Event (timing enabled) recorded around the three phases."""
         nq = int(q.shape[0])
         lay, slot, gathered = self._buffers(nq, k)
+        if events:
+            events[0].record()
         self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        if events:
+            events[1].record()
         if self.world > 1:
             self.dist.all_gather_into_tensor(gathered, slot, group=self.group)
-        return self._merge(gathered, self.world, nq, k, lay)
+        if events:
+            events[2].record()
+        out = self._merge(gathered, self.world, nq, k, lay)
+        if events:
+            events[3].record()
+        return out

@@ -652,3 +652,29 @@ def test_mma128_with_filters_ties_and_nan(oracle):
             s, r, c = idx.search(Q, k, flt, options=N.OPT_FORCE_MMA128)
             check_all(oracle, Xs, Q, m, k, s, r, c, dtype)
         idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 shards of any width / small batches: candidates from the bf16 shadow on the CUDA cores,
+# exact rescoring + certificate + exact rescan (same machinery as the 128-query path)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim,nq,k", [(20000, 1536, 1, 10), (9000, 1536, 6, 10), (30000, 768, 3, 10), (5000, 100, 2, 100),
+                                        (64, 64, 1, 5), (3000, 2000, 1, 40)])
+def test_gemv_shadow_rescore_exact(oracle, monkeypatch, n, dim, nq, k):
+    monkeypatch.setenv("MRAG_SHADOW_GEMV_MIN_ELEMS", "0")
+    X, valid = synth.make_corpus(n, dim, seed=n + dim + 3, null_frac=3e-3)
+    X[10:14] = 0.0
+    Q = synth.make_queries(X, nq, seed=k + 3)
+    idx = Index(dim, "f32", 0, n + 5)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k)
+    assert idx.last_scan_kind() == "gemv_shadow"
+    check_all(oracle, X, Q, valid.astype(bool), k, s, r, c, "f32")
+    monkeypatch.setenv("MRAG_APPROX_EPS_SCALE", "1e6")           # every certificate fails -> exact rescan
+    s2, r2, c2 = idx.search(Q, k)
+    assert _fallbacks() == nq
+    check_all(oracle, X, Q, valid.astype(bool), k, s2, r2, c2, "f32")
+    monkeypatch.setenv("MRAG_SHADOW_GEMV_MIN_ELEMS", str(1 << 60))
+    idx.search(Q, k)
+    assert idx.last_scan_kind() == "gemv"                          # small shards keep the exact fp32 scan
+    idx.close()
