@@ -219,25 +219,34 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
                     const float nx = acc[j][NQ];
                     if (!HYB && !(nx > 0.0f)) continue;     // zero-norm row: similarity is NaN (NaN tail pass)
                     const float inv = rsqrtf(nx);
-                    mrag_chunkfeat f;
-                    const uint64_t* jt = nullptr;
-                    uint32_t auth_code = 31u;
+                    // hybrid: lane L scores query L of the group (the queries' rerank scores in parallel, not 4x in
+                    // lock step), then the scores travel by shuffle into the warp-uniform select below
+                    float hyb_s = CUDART_NAN_F;
                     if (HYB) {
-                        f = a.feat[r[j]];
-                        auth_code = a.authority[r[j]];
-                        const uint32_t d = a.doc_idx[r[j]];
-                        if (a.doc_jtags && int64_t(d) < a.n_jtag_docs) jt = a.doc_jtags + size_t(d) * MRAG_JTAG_WORDS;
+                        float dotL = 0.0f, qinvL = 0.0f;
+                        uint32_t mqL = 0u;
+#pragma unroll
+                        for (int qi = 0; qi < NQ; ++qi) {
+                            dotL = (lane == qi) ? acc[j][qi] : dotL;
+                            qinvL = (lane == qi) ? qinv[qi] : qinvL;
+                            mqL = (lane == qi) ? mq[qi] : mqL;
+                        }
+                        if (lane < nq_here && ((mqL >> (r[j] & 31u)) & 1u)) {      // passes the filter and this query's coverage floor
+                            const mrag_chunkfeat f = a.feat[r[j]];
+                            const uint32_t auth_code = a.authority[r[j]];
+                            const uint32_t d = a.doc_idx[r[j]];
+                            const uint64_t* jt = (a.doc_jtags && int64_t(d) < a.n_jtag_docs) ? a.doc_jtags + size_t(d) * MRAG_JTAG_WORDS : nullptr;
+                            const float cs = (nx > 0.0f) ? dotL * inv * qinvL : CUDART_NAN_F;
+                            // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
+                            const float c01 = (cs == cs) ? cs : 1.0f;
+                            hyb_s = hybrid_score(hq[lane], f, hybrid_eval(hq[lane], f, jt), c01, auth_code);
+                        }
                     }
 #pragma unroll
                     for (int qi = 0; qi < NQ; ++qi) {
                         if (qi >= nq_here) break;
                         float s = (nx > 0.0f) ? acc[j][qi] * inv * qinv[qi] : CUDART_NAN_F;
-                        if (HYB) {
-                            if (!((mq[qi] >> (r[j] & 31u)) & 1u)) continue;       // filtered out or below this query's coverage floor
-                            // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
-                            const float c01 = (s == s) ? s : 1.0f;
-                            s = hybrid_score(hq[qi], f, hybrid_eval(hq[qi], f, jt), c01, auth_code);
-                        }
+                        if (HYB) s = __shfl_sync(kFull, hyb_s, qi);           // NaN: row not eligible for this query
                         if (!(s == s)) continue;            // zero-norm query
                         const uint64_t key = make_key(s, r[j]);
                         if (key > thr[qi] && key < ubk[qi]) {
