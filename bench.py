@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the CPU baseline sample")
     ap.add_argument("--cpu-queries", type=int, default=8, help="queries of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--threads", type=int, default=32, help="host threads of the concurrent single-query measurement (0 = skip)")
     ap.add_argument("--tag-filter", type=int, default=0, metavar="M",
                     help="document-tag filter passing every M-th document (0 = no filter); C2 uses 10")
     ap.add_argument("--payer-filter", type=int, default=0, metavar="M",
@@ -503,6 +504,33 @@ def main():
                           "scan_frac_of_hbm_peak": rr["frac"] if rr else None,
                           "kernel": f"scan_{idx.last_scan_kind()}"})
 
+    # ---- serving view: T host threads issuing single-query searches through the host-buffer C ABI, with and
+    #      without request coalescing (concurrent requests share one pass over the corpus)
+    concurrent = None
+    if world == 1 and args.threads > 0:
+        from mrag_b200 import _native as N
+        Qc = synth.cuda_queries(plant, 256, args.dim, dev, seed=99).cpu().numpy()
+
+        def serve(opts, seconds=1.0):
+            done = [0] * args.threads
+            stop = time.perf_counter() + seconds
+
+            def worker(t):
+                i = t
+                while time.perf_counter() < stop:
+                    idx.search(Qc[i % 256:i % 256 + 1], args.k, flt, options=opts)
+                    done[t] += 1
+                    i += args.threads
+            th = [threading.Thread(target=worker, args=(t,)) for t in range(args.threads)]
+            t0 = time.perf_counter()
+            [x.start() for x in th]
+            [x.join() for x in th]
+            return sum(done) / (time.perf_counter() - t0)
+        serve(0, 0.2)
+        concurrent = {"threads": args.threads, "qps_independent_calls": serve(0),
+                      "qps_coalesced_calls": serve(N.OPT_COALESCE) if flt is None else None,
+                      "note": "single-query mrag_search calls from host threads, host buffers; coalesced = MRAG_OPT_COALESCE"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -530,6 +558,8 @@ def main():
         }
         if shard_phases:
             line["shard_phases_ms"] = shard_phases
+        if concurrent:
+            line["concurrent_single_query"] = concurrent
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

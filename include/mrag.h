@@ -165,7 +165,12 @@ enum {
     MRAG_OPT_FORCE_GEMV  = 1u << 1, /* pin the CUDA-core streaming kernel (testing / tuning) */
     MRAG_OPT_FORCE_MMA   = 1u << 2, /* pin the tcgen05 kernel (testing / tuning)             */
     MRAG_OPT_NO_SYNC     = 1u << 3, /* with DEVICE_IO: enqueue only, do not synchronise the stream */
-    MRAG_OPT_FORCE_MMA128 = 1u << 4 /* pin the 128-query candidate scan + exact rescoring (testing / tuning) */
+    MRAG_OPT_FORCE_MMA128 = 1u << 4, /* pin the 128-query candidate scan + exact rescoring (testing / tuning) */
+    MRAG_OPT_COALESCE    = 1u << 5  /* host buffers, no filter, NULL stream: requests from concurrent host threads that arrive
+                                       while a scan is in flight are served together by the next scan (one pass over the
+                                       corpus for up to 1024 queries).  The reference issues single-query statements from up
+                                       to 5 concurrent narrow searches per request plus uvicorn concurrency
+                                       (corpus_search_agent.py:794-797); a lone request is served immediately. */
 };
 
 /*

@@ -18,7 +18,7 @@ MRAG_PAYER_WORDS, MRAG_SMALL_WORDS, MRAG_TAG_WORDS = 16, 4, 8
 MRAG_CODE_NONE = 0xFFFF
 F_PAYER, F_STATE, F_PROGRAM, F_AUTHORITY, F_SOURCE_TYPE = 1, 2, 4, 8, 16
 F_DOC_EQ, F_DOC_POOL, F_TAG_STRICT, F_TAG_RELAXED = 32, 64, 128, 256
-OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC, OPT_FORCE_MMA128 = 1, 2, 4, 8, 16
+OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC, OPT_FORCE_MMA128, OPT_COALESCE = 1, 2, 4, 8, 16, 32
 MRAG_PHRASE_WORDS, MRAG_JPD_CATS, MRAG_JTAG_WORDS, MRAG_HYB_MAX_PHRASES = 2, 11, 4, 16
 CF_SHORT_TEXT, CF_CONTACT_VALUE, CF_PROMOTED = 1, 2, 4
 

@@ -8,6 +8,7 @@ match_score, _arm) and the same fail-soft rule: any exception is logged and ``[]
 from __future__ import annotations
 
 import asyncio
+import os
 import json
 import logging
 from dataclasses import dataclass, field
@@ -161,7 +162,8 @@ def vector_arm(
             f: Filter = table.filter_corpus(filters, include_document_ids)
             if tagclause is not None:
                 tagclause(f)
-            scores, rows, counts = table.index.search(q[None, :], sql_limit, f if f.active else None)
+            opts = N.OPT_COALESCE if (not f.active and os.getenv("MRAG_COALESCE", "1") != "0") else 0
+            scores, rows, counts = table.index.search(q[None, :], sql_limit, f if f.active else None, options=opts)
             n = int(counts[0])
             return rows[0, :n], scores[0, :n]
 

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -153,6 +154,18 @@ struct mrag_index {
     std::shared_mutex lock;             // searches share, writers exclude
     std::mutex ws_lock;
     std::vector<Workspace*> pool;
+    // request coalescing (MRAG_OPT_COALESCE): unfiltered host-buffer searches that arrive while a scan is in flight
+    // queue up and run as ONE batch (one pass over the corpus serves up to 1024 queries) when it ends
+    struct Pending {
+        const float* q; int nq; int k; uint32_t options;
+        float* scores; int64_t* rows; int32_t* counts;
+        int rc = 0; std::string err; bool done = false;
+    };
+    std::mutex co_lock;
+    std::condition_variable co_cv;
+    std::vector<Pending*> co_queue;
+    bool co_busy = false;
+    std::atomic<int64_t> co_batches{0}, co_requests{0};
 };
 
 struct DeviceGuard {
@@ -1038,8 +1051,88 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     return MRAG_OK;
 }
 
+static int search_direct(mrag_index* x, const float* q, int nq, int k, const mrag_filter* filter, float* scores,
+                         int64_t* rows, int32_t* counts, uint32_t options, void* stream);
+
+// One thread at a time is the "leader": it drains every queued request with its own k into one batch, runs it, hands
+// the results back and passes leadership on.  No timer: an idle index serves a lone request immediately; under load
+// the batch is whatever arrived during the previous scan.
+static int search_coalesced(mrag_index* x, const float* q, int nq, int k, float* scores, int64_t* rows, int32_t* counts,
+                            uint32_t options) {
+    mrag_index::Pending me;
+    me.q = q; me.nq = nq; me.k = k; me.options = options; me.scores = scores; me.rows = rows; me.counts = counts;
+    std::unique_lock<std::mutex> l(x->co_lock);
+    x->co_queue.push_back(&me);
+    x->co_requests.fetch_add(1, std::memory_order_relaxed);
+    for (;;) {
+        if (me.done) break;
+        if (x->co_busy) { x->co_cv.wait(l); continue; }
+        // become the leader for one batch
+        x->co_busy = true;
+        std::vector<mrag_index::Pending*> batch;
+        int total = 0;
+        for (auto it = x->co_queue.begin(); it != x->co_queue.end();) {
+            mrag_index::Pending* p = *it;
+            if (p->k == me.k && p->options == me.options && total + p->nq <= 1024) { batch.push_back(p); total += p->nq; it = x->co_queue.erase(it); }
+            else ++it;
+        }
+        l.unlock();
+        int rc = MRAG_OK;
+        if (batch.size() == 1) {
+            mrag_index::Pending* p = batch[0];
+            rc = search_direct(x, p->q, p->nq, p->k, nullptr, p->scores, p->rows, p->counts, p->options, nullptr);
+            p->rc = rc; if (rc != MRAG_OK) p->err = t_err;
+        } else {
+            const size_t dim = size_t(x->dim);
+            std::vector<float> Q(size_t(total) * dim), S(size_t(total) * me.k);
+            std::vector<int64_t> R(size_t(total) * me.k);
+            std::vector<int32_t> C;
+            C.resize(size_t(total));
+            size_t off = 0;
+            for (auto* p : batch) { memcpy(Q.data() + off * dim, p->q, size_t(p->nq) * dim * 4); off += size_t(p->nq); }
+            rc = search_direct(x, Q.data(), total, me.k, nullptr, S.data(), R.data(), C.data(), me.options, nullptr);
+            off = 0;
+            for (auto* p : batch) {
+                if (rc == MRAG_OK) {
+                    memcpy(p->scores, S.data() + off * me.k, size_t(p->nq) * me.k * 4);
+                    memcpy(p->rows, R.data() + off * me.k, size_t(p->nq) * me.k * 8);
+                    memcpy(p->counts, C.data() + off, size_t(p->nq) * 4);
+                } else {
+                    p->err = t_err;
+                }
+                p->rc = rc;
+                off += size_t(p->nq);
+            }
+        }
+        x->co_batches.fetch_add(1, std::memory_order_relaxed);
+        l.lock();
+        for (auto* p : batch) p->done = true;
+        x->co_busy = false;
+        x->co_cv.notify_all();
+        // (if this thread's own request had a different k than the batch it led -- impossible: it leads its own k)
+    }
+    if (me.rc != MRAG_OK) t_err = me.err;
+    return me.rc;
+}
+
 extern "C" int mrag_search(mrag_index* x, const float* q, int nq, int k, const mrag_filter* filter, float* scores,
                            int64_t* rows, int32_t* counts, uint32_t options, void* stream) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_search: null index");
+    if ((options & MRAG_OPT_COALESCE) && !(options & MRAG_OPT_DEVICE_IO) && !stream && !(filter && filter->flags) &&
+        q && scores && rows && counts && nq >= 1 && nq <= 1024 && k >= 1 && k <= MRAG_MAX_K)
+        return search_coalesced(x, q, nq, k, scores, rows, counts, options & ~uint32_t(MRAG_OPT_COALESCE));
+    return search_direct(x, q, nq, k, filter, scores, rows, counts, options & ~uint32_t(MRAG_OPT_COALESCE), stream);
+}
+
+// (debugging aid, not in mrag.h) coalescing counters: out2[0] = batches run, out2[1] = requests served
+extern "C" int mrag_debug_coalesce_stats(mrag_index* x, int64_t* out2) {
+    if (!x || !out2) return MRAG_ERR_ARG;
+    out2[0] = x->co_batches.load(); out2[1] = x->co_requests.load();
+    return MRAG_OK;
+}
+
+static int search_direct(mrag_index* x, const float* q, int nq, int k, const mrag_filter* filter, float* scores,
+                         int64_t* rows, int32_t* counts, uint32_t options, void* stream) {
     if (!x) return fail(MRAG_ERR_ARG, "mrag_search: null index");
     if (nq < 0) return fail(MRAG_ERR_ARG, "mrag_search: nq < 0");
     if (nq == 0) return MRAG_OK;

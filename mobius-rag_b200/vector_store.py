@@ -125,7 +125,10 @@ class B200VectorStore(VectorStore):
         if q.shape[0] != t.index.dim:
             raise ValueError(f"different vector dimensions {t.index.dim} and {q.shape[0]}")   # pgvector's error
         flt = t.filter_pg_store(document_id, filters)
-        scores, rows, counts = t.index.search(q[None, :], k, flt)
+        # unfiltered requests from concurrent threads (asearch -> to_thread) share one pass over the corpus
+        from . import _native as N
+        opts = N.OPT_COALESCE if (flt is None and os.getenv("MRAG_COALESCE", "1") != "0") else 0
+        scores, rows, counts = t.index.search(q[None, :], k, flt, options=opts)
         out: list[dict] = []
         for j in range(int(counts[0])):
             r = int(rows[0, j])

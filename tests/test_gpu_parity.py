@@ -678,3 +678,41 @@ def test_gemv_shadow_rescore_exact(oracle, monkeypatch, n, dim, nq, k):
     idx.search(Q, k)
     assert idx.last_scan_kind() == "gemv"                          # small shards keep the exact fp32 scan
     idx.close()
+
+
+def test_coalesced_concurrent_searches(oracle):
+    """MRAG_OPT_COALESCE: single-query searches from many host threads are served in shared passes and every
+    caller gets exactly what a lone search returns."""
+    import ctypes as C
+    n, dim, k = 150_000, 256, 10
+    X, valid = synth.make_corpus(n, dim, seed=77)
+    idx = Index(dim, "bf16", 0, n)
+    idx.append(X, make_meta(n, valid=valid))
+    T, per = 16, 12
+    Q = synth.make_queries(X, T * per, seed=78)
+    want = [idx.search(Q[i:i + 1], k) for i in range(T * per)]
+    got = [None] * (T * per)
+    errs = []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                i = t * per + j
+                got[i] = idx.search(Q[i:i + 1], k, options=N.OPT_COALESCE)
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs
+    for g, w in zip(got, want):
+        assert (g[1] == w[1]).all() and (g[2] == w[2]).all()
+        assert np.abs(g[0] - w[0]).max() <= 2e-6
+    stats = (C.c_int64 * 2)()
+    N.load().mrag_debug_coalesce_stats(idx._h, stats)
+    assert stats[1] == T * per and 1 <= stats[0] <= stats[1]
+    # mixed k and a filtered call (never coalesced) still work side by side
+    s1 = idx.search(Q[:1], 5, options=N.OPT_COALESCE)
+    s2 = idx.search(Q[:1], 5, Filter().doc_eq(7), options=N.OPT_COALESCE)
+    assert s1[2][0] == 5 and s2[2][0] <= 5
+    idx.close()
