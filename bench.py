@@ -374,7 +374,7 @@ def main():
 
     def make_searcher():
         if world > 1:
-            return sharded.ShardedSearcher(index=idx)
+            return sharded.ShardedSearcher(index=idx, exchange=os.environ.get("MRAG_EXCHANGE", "auto"))
         return None
     ss = make_searcher()
 
@@ -558,6 +558,9 @@ def main():
         }
         if shard_phases:
             line["shard_phases_ms"] = shard_phases
+        if ss is not None:
+            line["config"]["exchange"] = ("peer stores inside the merge kernel (symmetric memory)" if ss.exchange != "nccl" and ss._p2p
+                                          else "NCCL all_gather_into_tensor + merge kernel")
         if concurrent:
             line["concurrent_single_query"] = concurrent
         print(json.dumps(line), flush=True)

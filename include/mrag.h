@@ -273,6 +273,18 @@ int mrag_merge_topk(int device, int n_lists, int nq, int k,
                     int64_t stride_scores, int64_t stride_rows, int64_t stride_counts,
                     float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream);
 
+/* K4 fused with the exchange (row-sharded search without a collective call): every rank's results travel by peer
+ * STORES over NVLink into each peer's gather buffer, a per-(peer, query) flag follows, and the same kernel waits for
+ * the peers' flags and merges.  peer_bufs: HOST array of `world` (<= 8) device pointers, peer_bufs[r] = rank r's
+ * buffer mapped into this process (symmetric memory), each laid out as
+ *     2 gather areas of world * slot_bytes  |  flags u32[world][nq]   (zero-initialised once)
+ * with a slot = rows i64[nq*k] | scores f32[nq*k] at scores_off | counts i32[nq] at counts_off.  The caller writes its
+ * own results into slot `rank` of area (epoch & 1) of ITS buffer (e.g. with mrag_search, MRAG_OPT_DEVICE_IO) and then
+ * calls this with epoch = 1, 2, 3, ... on every rank.  Outputs as mrag_merge_topk. */
+int mrag_exchange_merge(int device, int world, int rank, int nq, int k, void* const* peer_bufs,
+                        int64_t slot_bytes, int64_t scores_off, int64_t counts_off, uint32_t epoch,
+                        float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream);
+
 /* K2 alone: evaluate `filter` into a row bitmap (bit r of word r/32), DEVICE pointer,
  * ceil(size/32) words; *n_pass (HOST, may be NULL) gets the popcount. */
 int mrag_filter_mask(mrag_index* idx, const mrag_filter* filter, uint32_t* d_mask_out,

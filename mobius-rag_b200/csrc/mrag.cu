@@ -1478,6 +1478,38 @@ extern "C" int mrag_merge_topk(int device, int n_lists, int nq, int k, const flo
     return MRAG_OK;
 }
 
+extern "C" int mrag_exchange_merge(int device, int world, int rank, int nq, int k, void* const* peer_bufs,
+                                   int64_t slot_bytes, int64_t scores_off, int64_t counts_off, uint32_t epoch,
+                                   float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || nq < 1 || k < 1) return fail(MRAG_ERR_ARG, "mrag_exchange_merge: bad sizes");
+    if (int64_t(world) * k > kXMergeMaxSlots) return fail(MRAG_ERR_ARG, "mrag_exchange_merge: world*k = %lld > %d", (long long)world * k, kXMergeMaxSlots);
+    if (!peer_bufs || !d_scores_out || !d_rows_out || !d_counts_out) return fail(MRAG_ERR_ARG, "mrag_exchange_merge: null buffer");
+    if (epoch == 0) return fail(MRAG_ERR_ARG, "mrag_exchange_merge: epochs start at 1 (flags are zero-initialised)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_exchange_merge: cudaSetDevice(%d) failed (no CPU path)", device);
+    static bool attr_set[64] = {};
+    if (device < 64 && !attr_set[device]) {
+        CU(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXMergeMaxSlots * 12));
+        attr_set[device] = true;
+    }
+    XchgArgs a{};
+    a.world = world; a.rank = rank; a.nq = nq; a.k = k;
+    for (int p = 0; p < world; ++p) {
+        if (!peer_bufs[p]) return fail(MRAG_ERR_ARG, "mrag_exchange_merge: peer buffer %d is null", p);
+        a.bufs[p] = static_cast<unsigned char*>(peer_bufs[p]);
+    }
+    a.slot_bytes = slot_bytes; a.scores_off = scores_off; a.counts_off = counts_off;
+    a.area_bytes = int64_t(world) * slot_bytes;
+    a.flags_off = 2 * a.area_bytes;
+    a.epoch = epoch;
+    a.scores_out = d_scores_out; a.rows_out = d_rows_out; a.counts_out = d_counts_out;
+    const int total = world * k;
+    const size_t smem = size_t(host_next_pow2(total < 2 ? 2 : total)) * 12;
+    xchg_merge_kernel<<<nq, kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    LAUNCHED();
+    return MRAG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------

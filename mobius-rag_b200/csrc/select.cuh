@@ -311,4 +311,107 @@ __global__ void __launch_bounds__(kMergeThreads, 1) xmerge_kernel(const XMergeAr
     if (tid == 0) a.counts_out[q] = got;
 }
 
+// K4 fused with the exchange: instead of an allgather followed by the merge, every rank's block q STORES its k
+// results for query q straight into each peer's gather buffer over NVLink (peer-mapped memory), raises a flag per
+// (peer, query), waits for the peers' flags for the same query and merges -- one kernel, no collective call.
+// Slot layout (bytes): rows i64[nq*k] | scores f32[nq*k] | counts i32[nq], slot r of a gather area = rank r's results.
+// flags: [world][nq] u32 per rank, monotonically increasing epochs; two gather areas alternate by epoch parity (a rank
+// can be at most one step ahead of a peer, because finishing a step needs that peer's flag for it).
+struct XchgArgs {
+    int world, rank, nq, k;
+    unsigned char* bufs[8];        // peer-mapped base of every rank's buffer (bufs[rank] = own)
+    int64_t area_bytes;            // one gather area = world * slot_bytes
+    int64_t slot_bytes, scores_off, counts_off;
+    int64_t flags_off;             // flags start (after the two gather areas)
+    uint32_t epoch;
+    float* scores_out; int64_t* rows_out; int32_t* counts_out;
+};
+
+__global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const XchgArgs a) {
+    extern __shared__ __align__(16) unsigned char xm_smem[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int64_t area = int64_t(a.epoch & 1u) * a.area_bytes;
+    unsigned char* own_slot = a.bufs[a.rank] + area + int64_t(a.rank) * a.slot_bytes;
+    // 1. my results for query q -> every peer's gather area (slot = my rank)
+    const int64_t* my_rows = reinterpret_cast<const int64_t*>(own_slot) + size_t(q) * a.k;
+    const float* my_scores = reinterpret_cast<const float*>(own_slot + a.scores_off) + size_t(q) * a.k;
+    const int32_t my_count = *(reinterpret_cast<const int32_t*>(own_slot + a.counts_off) + q);
+    for (int p = 0; p < a.world; ++p) {
+        if (p == a.rank) continue;
+        unsigned char* dst = a.bufs[p] + area + int64_t(a.rank) * a.slot_bytes;
+        for (int i = tid; i < a.k; i += kMergeThreads) {
+            reinterpret_cast<int64_t*>(dst)[size_t(q) * a.k + i] = my_rows[i];
+            reinterpret_cast<float*>(dst + a.scores_off)[size_t(q) * a.k + i] = my_scores[i];
+        }
+        if (tid == 0) reinterpret_cast<int32_t*>(dst + a.counts_off)[q] = my_count;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. raise my flag for query q at every peer; 3. wait for every peer's flag for query q
+    if (tid < a.world && tid != a.rank) {
+        uint32_t* peer_flag = reinterpret_cast<uint32_t*>(a.bufs[tid] + a.flags_off) + size_t(a.rank) * a.nq + q;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(a.epoch) : "memory");
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.bufs[a.rank] + a.flags_off) + size_t(tid) * a.nq + q;
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (int32_t(v - a.epoch) >= 0) break;
+            if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a peer died
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    // 4. k-way merge of the world lists of query q (same order as xmerge_kernel)
+    const unsigned char* g = a.bufs[a.rank] + area;
+    const int total = a.world * a.k;
+    const int n2 = next_pow2(total < 2 ? 2 : total);
+    int64_t* sr = reinterpret_cast<int64_t*>(xm_smem);
+    uint32_t* sc = reinterpret_cast<uint32_t*>(xm_smem + size_t(n2) * 8);
+    int got = 0;
+    for (int l = 0; l < a.world; ++l) got += reinterpret_cast<const int32_t*>(g + int64_t(l) * a.slot_bytes + a.counts_off)[q];
+    got = got < a.k ? got : a.k;
+    for (int i = tid; i < n2; i += kMergeThreads) {
+        uint32_t c = 0; int64_t r = INT64_MAX;
+        if (i < total) {
+            const int l = i / a.k, j = i - l * a.k;
+            const unsigned char* slot = g + int64_t(l) * a.slot_bytes;
+            if (j < reinterpret_cast<const int32_t*>(slot + a.counts_off)[q]) {
+                const float s = reinterpret_cast<const float*>(slot + a.scores_off)[size_t(q) * a.k + j];
+                r = reinterpret_cast<const int64_t*>(slot)[size_t(q) * a.k + j];
+                c = (s == s) ? f2ord(s) : 1u;
+                if (c < 2u) c = (s == s) ? 2u : 1u;
+            }
+        }
+        sc[i] = c; sr[i] = r;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += kMergeThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint32_t ci = sc[i], cp = sc[p]; const int64_t ri = sr[i], rp = sr[p];
+                    const bool first_half = (i & kk) == 0;
+                    const bool swap = first_half ? xm_before(cp, rp, ci, ri) : xm_before(ci, ri, cp, rp);
+                    if (swap) { sc[i] = cp; sc[p] = ci; sr[i] = rp; sr[p] = ri; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < a.k; i += kMergeThreads) {
+        const size_t o = size_t(q) * a.k + i;
+        if (i < got) {
+            const uint32_t c = sc[i];
+            a.scores_out[o] = (c == 1u) ? CUDART_NAN_F : ord2f(c);
+            a.rows_out[o] = sr[i];
+        } else {
+            a.scores_out[o] = CUDART_NAN_F;
+            a.rows_out[o] = -1;
+        }
+    }
+    if (tid == 0) a.counts_out[q] = got;
+}
+
 }  // namespace mrag

@@ -50,7 +50,7 @@ class ShardedSearcher:
     must return (scores, rows, counts) of the global top-k."""
 
     def __init__(self, index=None, group=None, local_search: Callable | None = None, merge: Callable | None = None,
-                 device=None):
+                 device=None, exchange: str = "auto"):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -61,6 +61,11 @@ class ShardedSearcher:
         self._local = local_search or self._cuda_local
         self._merge = merge or self._cuda_merge
         self._buf_key = None
+        # "p2p": results travel by peer stores over NVLink inside the merge kernel (mrag_exchange_merge) -- no
+        # collective call; "nccl": all_gather_into_tensor + merge kernel; "auto": p2p when symmetric memory is there
+        self.exchange = exchange
+        self._p2p = None
+        self._epoch = 0
 
     # -- buffers -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -93,12 +98,67 @@ class ShardedSearcher:
         return merge_topk(self.index.device, scores0, rows0, counts0, world, nq, k,
                           (lay["size"] // 4, lay["size"] // 8, lay["size"] // 4))
 
+    # -- peer-to-peer exchange -------------------------------------------------------------------
+    def _p2p_state(self, nq: int, k: int):
+        """Symmetric (peer-mapped) buffer for this (nq, k): 2 gather areas + flags; None if unavailable."""
+        if self.exchange == "nccl" or self.world == 1 or self.world > 8 or self.index is None:
+            return None
+        key = (nq, k)
+        if self._p2p is not None and self._p2p["key"] == key:
+            return self._p2p
+        try:
+            import ctypes as C
+            import torch
+            import torch.distributed._symmetric_memory as symm_mem
+            lay = packed_layout(nq, k)
+            nbytes = 2 * self.world * lay["size"] + self.world * nq * 4
+            dev = torch.device(f"cuda:{self.index.device}")
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            gname = self.group.group_name if self.group is not None else self.dist.group.WORLD.group_name
+            hdl = symm_mem.rendezvous(buf, gname)
+            torch.cuda.synchronize(dev)
+            hdl.barrier()
+            ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._p2p = {"key": key, "lay": lay, "buf": buf, "hdl": hdl, "ptrs": ptrs}
+            self._epoch = 0
+        except Exception as exc:                    # no symmetric memory on this system: NCCL path
+            if self.exchange == "p2p":
+                raise
+            import logging
+            logging.getLogger(__name__).info("sharded search: symmetric memory unavailable (%s); using NCCL allgather", exc)
+            self.exchange = "nccl"
+            self._p2p = None
+        return self._p2p
+
+    def _search_p2p(self, st, q, k: int, flt):
+        import torch
+        from . import _native as N
+        nq = int(q.shape[0])
+        lay, buf = st["lay"], st["buf"]
+        self._epoch += 1
+        area = (self._epoch & 1) * self.world * lay["size"]
+        slot = buf[area + self.rank * lay["size"]: area + (self.rank + 1) * lay["size"]]
+        self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        out = (torch.empty((nq, k), dtype=torch.float32, device=buf.device),
+               torch.empty((nq, k), dtype=torch.int64, device=buf.device),
+               torch.empty((nq,), dtype=torch.int32, device=buf.device))
+        stream = torch.cuda.current_stream(buf.device).cuda_stream
+        N.check(N.load().mrag_exchange_merge(self.index.device, self.world, self.rank, nq, int(k), st["ptrs"],
+                                             lay["size"], lay["scores_off"], lay["counts_off"], self._epoch,
+                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stream))
+        return out
+
     # -- the search --------------------------------------------------------------------------
     def search(self, q, k: int, flt=None, events=None):
         """q: [nq, dim] float32 on this rank's device, identical on every rank.
         Returns (scores [nq,k], rows [nq,k] global ids, counts [nq]) on every rank.
         events: optional list of 4 torch.cuda.Event (timing enabled) recorded around the three phases."""
         nq = int(q.shape[0])
+        if self._local == self._cuda_local and self._merge == self._cuda_merge and not events:
+            st = self._p2p_state(nq, k)
+            if st is not None:
+                return self._search_p2p(st, q, k, flt)
         lay, slot, gathered = self._buffers(nq, k)
         if events:
             events[0].record()

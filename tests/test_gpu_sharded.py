@@ -61,7 +61,7 @@ def _free_port() -> int:
     return p
 
 
-def _nccl_worker(rank, world, port, n, dim, nq, k, outdir):
+def _nccl_worker(rank, world, port, n, dim, nq, k, outdir, exchange="nccl"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -76,10 +76,11 @@ def _nccl_worker(rank, world, port, n, dim, nq, k, outdir):
         idx = Index(dim, "bf16", rank, hi - lo)
         idx.append(X[lo:hi], meta[lo:hi])
         idx.set_row_base(lo)
-        ss = sharded.ShardedSearcher(index=idx)
+        ss = sharded.ShardedSearcher(index=idx, exchange=exchange)
         qd = torch.from_numpy(Q).cuda()
-        for _ in range(2):
+        for _ in range(5):                             # several epochs: both gather areas and the flags are reused
             s, r, c = ss.search(qd, k)
+        assert ss.exchange == exchange
         torch.cuda.synchronize()
         np.savez(os.path.join(outdir, f"out{rank}.npz"), s=s.cpu().numpy(), r=r.cpu().numpy(), c=c.cpu().numpy())
         idx.close()
@@ -98,4 +99,19 @@ def test_sharded_nccl_two_ranks(oracle, tmp_path):
     Q = synth.make_queries(X, nq, seed=193)
     outs = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
     assert (outs[0]["r"] == outs[1]["r"]).all() and (outs[0]["c"] == outs[1]["c"]).all()     # every rank gets the same answer
+    _check(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, outs[0]["s"], outs[0]["r"], outs[0]["c"], 1e-2)
+
+
+def test_sharded_p2p_exchange_two_ranks(oracle, tmp_path):
+    """The fused exchange + merge kernel (peer stores over NVLink, no collective call) gives what NCCL + K4 gives."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, dim, nq, k = 80000, 768, 7, 10
+    mp.spawn(_nccl_worker, args=(2, _free_port(), n, dim, nq, k, str(tmp_path), "p2p"), nprocs=2, join=True)
+    X, valid = synth.make_corpus(n, dim, seed=191, null_frac=1e-3)
+    Q = synth.make_queries(X, nq, seed=193)
+    outs = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
+    assert (outs[0]["r"] == outs[1]["r"]).all() and (outs[0]["c"] == outs[1]["c"]).all()
     _check(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, outs[0]["s"], outs[0]["r"], outs[0]["c"], 1e-2)
