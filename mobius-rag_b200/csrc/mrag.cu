@@ -674,7 +674,7 @@ static int64_t sample_min_tiles(int num_sms) {
 // set is wide (many blocks in flight sorting <= 2048 keys each, then one block per query)
 // (nblocks = queries served by this launch; the group lists are indexed by query id, so they are sized by m.nq)
 static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
-    if (int64_t(m.P) * m.kp > kMergeSlots / 2 && !m.gthr_out) {
+    if (int64_t(m.P) * m.kp > kMergeSlots && !m.gthr_out) {      // everything fits one block's shared memory otherwise
         MergeArgs m1 = m;
         m1.Pg = std::max(2, (kMergeSlots / 2) / m.kp);
         const int groups = int(ceil_div(m.P, m1.Pg));
@@ -798,7 +798,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         MmaArgs sa = a;
         sa.stats = nullptr;
         // 4 tiles per CTA (16 for large k, whose bound must sit higher to keep the buffers quiet), at most a quarter of the shard
-        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kc > 64 ? 16 : 4, tiles / (4 * int64_t(x->num_sms)))));
+        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kc > 64 ? 16 : 4, ceil_div(tiles, (kc > 64 ? 64 : 256) * int64_t(x->num_sms)))));
         sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
         const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
         sa.P = sgrid;
@@ -994,8 +994,9 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 MmaArgs sa = a;
                 sa.stats = nullptr;
                 sa.tstamps = ts_sample;
-                // 4 (k <= 64) or 8 tiles per CTA, at most a quarter of the shard
-                const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kr <= 64 ? 4 : 8, tiles / (4 * int64_t(x->num_sms)))));
+                // one sampled tile per 256 tiles a CTA will scan, up to 4 (k <= 64) or 8: the bound has to sit high enough
+                // that a CTA admits only a handful of rows per query, which scales with the rows a CTA sees
+                const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kr <= 64 ? 4 : 8, ceil_div(tiles, 256 * int64_t(x->num_sms)))));
                 sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
                 const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
                 sa.P = sgrid;

@@ -686,6 +686,26 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 }
                 for (int i = a.k; i < a.kp; ++i) out[i] = 0ull;
             }
+        } else if (a.k <= 16) {
+            // small k: every thread extracts the k best of ITS buffer by repeated maximum (k * n compares, all 32
+            // queries of the warp at once) instead of 32 warp-wide rank sorts one after the other
+            if (live) {
+                uint64_t* out = a.part + (size_t(qsrc) * a.P + blockIdx.x) * a.kp;
+                const int n = st.cnt;
+                const int have = n < a.k ? n : a.k;
+                for (int i = 0; i < a.kp; ++i) {
+                    uint64_t best = 0ull;
+                    if (i < have) {
+                        int bi = 0;
+                        for (int j = 0; j < n; ++j) {
+                            const uint64_t v = mybuf[j];
+                            if (v > best) { best = v; bi = j; }
+                        }
+                        mybuf[bi] = 0ull;
+                    }
+                    out[i] = best;
+                }
+            }
         } else {
             for (int L = 0; L < 32; ++L) {
                 const int qL = (quarter & 1) * 32 + L;
