@@ -716,3 +716,60 @@ def test_coalesced_concurrent_searches(oracle):
     s2 = idx.search(Q[:1], 5, Filter().doc_eq(7), options=N.OPT_COALESCE)
     assert s1[2][0] == 5 and s2[2][0] <= 5
     idx.close()
+
+
+def test_filter_mask_random_combinations():
+    """K2 is integer / bitset work: 150 random conjunctions of every clause kind must reproduce, bit for bit, the
+    same predicate evaluated with numpy on the codes."""
+    n, dim = 40000, 16
+    X, valid = synth.make_corpus(n, dim, seed=51, null_frac=5e-3)
+    meta, doc_tags, info = synth.make_metadata(n, seed=52, rows_per_doc=24, valid=valid)
+    idx = Index(dim, "f32", 0, n)
+    idx.append(X, meta)
+    idx.set_doc_tags(0, doc_tags)
+    v = valid.astype(bool)
+    doc = meta["doc_idx"]
+    n_docs = info["n_docs"]
+    tagmat = info["tagmat"]
+    rng = np.random.default_rng(53)
+    nP, nS, nPr, nA, nT = len(synth.PAYERS), len(synth.STATES), len(synth.PROGRAMS), len(synth.AUTHORITIES), len(synth.SOURCE_TYPES)
+    for case in range(150):
+        f = Filter()
+        want = v.copy()
+        kinds = rng.choice(8, size=int(rng.integers(1, 5)), replace=False)
+        for kind in kinds:
+            if kind == 0:
+                codes = rng.choice(nP, size=int(rng.integers(1, 4)), replace=False)
+                alt = rng.choice(nP, size=int(rng.integers(0, 3)), replace=False)
+                st = int(rng.integers(0, nS))
+                if len(alt):
+                    f.payer_in(codes, alt, st)
+                    want &= np.isin(meta["payer"], codes) | (np.isin(meta["payer"], alt) & (meta["state"] == st))
+                else:
+                    f.payer_in(codes)
+                    want &= np.isin(meta["payer"], codes)
+            elif kind == 1:
+                c = int(rng.integers(0, nS)); f.state_eq(c); want &= meta["state"] == c
+            elif kind == 2:
+                c = int(rng.integers(0, nPr)); f.program_eq(c); want &= meta["program"] == c
+            elif kind == 3:
+                c = int(rng.integers(0, nA)); f.authority_eq(c); want &= meta["authority"] == c
+            elif kind == 4:
+                c = int(rng.integers(0, nT)); f.source_type_eq(c); want &= meta["source_type"] == c
+            elif kind == 5:
+                pool = rng.choice(n_docs, size=int(rng.integers(0, 400)), replace=False)
+                f.doc_pool(pool); want &= np.isin(doc, pool)
+            elif kind == 6:
+                bits = rng.choice(64, size=int(rng.integers(1, 6)), replace=False)
+                f.tag_relaxed(bits); want &= tagmat[:, bits].any(axis=1)[doc]
+            else:
+                sc = rng.choice(nS, size=int(rng.integers(0, 3)), replace=False)
+                pc = rng.choice(nPr, size=int(rng.integers(0, 3)), replace=False)
+                yc = rng.choice(nP, size=int(rng.integers(0, 3)), replace=False)
+                f.tag_strict(sc, pc, yc)
+                want &= np.isin(meta["state"], sc) | np.isin(meta["program"], pc) | np.isin(meta["payer"], yc)
+        bits, n_pass = idx.filter_mask(f)
+        got = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (got == want).all(), (case, kinds)
+        assert n_pass == int(want.sum())
+    idx.close()
