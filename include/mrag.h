@@ -157,6 +157,14 @@ int mrag_dim(const mrag_index* idx);
 int mrag_index_dtype(const mrag_index* idx);
 int mrag_device(const mrag_index* idx);
 
+/* --- snapshot --------------------------------------------------------------------------
+ * One shard <-> one file: rows, 1/|x|, metadata columns, NULL / live bitmaps, document tag sets, hybrid features.
+ * The GPU copy is derived data (re-creatable from rag_published_embeddings); `user_version` carries
+ * corpus_state.corpus_version (publish.py:314) so a stale snapshot can be recognised. mrag_load creates the index
+ * on `device` with room for `capacity` rows (<= 0: exactly the rows in the file). */
+int mrag_save(mrag_index* idx, const char* path, int64_t user_version);
+int mrag_load(mrag_index** out, const char* path, int device, int64_t capacity, int64_t* user_version);
+
 /* --- read side ---------------------------------------------------------------------- */
 
 /* search options */

@@ -28,7 +28,7 @@ EXPORTS = [
     "mrag_search", "mrag_set_row_base", "mrag_merge_topk", "mrag_filter_mask", "mrag_last_kernel_ms",
     "mrag_profile_begin", "mrag_profile_read", "mrag_launch_count", "mrag_last_scan_kind",
     "mrag_last_error", "mrag_version",
-    "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge",
+    "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge", "mrag_save", "mrag_load",
 ]
 
 
@@ -152,6 +152,10 @@ def load(build_if_missing: bool = True):
     lib.mrag_search_hybrid.argtypes = [vp, vp, i32, i32, C.POINTER(FilterStruct), vp, vp, vp, vp, vp, vp]
     lib.mrag_dtag_mask.restype = i32
     lib.mrag_dtag_mask.argtypes = [vp, C.POINTER(FilterStruct), vp, i32, vp, vp]
+    lib.mrag_save.restype = i32
+    lib.mrag_save.argtypes = [vp, C.c_char_p, i64]
+    lib.mrag_load.restype = i32
+    lib.mrag_load.argtypes = [C.POINTER(vp), C.c_char_p, i32, i64, C.POINTER(i64)]
     lib.mrag_exchange_merge.restype = i32
     lib.mrag_exchange_merge.argtypes = [i32, i32, i32, i32, i32, vp, i64, i64, i64, u32, vp, vp, vp, vp]
     for name in ("mrag_last_scan_kind", "mrag_last_error", "mrag_version"):

@@ -1416,6 +1416,145 @@ extern "C" int mrag_dtag_mask(mrag_index* x, const mrag_filter* filter, const ui
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// snapshot: one shard <-> one file (the GPU-resident copy is re-creatable from the table and keyed
+// by corpus_state.corpus_version, publish.py:314; a snapshot makes the cold start one sequential read)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct SnapHeader {
+    char magic[8];            // "MRAGSNP1"
+    int32_t dim, ld, dtype, reserved;
+    int64_t size, n_docs, n_tag_docs, n_jtag_docs, has_feat, row_base, user_version;
+};
+
+struct SnapIO {
+    FILE* f = nullptr;
+    void* pinned = nullptr;
+    size_t chunk = size_t(64) << 20;
+    cudaStream_t s = nullptr;
+    ~SnapIO() { if (f) fclose(f); if (pinned) cudaFreeHost(pinned); }
+    int init(const char* path, const char* mode, cudaStream_t stream) {
+        f = fopen(path, mode);
+        if (!f) return fail(MRAG_ERR_ARG, "snapshot: cannot open %s", path);
+        if (cudaMallocHost(&pinned, chunk) != cudaSuccess) return fail(MRAG_ERR_OOM, "snapshot: pinned staging buffer");
+        s = stream;
+        return MRAG_OK;
+    }
+    int put(const void* dev, size_t bytes) {                 // device -> file
+        const char* p = static_cast<const char*>(dev);
+        for (size_t off = 0; off < bytes; off += chunk) {
+            const size_t m = std::min(chunk, bytes - off);
+            if (cudaMemcpyAsync(pinned, p + off, m, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+                return fail(MRAG_ERR_CUDA, "snapshot: D2H failed");
+            if (fwrite(pinned, 1, m, f) != m) return fail(MRAG_ERR_ARG, "snapshot: short write");
+        }
+        return MRAG_OK;
+    }
+    int get(void* dev, size_t bytes) {                       // file -> device
+        char* p = static_cast<char*>(dev);
+        for (size_t off = 0; off < bytes; off += chunk) {
+            const size_t m = std::min(chunk, bytes - off);
+            if (fread(pinned, 1, m, f) != m) return fail(MRAG_ERR_ARG, "snapshot: short read (truncated file?)");
+            if (cudaMemcpyAsync(p + off, pinned, m, cudaMemcpyHostToDevice, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+                return fail(MRAG_ERR_CUDA, "snapshot: H2D failed");
+        }
+        return MRAG_OK;
+    }
+};
+}  // namespace
+
+extern "C" int mrag_save(mrag_index* x, const char* path, int64_t user_version) {
+    if (!x || !path) return fail(MRAG_ERR_ARG, "mrag_save: null argument");
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_save: cudaSetDevice failed (no CPU path)");
+    SnapIO io;
+    int rc = io.init(path, "wb", x->wstream);
+    if (rc != MRAG_OK) return rc;
+    SnapHeader h{};
+    memcpy(h.magic, "MRAGSNP1", 8);
+    h.dim = x->dim; h.ld = x->ld; h.dtype = x->dtype; h.size = x->size; h.n_docs = x->n_docs; h.n_tag_docs = x->n_tag_docs;
+    h.n_jtag_docs = x->n_jtag_docs; h.has_feat = x->feat ? 1 : 0; h.row_base = x->row_base; h.user_version = user_version;
+    if (fwrite(&h, sizeof h, 1, io.f) != 1) return fail(MRAG_ERR_ARG, "mrag_save: short write");
+    const size_t n = size_t(x->size), words = (n + 31) / 32;
+    if ((rc = io.put(x->rows, n * x->ld * elem_size(x->dtype))) || (rc = io.put(x->inv_norm, n * 4)) ||
+        (rc = io.put(x->cols.doc_idx, n * 4)) || (rc = io.put(x->cols.payer, n * 2)) || (rc = io.put(x->cols.state, n)) ||
+        (rc = io.put(x->cols.program, n)) || (rc = io.put(x->cols.authority, n)) || (rc = io.put(x->cols.source_type, n)) ||
+        (rc = io.put(x->cols.valid, words * 4)) || (rc = io.put(x->cols.live, words * 4)))
+        return rc;
+    if (x->n_tag_docs && (rc = io.put(x->doc_tags, size_t(x->n_tag_docs) * MRAG_TAG_WORDS * 8))) return rc;
+    if (x->n_jtag_docs && (rc = io.put(x->doc_jtags, size_t(x->n_jtag_docs) * MRAG_JTAG_WORDS * 8))) return rc;
+    if (x->feat && (rc = io.put(x->feat, n * sizeof(mrag_chunkfeat)))) return rc;
+    return MRAG_OK;
+}
+
+__global__ void shadow_from_rows_kernel(const float* __restrict__ rows, __nv_bfloat16* __restrict__ shadow, size_t count) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) shadow[i] = __float2bfloat16_rn(rows[i]);
+}
+
+extern "C" int mrag_load(mrag_index** out, const char* path, int device, int64_t capacity, int64_t* user_version) {
+    if (!out || !path) return fail(MRAG_ERR_ARG, "mrag_load: null argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(MRAG_ERR_ARG, "mrag_load: cannot open %s", path);
+    SnapHeader h{};
+    const bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "MRAGSNP1", 8) == 0;
+    fclose(f);
+    if (!ok) return fail(MRAG_ERR_ARG, "mrag_load: %s is not an mrag snapshot", path);
+    if (capacity <= 0) capacity = std::max<int64_t>(h.size, 1);
+    if (capacity < h.size) return fail(MRAG_ERR_ARG, "mrag_load: capacity %lld < %lld rows in the snapshot", (long long)capacity, (long long)h.size);
+    mrag_index* x = nullptr;
+    int rc = mrag_create(&x, h.dim, h.dtype, device, capacity);
+    if (rc != MRAG_OK) return rc;
+    DeviceGuard g(device);
+    SnapIO io;
+    rc = io.init(path, "rb", x->wstream);
+    if (rc == MRAG_OK && fseek(io.f, long(sizeof h), SEEK_SET) != 0) rc = fail(MRAG_ERR_ARG, "mrag_load: seek failed");
+    const size_t n = size_t(h.size), words = (n + 31) / 32;
+    if (rc == MRAG_OK) {
+        (rc = io.get(x->rows, n * h.ld * elem_size(h.dtype))) || (rc = io.get(x->inv_norm, n * 4)) ||
+        (rc = io.get(x->cols.doc_idx, n * 4)) || (rc = io.get(x->cols.payer, n * 2)) || (rc = io.get(x->cols.state, n)) ||
+        (rc = io.get(x->cols.program, n)) || (rc = io.get(x->cols.authority, n)) || (rc = io.get(x->cols.source_type, n)) ||
+        (rc = io.get(x->cols.valid, words * 4)) || (rc = io.get(x->cols.live, words * 4));
+    }
+    if (rc == MRAG_OK && h.n_tag_docs) {
+        x->tag_docs_cap = h.n_tag_docs;
+        if (cudaMalloc(&x->doc_tags, size_t(h.n_tag_docs) * MRAG_TAG_WORDS * 8) != cudaSuccess) rc = fail(MRAG_ERR_OOM, "mrag_load: doc tags");
+        else rc = io.get(x->doc_tags, size_t(h.n_tag_docs) * MRAG_TAG_WORDS * 8);
+    }
+    if (rc == MRAG_OK && h.n_jtag_docs) {
+        x->jtag_docs_cap = h.n_jtag_docs;
+        if (cudaMalloc(&x->doc_jtags, size_t(h.n_jtag_docs) * MRAG_JTAG_WORDS * 8) != cudaSuccess) rc = fail(MRAG_ERR_OOM, "mrag_load: doc j-tags");
+        else rc = io.get(x->doc_jtags, size_t(h.n_jtag_docs) * MRAG_JTAG_WORDS * 8);
+    }
+    if (rc == MRAG_OK && h.has_feat) {
+        const int64_t cap32 = ceil_div(x->capacity, 32) * 32;
+        if (cudaMalloc(&x->feat, size_t(cap32) * sizeof(mrag_chunkfeat)) != cudaSuccess) rc = fail(MRAG_ERR_OOM, "mrag_load: features");
+        else {
+            cudaMemsetAsync(x->feat, 0, size_t(cap32) * sizeof(mrag_chunkfeat), x->wstream);
+            rc = io.get(x->feat, n * sizeof(mrag_chunkfeat));
+        }
+    }
+    if (rc == MRAG_OK && x->shadow && n) {                   // the bf16 shadow is derived data: rebuilt, not stored
+        const size_t count = n * size_t(h.ld);
+        shadow_from_rows_kernel<<<unsigned((count + 255) / 256), 256, 0, x->wstream>>>(static_cast<const float*>(x->rows), x->shadow, count);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaStreamSynchronize(x->wstream) != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_load: shadow rebuild failed");
+    }
+    if (rc != MRAG_OK) {
+        std::string keep = t_err;
+        mrag_destroy(x);
+        t_err = keep;
+        return rc;
+    }
+    x->size = h.size; x->n_docs = h.n_docs; x->n_tag_docs = h.n_tag_docs; x->n_jtag_docs = h.n_jtag_docs; x->row_base = h.row_base;
+    if (user_version) *user_version = h.user_version;
+    *out = x;
+    return MRAG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // K2 alone, K4
 // ------------------------------------------------------------------------------------------

@@ -142,6 +142,25 @@ class Index:
         N.check(self._lib.mrag_create(C.byref(self._h), int(dim), dt, int(device), int(capacity)))
         self.dim, self.dtype, self.device, self.capacity = int(dim), dt, int(device), int(capacity)
 
+    # -- snapshot --------------------------------------------------------------------------
+    def save(self, path: str, version: int = 0) -> None:
+        """Write this shard to one file (mrag_save); ``version`` = corpus_state.corpus_version."""
+        N.check(self._lib.mrag_save(self._h, str(path).encode(), int(version)))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, capacity: int = 0) -> tuple["Index", int]:
+        """(Index, version) from a snapshot file (mrag_load)."""
+        self = cls.__new__(cls)
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        ver = C.c_int64(0)
+        N.check(self._lib.mrag_load(C.byref(self._h), str(path).encode(), int(device), int(capacity), C.byref(ver)))
+        self.dim = int(self._lib.mrag_dim(self._h))
+        self.dtype = int(self._lib.mrag_index_dtype(self._h))
+        self.device = int(device)
+        self.capacity = int(self._lib.mrag_capacity(self._h))
+        return self, int(ver.value)
+
     # -- lifecycle -------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:

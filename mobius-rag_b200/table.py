@@ -136,6 +136,42 @@ class PublishedTable:
             self.doc_p_tags.pop(str(document_id), None)
             return n
 
+    # -- snapshot ------------------------------------------------------------------------------
+    _HOST_STATE = ("id", "document_id", "source_type", "source_id", "document_payer", "document_state", "document_program",
+                   "document_authority_level", "extra", "doc_idx", "_next_doc", "doc_d_tags", "doc_p_tags")
+
+    def save(self, dirpath: str, corpus_version: int = 0) -> None:
+        """Snapshot = the device shard (``index.mrag``) + the host half of the table (``table.pkl``): ids, hydration
+        columns, vocabularies, document maps.  Keyed by corpus_state.corpus_version (publish.py:314)."""
+        import os
+        import pickle
+        os.makedirs(dirpath, exist_ok=True)
+        with self.lock:
+            self.index.save(os.path.join(dirpath, "index.mrag"), corpus_version)
+            state = {k: getattr(self, k) for k in self._HOST_STATE}
+            state["vocab"] = self.vocab
+            state["corpus_version"] = int(corpus_version)
+            with open(os.path.join(dirpath, "table.pkl"), "wb") as f:
+                pickle.dump(state, f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    @classmethod
+    def load(cls, dirpath: str, device: int = 0, capacity: int = 0) -> tuple["PublishedTable", int]:
+        """(table, corpus_version) from a snapshot directory; the cold start is one sequential read."""
+        import os
+        import pickle
+        with open(os.path.join(dirpath, "table.pkl"), "rb") as f:
+            state = pickle.load(f)
+        self = cls.__new__(cls)
+        self.index, ver = Index.load(os.path.join(dirpath, "index.mrag"), device, capacity)
+        if ver != state["corpus_version"] or len(self.index) != len(state["id"]):
+            self.index.close()
+            raise ValueError("snapshot is inconsistent: index.mrag and table.pkl come from different versions")
+        self.lock = threading.RLock()
+        self.vocab = state["vocab"]
+        for k in cls._HOST_STATE:
+            setattr(self, k, state[k])
+        return self, ver
+
     # -- WHERE builders ------------------------------------------------------------------------
     def filter_pg_store(self, document_id: str | None, filters: dict | None) -> Filter | None:
         """WHERE of PgVectorStore._search_async (vector_store.py:245-267)."""

@@ -773,3 +773,30 @@ def test_filter_mask_random_combinations():
         assert (got == want).all(), (case, kinds)
         assert n_pass == int(want.sum())
     idx.close()
+
+
+def test_snapshot_round_trip(oracle, tmp_path):
+    """save -> load gives a table that answers every kind of call byte for byte (rows, NULL / deleted rows,
+    filters, document tags, fp32 shadow rebuilt on load)."""
+    from helpers import build_tables
+    ot, pt, X, valid, meta, info = build_tables(oracle, 5000, 96, seed=17, dtype="f32")
+    pt.delete_document(ot.document_id[100])
+    pt.save(str(tmp_path / "snap"), corpus_version=42)
+    pt2, ver = mrag_b200.PublishedTable.load(str(tmp_path / "snap"), device=0, capacity=6000)
+    assert ver == 42 and len(pt2) == len(pt)
+    rng = np.random.default_rng(5)
+    Q = synth.make_queries(X, 9, seed=18)
+    for flt in (None, Filter().state_eq(0), Filter().tag_relaxed([0, 3])):
+        a = pt.index.search(Q, 20, flt)
+        b = pt2.index.search(Q, 20, flt)
+        assert all((x == y).all() or (np.isnan(x) == np.isnan(y)).all() for x, y in zip(a, b))
+        assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    emb = X[int(rng.integers(0, len(X)))].tolist()
+    assert mrag_b200.vector_arm(pt, emb, 10, None, None) == mrag_b200.vector_arm(pt2, emb, 10, None, None)
+    # the loaded table keeps working as a table: insert + search
+    pt2.insert([{"id": "new-1", "document_id": "doc-new", "source_type": "fact", "source_id": "s"}], [X[3].tolist()])
+    hit = mrag_b200.B200VectorStore(table=pt2).search(X[3].tolist(), 3)
+    assert any(h["id"] == "new-1" for h in hit)
+    with pytest.raises(N.MragError):
+        Index.load(str(tmp_path / "snap" / "table.pkl"))          # not a snapshot file
+    pt.index.close(); pt2.index.close()
