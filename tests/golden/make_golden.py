@@ -270,6 +270,26 @@ def make_rerank_golden(oracle, ref_cs):
     arms = {"bm25": bm_arm, "vector": vec_arm, "dtag": dtag_out[1]["result"]}
     fused = ref_cs._rrf_merge({a: [dict(c) for c in lst] for a, lst in arms.items()})
     dump_json({"dtag": dtag_out, "rrf": {"arms": arms, "fused": fused}}, "dtag_rrf.json")
+    # ---- the text rules the product's shim restates (hybrid.py), evaluated by the reference's own helpers
+    helper_rows = []
+    for i in list(range(0, len(rows), 9))[:100]:
+        c = ref_cs._row_to_base_dict(rows[i])
+        d = doc_by_id[rows[i]["document_id"]]
+        if d["has_tags_row"]:
+            c["_doc_d_tags"] = list(d["d_tags"]); c["_doc_j_tags"] = list(d["j_tags"]); c["_doc_p_tags"] = list(d["p_tags"])
+        body = ref_cs._body_haystack(c)
+        helper_rows.append({
+            "row": i, "body_haystack": body, "meta_haystack": ref_cs._meta_haystack(c),
+            "classify_jpd": ref_cs._classify_jpd(body), "length_score": ref_cs._length_score(c.get("text") or ""),
+            "authority_score": ref_cs._authority_score(c.get("authority_level")),
+            "contact_value": bool(ref_cs._CONTACT_VALUE_RE.search(c.get("text") or "")),
+        })
+    queries = ["sunshine health provider services phone number", "what is the appeal process", "EDI payer-id for claims",
+               "toll free hotline", "prior authorization criteria for inpatient level of care", ""]
+    helper_q = [{"query": q, "classify_jpd": ref_cs._classify_jpd(q) if q else {}, "contact_query": bool(ref_cs._CONTACT_QUERY_RE.search(q)) if q else False}
+                for q in queries]
+    dump_json({"rows": helper_rows, "queries": helper_q, "confidence": {str(x): ref_cs._confidence_label(x) for x in (0.0, 0.17, 0.18, 0.34, 0.35, 0.54, 0.55, 0.9)}},
+              "text_rules.json")
     print("dtag results:", [len(c["result"]) for c in dtag_out], "rrf fused:", len(fused))
     np.savez_compressed(os.path.join(HERE, "hybrid_vectors.npz"), X=X)
     dump_json({"docs": docs, "rows": rows, "promoted": promoted, "phrase_pool": PHRASE_POOL}, "hybrid_table.json")
