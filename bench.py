@@ -55,7 +55,9 @@ def parse_args():
                     help="document-tag filter passing every M-th document (0 = no filter); C2 uses 10")
     ap.add_argument("--payer-filter", type=int, default=0, metavar="M",
                     help="payor bitset filter passing the documents of 1 payer out of M (0 = none); C4 uses 13")
-    ap.add_argument("--workload", default="", choices=["", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--doc-pool", type=int, default=0, metavar="D",
+                    help="document_id = ANY(pool) filter with D random documents (64 rows each); the pinned-pool case of corpus_search.py:414-420")
+    ap.add_argument("--workload", default="", choices=["", "c2", "c3", "c4", "c5", "pool"],
                     help="shortcut: c2 = 1Mx768 fp32, batch 256, top-10, tag filter 10%%; c3 = 10Mx768 bf16 top-100; "
                          "c5 = hybrid rerank over 10M chunks, 22-query bank, top-50")
     return ap.parse_args()
@@ -233,7 +235,8 @@ def workload_config(args, batch):
     return {
         "workload": f"{args.rows}x{args.dim} {args.dtype} corpus, top-{args.k}, query batch {batch}, row-sharded",
         "rows": args.rows, "dim": args.dim, "corpus_dtype": args.dtype, "accumulate": "f32", "k": args.k, "batch": batch,
-        "filter": (f"payor bitset passing 1/{args.payer_filter} of the documents" if args.payer_filter else
+        "filter": (f"document_id = ANY(pool of {args.doc_pool} documents)" if args.doc_pool else
+                   f"payor bitset passing 1/{args.payer_filter} of the documents" if args.payer_filter else
                    "embedding_vec IS NOT NULL only" if not args.tag_filter else
                    f"document tag filter (relaxed, 1 tag) passing 1/{args.tag_filter} of the documents"), "l2": "inputs larger than L2 (no flush needed)",
         "parallelism": f"rowshard{args.gpus}",
@@ -346,6 +349,11 @@ def main():
     elif args.workload == "c4":
         # one GPU's share of 50M x 1536 bf16 sharded over 8 (6.25M rows, 19.2 GB), per-payor bitset, top-10, single queries
         args.rows, args.dim, args.dtype, args.k, args.batch, args.payer_filter, args.sweep = 6_250_000, 1536, "bf16", 10, 1, 13, "4"
+    elif args.workload == "pool":
+        # the case the reference works around (exact cosine sort over a pinned pool: 130 ms warm .. 14 s cold on Cloud SQL,
+        # corpus_search.py:414-420): production-shaped corpus, one query, a 50-document pool
+        args.rows, args.dim, args.dtype, args.k, args.batch, args.sweep = 1_900_000, 1536, "f32", 10, 1, ""
+        args.doc_pool = args.doc_pool or 50
     elif args.workload == "c5":
         args.rows, args.dim, args.dtype, args.k, args.batch, args.sweep = 10_000_000, 768, "bf16", 50, 22, ""
     if args.impl == "reference":
@@ -401,6 +409,11 @@ def main():
         idx.set_doc_tags(0, bits)
         flt = mi.Filter().tag_relaxed([0])
         pass_frac = float(np.ceil(n_docs / args.tag_filter) / n_docs)
+    if args.doc_pool:
+        n_docs_all = (args.rows + 63) // 64
+        pool = np.random.default_rng(5).choice(n_docs_all, size=min(args.doc_pool, n_docs_all), replace=False).astype(np.uint32)
+        flt = (flt or mi.Filter()).doc_pool(pool)
+        pass_frac *= len(pool) / n_docs_all
     if args.payer_filter:
         flt = (flt or mi.Filter()).payer_in([3 % args.payer_filter])
         pass_frac *= 1.0 / args.payer_filter

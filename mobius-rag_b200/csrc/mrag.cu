@@ -946,7 +946,9 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     // fp32 shards that cannot (dim > 768) or should not (few queries) take the tensor-core candidate scan still
     // halve their traffic by nominating from the bf16 shadow on the CUDA cores
     const bool use_shadow_gemv = !use_mma128 && !use_mma && x->dtype == MRAG_F32 && x->shadow && n > 0 && k <= kMma128MaxK &&
-                                 !(options & (MRAG_OPT_FORCE_GEMV | MRAG_OPT_FORCE_MMA | MRAG_OPT_FORCE_MMA128)) && shadow_gemv_wanted(n, ld);
+                                 !(options & (MRAG_OPT_FORCE_GEMV | MRAG_OPT_FORCE_MMA | MRAG_OPT_FORCE_MMA128)) && shadow_gemv_wanted(n, ld) &&
+                                 // a document pool / single document is selective: the exact scan touches few rows and needs fewer launches
+                                 !(filter && (filter->flags & (MRAG_F_DOC_EQ | MRAG_F_DOC_POOL)));
     if (use_mma128 || use_shadow_gemv) {
         int rc = search_approx_rescore(x, w, ev, nq, k, mask, d_scores, d_rows, d_counts, s, use_shadow_gemv);
         if (rc != MRAG_OK) return rc;
