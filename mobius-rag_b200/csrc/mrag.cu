@@ -1020,6 +1020,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p;
             a.ub = (r > 0) ? w->ub.p : nullptr;
             a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid;
+            a.unit_log2 = (filter && (filter->flags & (MRAG_F_DOC_EQ | MRAG_F_DOC_POOL))) ? 2 : 0;
             int rc = run_scan_gemv(x, a, nq, grid, s);
             if (rc != MRAG_OK) return rc;
             t_last_kind = "gemv";
