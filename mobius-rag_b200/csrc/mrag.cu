@@ -16,6 +16,7 @@
 #include "scan_gemv.cuh"
 #include "scan_mma.cuh"
 #include "scan_mma128.cuh"
+#include "scan_mma256.cuh"
 #include "select.cuh"
 #include "rescore.cuh"
 
@@ -149,6 +150,7 @@ struct mrag_index {
     uint64_t* doc_jtags = nullptr;      // [jtag_docs_cap][MRAG_JTAG_WORDS]
     int64_t n_jtag_docs = 0, jtag_docs_cap = 0;
     CUtensorMap tmap;                   // bf16 rows (or the shadow) as a 2-D tensor, 64x64 boxes, SWIZZLE_128B
+    CUtensorMap tmap32;                 // the same tensor with 64x32 boxes (half tiles of the CTA-pair scan)
     bool has_tmap = false;
     cudaStream_t wstream = nullptr;     // write-side stream
     std::shared_mutex lock;             // searches share, writers exclude
@@ -197,7 +199,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_corpus_tmap(mrag_index* x, void* base, int64_t alloc_rows) {
+static int make_corpus_tmap(mrag_index* x, CUtensorMap* out, void* base, int64_t alloc_rows, int box_rows) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -205,10 +207,10 @@ static int make_corpus_tmap(mrag_index* x, void* base, int64_t alloc_rows) {
         return fail(MRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t gdim[2] = {cuuint64_t(x->ld), cuuint64_t(alloc_rows)};
     cuuint64_t gstride[1] = {cuuint64_t(x->ld) * 2};
-    cuuint32_t box[2] = {cuuint32_t(kMmaKBlock), cuuint32_t(kMmaTileRows)};
+    cuuint32_t box[2] = {cuuint32_t(kMmaKBlock), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<PFN_tmapEncodeTiled>(fn)(
-        &x->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
     x->has_tmap = true;
@@ -280,7 +282,9 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     }
     if ((dtype == MRAG_BF16 || x->shadow) && x->ld <= kMmaMaxLd) {
         // rows past `capacity` inside the allocation are never selected (mask bits are zero)
-        if (make_corpus_tmap(x, dtype == MRAG_BF16 ? x->rows : static_cast<void*>(x->shadow), cap32 + 64) != MRAG_OK) {
+        void* tbase = dtype == MRAG_BF16 ? x->rows : static_cast<void*>(x->shadow);
+        if (make_corpus_tmap(x, &x->tmap, tbase, cap32 + 64, kMmaTileRows) != MRAG_OK ||
+            make_corpus_tmap(x, &x->tmap32, tbase, cap32 + 64, kMma256HalfRows) != MRAG_OK) {
             std::string keep = t_err;
             mrag_destroy(x);
             t_err = keep;
@@ -733,6 +737,33 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
     return MRAG_OK;
 }
 
+// the CTA-pair scan: 256 queries per pass (two CTAs of a cluster share every corpus tile)
+static int launch_scan_mma256(mrag_index* x, MmaArgs a, int nq, int npairs, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        CU(cudaFuncSetAttribute(scan_mma256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set[dev] = true;
+    }
+    const int smem_cap = a.gcand ? 0 : a.cap;
+    const int kblocks = a.ld / kMmaKBlock;
+    a.kbs = kblocks % 4 == 0 ? 4 : kblocks % 3 == 0 ? 3 : kblocks % 2 == 0 ? 2 : 1;     // k-blocks per stage
+    const size_t fixed = mma256_smem_bytes(0, smem_cap);
+    const size_t stage = size_t(a.kbs) * kMma256StageBytes;
+    if (fixed + 3 * stage > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma256: candidate buffers do not fit");
+    a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / stage));
+    const size_t smem = mma256_smem_bytes(a.stages, smem_cap, a.kbs);
+    a.P = npairs;
+    for (int q0 = 0; q0 < nq; q0 += 2 * kMma128Queries) {
+        a.q0 = q0;
+        a.nq = std::min(2 * kMma128Queries, nq - q0);
+        scan_mma256_kernel<<<2 * npairs, kMmaThreads, smem, s>>>(x->tmap32, a);
+        LAUNCHED();
+    }
+    return MRAG_OK;
+}
+
 // Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or
 // the bf16 shadow), exact rescoring of the K' = k + 32 nominees from the primary rows, certificate,
 // exact CUDA-core rescan of the queries that fail it.  Results are EXACT (same arithmetic as scan_gemv).
@@ -762,6 +793,8 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
     CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
     int rc;
+    bool use_pairs = false;
+    int npairs = 0;
     if (gen_gemv) {
         ScanArgs ga{};
         ga.rows = x->shadow; ga.n = n; ga.ld = ld; ga.mask = mask; ga.q = w->qpad.p; ga.qinv = w->qinv.p; ga.ub = nullptr;
@@ -812,13 +845,23 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
         LAUNCHED();
     }
-    rc = launch_scan_mma128<0>(x, a, nq, grid, s);
+    // more than 128 queries: CTA pairs share every corpus tile (256 queries per pass)
+    static const bool pairs_ok = [] { const char* e = getenv("MRAG_MMA256"); return !(e && e[0] == '0'); }();
+    use_pairs = pairs_ok && nq > kMma128Queries && x->num_sms >= 2;
+    if (use_pairs) {
+        npairs = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms / 2, tiles)));
+        if (global_cand && w->gcand.reserve(size_t(2 * npairs) * kMma128Queries * cap)) return MRAG_ERR_OOM;
+        if (global_cand) a.gcand = w->gcand.p;
+        rc = launch_scan_mma256(x, a, nq, npairs, s);
+    } else {
+        rc = launch_scan_mma128<0>(x, a, nq, grid, s);
+    }
     if (rc != MRAG_OK) return rc;
     }
     CU(cudaEventRecord(ev.e[2], s));
     // nominees per query, by approximate score
     MergeArgs m{};
-    m.part = w->part.p; m.P = gen_gemv ? ggrid : grid; m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
+    m.part = w->part.p; m.P = gen_gemv ? ggrid : (use_pairs ? npairs : grid); m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
     m.scores = w->cscores.p; m.rows = w->crows.p; m.counts = w->ccounts.p; m.row_base = 0;
     rc = launch_merge(w, m, nq, s);
     if (rc != MRAG_OK) return rc;

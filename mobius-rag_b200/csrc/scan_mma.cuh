@@ -71,6 +71,7 @@ struct MmaArgs {
     // *qcount == 0 makes the launch a no-op
     const int* qlist;
     const int* qcount;
+    int kbs;                 // scan_mma256: k-blocks per pipeline stage (divides ld / 64)
     uint64_t* gcand;         // scan_mma128, large k: candidate buffers in GLOBAL memory [gridDim][128][cap] (appends are
                              // rare once a bound exists; the buffers of one CTA stay in its L1 / L2); nullptr = shared memory
     uint32_t sleep_ns;       // suspend-time hint of the barrier waits
