@@ -738,30 +738,38 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
 }
 
 // the CTA-pair scan: 256 queries per pass (two CTAs of a cluster share every corpus tile)
-static int launch_scan_mma256(mrag_index* x, MmaArgs a, int nq, int npairs, cudaStream_t s) {
+template <int KBS>
+static int launch_scan_mma256_t(mrag_index* x, MmaArgs a, int nq, int npairs, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute(scan_mma256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(scan_mma256_kernel<KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
     const int smem_cap = a.gcand ? 0 : a.cap;
-    const int kblocks = a.ld / kMmaKBlock;
-    a.kbs = kblocks % 4 == 0 ? 4 : kblocks % 3 == 0 ? 3 : kblocks % 2 == 0 ? 2 : 1;     // k-blocks per stage
+    a.kbs = KBS;
     const size_t fixed = mma256_smem_bytes(0, smem_cap);
-    const size_t stage = size_t(a.kbs) * kMma256StageBytes;
+    const size_t stage = size_t(KBS) * kMma256StageBytes;
     if (fixed + 3 * stage > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma256: candidate buffers do not fit");
     a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / stage));
-    const size_t smem = mma256_smem_bytes(a.stages, smem_cap, a.kbs);
+    const size_t smem = mma256_smem_bytes(a.stages, smem_cap, KBS);
     a.P = npairs;
     for (int q0 = 0; q0 < nq; q0 += 2 * kMma128Queries) {
         a.q0 = q0;
         a.nq = std::min(2 * kMma128Queries, nq - q0);
-        scan_mma256_kernel<<<2 * npairs, kMmaThreads, smem, s>>>(x->tmap32, a);
+        scan_mma256_kernel<KBS><<<2 * npairs, kMmaThreads, smem, s>>>(x->tmap32, a);
         LAUNCHED();
     }
     return MRAG_OK;
+}
+
+static int launch_scan_mma256(mrag_index* x, const MmaArgs& a, int nq, int npairs, cudaStream_t s) {
+    const int kblocks = a.ld / kMmaKBlock;              // k-blocks per stage: the largest of 4, 3, 2, 1 that divides them
+    return kblocks % 4 == 0 ? launch_scan_mma256_t<4>(x, a, nq, npairs, s)
+         : kblocks % 3 == 0 ? launch_scan_mma256_t<3>(x, a, nq, npairs, s)
+         : kblocks % 2 == 0 ? launch_scan_mma256_t<2>(x, a, nq, npairs, s)
+                            : launch_scan_mma256_t<1>(x, a, nq, npairs, s);
 }
 
 // Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or

@@ -79,12 +79,16 @@ MRAG_DEVINL void umma_commit_2cta(uint64_t* bar) {     // arrives on `bar` in BO
 
 // MmaArgs as scan_mma128 (KREG = 0 only): a.q0 = first query of the PAIR (CTA rank r serves [q0 + 128 r, +128)),
 // a.nq <= 256, a.P = number of pairs; tmap32 = the corpus tensor map with 64 x 32 boxes.
+// KBS = k-blocks per pipeline stage (compile time, so that the 4 * KBS MMAs of a stage are issued from ONE descriptor
+// base with immediate offsets: the issue thread is the critical path -- ncu r1o: ~80 cycles per MMA with run-time
+// descriptor arithmetic, against 32 cycles of tensor work)
+template <int KBS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
 scan_mma256_kernel(const __grid_constant__ CUtensorMap tmap32, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                                     // stages * 4 KB
-    const int kbs = a.kbs;
+    constexpr int kbs = KBS;
     const int stage_bytes = kbs * kMma256StageBytes;
     float* xinv = reinterpret_cast<float*>(smem + size_t(a.stages) * stage_bytes);       // [8][64] 1/|x| of a tile's rows
     uint64_t* smem_cand = reinterpret_cast<uint64_t*>(xinv + kMma128InvSlots * 64);
@@ -208,13 +212,15 @@ scan_mma256_kernel(const __grid_constant__ CUtensorMap tmap32, const MmaArgs a) 
                     for (int kb = 0; kb < kblocks; kb += kbs) {
                         mbar_wait(&full_bar[s], ph, slp);
                         tc_fence_after();
-                        for (int j = 0; j < kbs; ++j) {
-                            const uint64_t bdesc = bdesc0 + uint64_t((size_t(s) * stage_bytes + size_t(j) * kMma256StageBytes) >> 4);
-                            const uint32_t a_tmem = tmem_base + uint32_t((kb + j) * (kMmaKBlock / 2));
-                            umma_ts_bf16_2cta(d_tmem, a_tmem, bdesc, kMma256Idesc, (kb + j) != 0 ? 1u : 0u);
-                            umma_ts_bf16_2cta(d_tmem, a_tmem + 8, bdesc + 2, kMma256Idesc, 1u);
-                            umma_ts_bf16_2cta(d_tmem, a_tmem + 16, bdesc + 4, kMma256Idesc, 1u);
-                            umma_ts_bf16_2cta(d_tmem, a_tmem + 24, bdesc + 6, kMma256Idesc, 1u);
+                        const uint64_t sdesc = bdesc0 + uint64_t((size_t(s) * stage_bytes) >> 4);
+                        const uint32_t abase = tmem_base + uint32_t(kb * (kMmaKBlock / 2));
+                        umma_ts_bf16_2cta(d_tmem, abase, sdesc, kMma256Idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int ji = 1; ji < 4 * KBS; ++ji) {
+                            constexpr int kStageDesc = kMma256StageBytes >> 4;
+                            const int j = ji >> 2, i = ji & 3;
+                            umma_ts_bf16_2cta(d_tmem, abase + uint32_t(j * (kMmaKBlock / 2) + i * 8),
+                                              sdesc + uint64_t(j * kStageDesc + i * 2), kMma256Idesc, 1u);
                         }
                         umma_commit_2cta(&empty_bar[s]);
                         if (kb + kbs >= kblocks) umma_commit_2cta(&tfull_bar[as]);
