@@ -724,10 +724,15 @@ static int launch_scan_mma128(mrag_index* x, MmaArgs a, int nq, int grid, cudaSt
     }
     if (KREG > 0) { a.cap = 0; a.gcand = nullptr; }
     const int smem_cap = a.gcand ? 0 : a.cap;           // candidate buffers in global memory take no shared memory
+    const int kblocks = a.ld / kMmaKBlock;
+    a.kbs = kblocks % 4 == 0 ? 4 : kblocks % 3 == 0 ? 3 : kblocks % 2 == 0 ? 2 : 1;     // k-blocks per stage
     const size_t fixed = mma128_smem_bytes(0, smem_cap);
-    if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma128: candidate buffers do not fit");
-    a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
-    const size_t smem = mma128_smem_bytes(a.stages, smem_cap);
+    const size_t stage = size_t(a.kbs) * kMmaStageBytes;
+    if (fixed + 2 * stage > size_t(kMaxSmem)) { a.kbs = 1; }
+    const size_t stage1 = size_t(a.kbs) * kMmaStageBytes;
+    if (fixed + 2 * stage1 > size_t(kMaxSmem)) return fail(MRAG_ERR_ARG, "scan_mma128: candidate buffers do not fit");
+    a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / stage1));
+    const size_t smem = mma128_smem_bytes(a.stages, smem_cap, a.kbs);
     for (int q0 = 0; q0 < nq; q0 += kMma128Queries) {
         a.q0 = q0;
         a.nq = std::min(kMma128Queries, nq - q0);

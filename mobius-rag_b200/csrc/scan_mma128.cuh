@@ -25,8 +25,10 @@ constexpr int kMma128Queries = 128;
 constexpr int kMma128InvSlots = 8;
 constexpr int kMma128Slack = 32;          // candidate buffer = K' + slack keys per query
 
-inline size_t mma128_smem_bytes(int stages, int cap) {
-    return 1024 /*align slack*/ + size_t(stages) * kMmaStageBytes + size_t(kMma128InvSlots) * 64 * 4 +
+// a pipeline stage = kbs k-blocks (kbs * 8 KB): one full / empty barrier pair, one wait and one commit per stage
+// (the MMA issue thread paces this kernel; fewer waits and commits per tile shorten its loop)
+inline size_t mma128_smem_bytes(int stages, int cap, int kbs = 1) {
+    return 1024 /*align slack*/ + size_t(stages) * kbs * kMmaStageBytes + size_t(kMma128InvSlots) * 64 * 4 +
            size_t(kMma128Queries) * cap * 8 + 1024 /*barriers*/;
 }
 
@@ -112,7 +114,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                                    // stages * 8 KB
-    float* xinv = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [4][64] 1/|x| of a tile's rows
+    const int kbs = a.kbs;
+    const int stage_bytes = kbs * kMmaStageBytes;
+    float* xinv = reinterpret_cast<float*>(smem + size_t(a.stages) * stage_bytes);      // [8][64] 1/|x| of a tile's rows
     uint64_t* smem_cand = reinterpret_cast<uint64_t*>(xinv + kMma128InvSlots * 64);      // [128 queries][cap] unless a.gcand
     uint64_t* cand = a.gcand ? a.gcand + size_t(blockIdx.x) * kMma128Queries * a.cap : smem_cand;
     uint64_t* bars = smem_cand + (a.gcand ? size_t(0) : size_t(kMma128Queries) * a.cap);
@@ -196,12 +200,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
                 }
                 __syncwarp();
                 if (++is == kMma128InvSlots) { is = 0; iph ^= 1u; }
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = 0; kb < kblocks; kb += kbs) {
                     mbar_wait(&empty_bar[s], ph ^ 1u, slp);
                     if (elect_one()) {
-                        mbar_expect_tx(&full_bar[s], kMmaStageBytes);
-                        tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
-                                    &full_bar[s]);
+                        mbar_expect_tx(&full_bar[s], uint32_t(stage_bytes));
+                        for (int j = 0; j < kbs; ++j)
+                            tma_load_2d(stage_base + size_t(s) * stage_bytes + size_t(j) * kMmaStageBytes, &tmap,
+                                        (kb + j) * kMmaKBlock, int(t * kMmaTileRows), &full_bar[s]);
                     }
                     __syncwarp();
                     if (++s == a.stages) { s = 0; ph ^= 1u; }
@@ -225,17 +230,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma128_kernel(const __gri
                     mbar_wait(&tempty_bar[as], aph ^ 1u, slp);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + uint32_t(kMmaDCol0 + as * kMmaTileRows);
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int kb = 0; kb < kblocks; kb += kbs) {
                         mbar_wait(&full_bar[s], ph, slp);
                         tc_fence_after();
-                        const uint64_t bdesc = bdesc0 + uint64_t(s) * (kMmaStageBytes >> 4);
-                        const uint32_t a_tmem = tmem_base + uint32_t(kb * (kMmaKBlock / 2));
-                        umma_ts_bf16(d_tmem, a_tmem, bdesc, idesc, kb != 0 ? 1u : 0u);
-                        umma_ts_bf16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
-                        umma_ts_bf16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
-                        umma_ts_bf16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
+                        for (int j = 0; j < kbs; ++j) {
+                            const uint64_t bdesc = bdesc0 + uint64_t((size_t(s) * stage_bytes + size_t(j) * kMmaStageBytes) >> 4);
+                            const uint32_t a_tmem = tmem_base + uint32_t((kb + j) * (kMmaKBlock / 2));
+                            umma_ts_bf16(d_tmem, a_tmem, bdesc, idesc, (kb + j) != 0 ? 1u : 0u);
+                            umma_ts_bf16(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
+                            umma_ts_bf16(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
+                            umma_ts_bf16(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
+                        }
                         umma_commit(&empty_bar[s]);
-                        if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+                        if (kb + kbs >= kblocks) umma_commit(&tfull_bar[as]);
                         if (++s == a.stages) { s = 0; ph ^= 1u; }
                     }
                     if (++as == 2) { as = 0; aph ^= 1u; }
