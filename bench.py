@@ -76,6 +76,19 @@ def load_traffic(kernel: str, args, n_local: int, q_per_launch: int):
     return float(e["dram_bytes"]) if e else None
 
 
+def load_tensor_peak():
+    """Dense bf16 TFLOP/s a kernel inside a long step can sustain (cuBLAS, back to back): MEASURED_PEAKS.json, else the
+    profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured sustained (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1400.0, "fallback sustained (B200_PROFILING.md)"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -486,6 +499,8 @@ def main():
     def roofline_of(m, batch):
         kind = idx.last_scan_kind()
         group = {"gemv": 4, "gemv_shadow": 4, "mma": 64, "mma128": 128}[kind]      # queries per scan launch
+        if kind == "mma128" and batch > 128:
+            group = 256                                                             # CTA pairs: 256 queries per pass
         scan_launches = (batch + group - 1) // group
         if not m["scan_ms"]:
             return None
@@ -500,9 +515,17 @@ def main():
                         + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12)
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         traffic = load_traffic(f"scan_{idx.last_scan_kind()}", args, n_local, q_per_launch)
-        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                "kernel": f"scan_{idx.last_scan_kind()}", "launches_per_step": scan_launches,
-                "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src}
+        out = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+               "kernel": f"scan_{idx.last_scan_kind()}", "launches_per_step": scan_launches,
+               "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src}
+        if kind in ("mma", "mma128"):
+            # the tensor-core view of the same launch: 2 flops per (query, row, dimension); the exact 64-query kernel
+            # multiplies the hi and lo halves of every query (128 tensor-memory lanes)
+            lanes = 2 * q_per_launch if kind == "mma" else q_per_launch
+            tf = 2.0 * lanes * n_pass * args.dim / (per_launch_ms * 1e-3) / 1e12
+            tpeak, tsrc = load_tensor_peak()
+            out["tensor"] = {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc}
+        return out
 
     # ---- headline
     m = measure(args.batch, args.steps, args.warmup, sample_clocks=True)
@@ -558,6 +581,7 @@ def main():
             rr = roofline_of(mm, b)
             sweep.append({"batch": b, "qps": b * mm["steps"] / (mm["ms"] * 1e-3), "ms_per_step": mm["ms"] / mm["steps"],
                           "scan_frac_of_hbm_peak": rr["frac"] if rr else None,
+                          "scan_frac_of_tensor_peak": rr["tensor"]["frac"] if rr and "tensor" in rr else None,
                           "kernel": f"scan_{idx.last_scan_kind()}"})
 
     # ---- serving view: T host threads issuing single-query searches through the host-buffer C ABI, with and

@@ -16,7 +16,7 @@
 #include "scan_gemv.cuh"
 #include "scan_mma.cuh"
 #include "scan_mma128.cuh"
-#include "scan_mma256.cuh"
+#include "scan_mma256w.cuh"
 #include "select.cuh"
 #include "rescore.cuh"
 
@@ -251,7 +251,7 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     cudaError_t e = cudaSuccess;
     // 2 MB of slack after the last row: the TMA / vector paths may touch a whole tile past `size`
     if (e == cudaSuccess) e = cudaMalloc(&x->rows, size_t(cap32) * row_bytes + (2u << 20));
-    if (e == cudaSuccess) e = cudaMalloc(&x->inv_norm, size_t(cap32 + 64) * 4);   // bulk-copied per 64-row tile
+    if (e == cudaSuccess) e = cudaMalloc(&x->inv_norm, size_t(cap32 + 128) * 4);  // bulk-copied per 64- or 128-row tile
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.doc_idx, size_t(cap32) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.payer, size_t(cap32) * 2);
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.state, size_t(cap32));
@@ -262,7 +262,7 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     if (e == cudaSuccess) e = cudaMemset(x->cols.valid, 0, size_t(cap32 / 32 + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&x->cols.live, size_t(cap32 / 32 + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(x->cols.live, 0, size_t(cap32 / 32 + 1) * 4);
-    if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32 + 64) * 4);
+    if (e == cudaSuccess) e = cudaMemset(x->inv_norm, 0, size_t(cap32 + 128) * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->wstream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         int code = (e == cudaErrorMemoryAllocation) ? MRAG_ERR_OOM : MRAG_ERR_CUDA;
@@ -777,6 +777,43 @@ static int launch_scan_mma256(mrag_index* x, const MmaArgs& a, int nq, int npair
                             : launch_scan_mma256_t<1>(x, a, nq, npairs, s);
 }
 
+// the CTA-pair scan with 128-row tiles (scan_mma256w.cuh): one accumulator, 8 select warps per CTA, candidate buffers
+// in global memory (a.gcand, [2 * npairs][2][128][cap]); writes 2 * npairs partial lists per query
+template <int KBS>
+static int launch_scan_mma256w_t(mrag_index* x, MmaArgs a, int nq, int npairs, cudaStream_t s) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        CU(cudaFuncSetAttribute(scan_mma256w_kernel<KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set[dev] = true;
+    }
+    if (!a.gcand) return fail(MRAG_ERR_ARG, "scan_mma256w: global candidate buffers required");
+    a.kbs = KBS;
+    const int ks = mma256w_smem_kblocks(a.ld);          // query k-blocks kept in shared memory (beyond 8 in tensor memory)
+    const size_t fixed = mma256w_smem_bytes(0, KBS, ks);
+    const size_t stage = size_t(KBS) * kMmaWStageBytes;
+    a.stages = int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / stage));
+    if (a.stages < 2) return fail(MRAG_ERR_ARG, "scan_mma256w: pipeline does not fit");
+    const size_t smem = mma256w_smem_bytes(a.stages, KBS, ks);
+    a.P = 2 * npairs;
+    for (int q0 = 0; q0 < nq; q0 += 2 * kMma128Queries) {
+        a.q0 = q0;
+        a.nq = std::min(2 * kMma128Queries, nq - q0);
+        scan_mma256w_kernel<KBS><<<2 * npairs, kMmaWThreads, smem, s>>>(x->tmap, a);
+        LAUNCHED();
+    }
+    return MRAG_OK;
+}
+
+static int launch_scan_mma256w(mrag_index* x, const MmaArgs& a, int nq, int npairs, cudaStream_t s) {
+    const int kblocks = a.ld / kMmaKBlock;
+    return kblocks % 4 == 0 ? launch_scan_mma256w_t<4>(x, a, nq, npairs, s)
+         : kblocks % 3 == 0 ? launch_scan_mma256w_t<3>(x, a, nq, npairs, s)
+         : kblocks % 2 == 0 ? launch_scan_mma256w_t<2>(x, a, nq, npairs, s)
+                            : launch_scan_mma256w_t<1>(x, a, nq, npairs, s);
+}
+
 // Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or
 // the bf16 shadow), exact rescoring of the K' = k + 32 nominees from the primary rows, certificate,
 // exact CUDA-core rescan of the queries that fail it.  Results are EXACT (same arithmetic as scan_gemv).
@@ -799,7 +836,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     // |approx - exact| <= 2^-9 (bf16 query) + 2^-9 (the shadow's rounding, fp32 corpora) + accumulation slop
     const float eps = ((gen_gemv ? 0.0f : 0x1p-9f) + (x->dtype == MRAG_F32 ? 0x1p-9f : 0.0f) + 5e-5f) * eps_scale;
 
-    if (w->part.reserve(size_t(nq) * std::max(std::max(grid, ggrid) * kpc, ggrid * kp)) || w->gthr.reserve(size_t(nq)) ||
+    if (w->part.reserve(size_t(nq) * std::max(std::max(grid + 1, ggrid) * kpc, ggrid * kp)) || w->gthr.reserve(size_t(nq)) ||
         w->cscores.reserve(size_t(nq) * kc) || w->crows.reserve(size_t(nq) * kc) || w->ccounts.reserve(size_t(nq)) ||
         w->ckeys.reserve(size_t(nq) * kc) || w->fb.reserve(size_t(nq) + 1))
         return MRAG_ERR_OOM;
@@ -807,7 +844,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
     int rc;
     bool use_pairs = false;
-    int npairs = 0;
+    int npairs = 0, nparts = 0;
     if (gen_gemv) {
         ScanArgs ga{};
         ga.rows = x->shadow; ga.n = n; ga.ld = ld; ga.mask = mask; ga.q = w->qpad.p; ga.qinv = w->qinv.p; ga.ub = nullptr;
@@ -843,8 +880,13 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         // anything below it (a CTA holds 1/#CTAs of the sample: its top 16 almost never truncate the sample's top K')
         MmaArgs sa = a;
         sa.stats = nullptr;
-        // 4 tiles per CTA (16 for large k, whose bound must sit higher to keep the buffers quiet), at most a quarter of the shard
-        const int per_cta = int(std::max<int64_t>(1, std::min<int64_t>(kc > 64 ? 16 : 4, ceil_div(tiles, (kc > 64 ? 64 : 256) * int64_t(x->num_sms)))));
+        // up to 32 tiles per CTA, at most ~3 % of the shard (16 and ~1.5 % for large k, where the register top-16 of the sampling
+        // kernel starts to truncate): the k'-th best of the sample is the admission bound of the full pass, and every row
+        // above it costs a buffer append and, every `slack` appends, a compaction.  Measured r1q (10M x 768, k = 10): 4 -> 32
+        // tiles per CTA = 3.18 -> 2.49 ms at 128 queries, 5.0 -> 3.36 ms at 256 (pair scan); 64 tiles cost more than they save
+        const char* pc_env = getenv("MRAG_SAMPLE128_PER_CTA");
+        const int per_cta = (pc_env && *pc_env) ? std::max(1, atoi(pc_env)) :
+            int(std::max<int64_t>(1, std::min<int64_t>(kc > 64 ? 16 : 32, ceil_div(tiles, (kc > 64 ? 64 : 32) * int64_t(x->num_sms)))));
         sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
         const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
         sa.P = sgrid;
@@ -861,11 +903,21 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     // more than 128 queries: CTA pairs share every corpus tile (256 queries per pass)
     static const bool pairs_ok = [] { const char* e = getenv("MRAG_MMA256"); return !(e && e[0] == '0'); }();
     use_pairs = pairs_ok && nq > kMma128Queries && x->num_sms >= 2;
-    if (use_pairs) {
+    // 128-row tiles (one MMA per 128 rows: half the per-MMA fixed cost per corpus byte) unless MRAG_MMA256W=0
+    const char* wide_env = getenv("MRAG_MMA256W");          // read per call: the tests switch between the two pair kernels
+    const bool wide_ok = !(wide_env && wide_env[0] == '0');
+    if (use_pairs && wide_ok) {
+        npairs = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms / 2, ceil_div(n, kMmaWTileRows))));
+        if (w->gcand.reserve(size_t(2 * npairs) * 2 * kMma128Queries * cap)) return MRAG_ERR_OOM;
+        a.gcand = w->gcand.p;
+        rc = launch_scan_mma256w(x, a, nq, npairs, s);
+        nparts = 2 * npairs;
+    } else if (use_pairs) {
         npairs = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms / 2, tiles)));
         if (global_cand && w->gcand.reserve(size_t(2 * npairs) * kMma128Queries * cap)) return MRAG_ERR_OOM;
         if (global_cand) a.gcand = w->gcand.p;
         rc = launch_scan_mma256(x, a, nq, npairs, s);
+        nparts = npairs;
     } else {
         rc = launch_scan_mma128<0>(x, a, nq, grid, s);
     }
@@ -874,7 +926,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     CU(cudaEventRecord(ev.e[2], s));
     // nominees per query, by approximate score
     MergeArgs m{};
-    m.part = w->part.p; m.P = gen_gemv ? ggrid : (use_pairs ? npairs : grid); m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
+    m.part = w->part.p; m.P = gen_gemv ? ggrid : (use_pairs ? nparts : grid); m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
     m.scores = w->cscores.p; m.rows = w->crows.p; m.counts = w->ccounts.p; m.row_base = 0;
     rc = launch_merge(w, m, nq, s);
     if (rc != MRAG_OK) return rc;

@@ -582,6 +582,23 @@ def test_mma128_rescore_exact(oracle, dtype, n, dim, nq, k):
     idx.close()
 
 
+@pytest.mark.parametrize("wide", ["1", "0"])
+@pytest.mark.parametrize("n,dim,nq,k", [(300_001, 768, 300, 10), (70_000, 320, 257, 40), (129, 64, 130, 3)])
+def test_pair_scan_both_tile_shapes(oracle, monkeypatch, wide, n, dim, nq, k):
+    """More than 128 queries: CTA pairs (cta_group::2).  MRAG_MMA256W=1 (default) = 128-row tiles, one accumulator,
+    8 select warps; =0 = 64-row tiles, two accumulators.  Ragged tails: rows % 128 != 0, a last pass whose second CTA
+    has no queries, a shard smaller than one tile."""
+    monkeypatch.setenv("MRAG_MMA256W", wide)
+    X, valid = synth.make_corpus(n, dim, seed=n % 1000 + dim, null_frac=2e-3)
+    Q = synth.make_queries(X, nq, seed=k + 40)
+    idx = Index(dim, "bf16", 0, n + 3)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA128)
+    assert idx.last_scan_kind() == "mma128"
+    check_all(oracle, stored(oracle, X, "bf16"), Q, valid.astype(bool), k, s, r, c, "bf16")
+    idx.close()
+
+
 def test_mma128_default_dispatch(oracle):
     n, dim = 8000, 768
     X, valid = synth.make_corpus(n, dim, seed=5)
