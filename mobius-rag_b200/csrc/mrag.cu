@@ -905,7 +905,9 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     use_pairs = pairs_ok && nq > kMma128Queries && x->num_sms >= 2;
     // 128-row tiles (one MMA per 128 rows: half the per-MMA fixed cost per corpus byte) unless MRAG_MMA256W=0
     const char* wide_env = getenv("MRAG_MMA256W");          // read per call: the tests switch between the two pair kernels
-    const bool wide_ok = !(wide_env && wide_env[0] == '0');
+    // (large k: two lists of K' + 32 keys per query and CTA in global memory cost more than the wider MMA saves --
+    //  measured r1q, k = 100: 4.74 ms per 256 queries against 4.36 ms with the 64-row pair kernel)
+    const bool wide_ok = wide_env ? wide_env[0] != '0' : kc <= 64;
     if (use_pairs && wide_ok) {
         npairs = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms / 2, ceil_div(n, kMmaWTileRows))));
         if (w->gcand.reserve(size_t(2 * npairs) * 2 * kMma128Queries * cap)) return MRAG_ERR_OOM;
