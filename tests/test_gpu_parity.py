@@ -583,7 +583,10 @@ def test_mma128_rescore_exact(oracle, dtype, n, dim, nq, k):
 
 
 @pytest.mark.parametrize("wide", ["1", "0"])
-@pytest.mark.parametrize("n,dim,nq,k", [(300_001, 768, 300, 10), (70_000, 320, 257, 40), (129, 64, 130, 3)])
+@pytest.mark.parametrize("n,dim,nq,k", [(300_001, 768, 300, 10), (70_000, 320, 257, 40), (129, 64, 130, 3),
+                                        # 9 / 10 / 11 k-blocks: 1 / 2 / 3 query k-blocks in shared memory; 576 = a pipeline
+                                        # stage (3 k-blocks) that mixes shared-memory and tensor-memory query operands
+                                        (20_000, 576, 200, 10), (20_000, 640, 129, 5), (9_000, 704, 256, 10)])
 def test_pair_scan_both_tile_shapes(oracle, monkeypatch, wide, n, dim, nq, k):
     """More than 128 queries: CTA pairs (cta_group::2).  MRAG_MMA256W=1 (default) = 128-row tiles, one accumulator,
     8 select warps; =0 = 64-row tiles, two accumulators.  Ragged tails: rows % 128 != 0, a last pass whose second CTA
