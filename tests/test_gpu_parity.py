@@ -599,6 +599,8 @@ def test_pair_scan_both_tile_shapes(oracle, monkeypatch, wide, n, dim, nq, k):
     s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA128)
     assert idx.last_scan_kind() == "mma128"
     check_all(oracle, stored(oracle, X, "bf16"), Q, valid.astype(bool), k, s, r, c, "bf16")
+    # the exact rescan would hide a broken candidate scan: on this data at most a few certificates fail
+    assert _fallbacks() <= max(2, nq // 10), _fallbacks()
     idx.close()
 
 
