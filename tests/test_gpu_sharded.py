@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from mrag_b200 import sharded, synth
-from mrag_b200.index import Filter, Index, make_meta
+from mrag_b200.index import Filter, Index
 
 pytestmark = pytest.mark.gpu
 

@@ -12,7 +12,7 @@ import numpy as np
 import mrag_b200  # noqa: F401
 from mrag_b200 import _native as N
 from mrag_b200 import synth
-from mrag_b200.index import FEAT_DTYPE, Filter, Index, make_meta
+from mrag_b200.index import FEAT_DTYPE, Filter, Index
 
 n, dim = 3000, 128
 X, valid = synth.make_corpus(n, dim, seed=1)
