@@ -1,10 +1,10 @@
 // scan_mma256w.cuh -- the CTA-pair candidate scan with 128-row tiles (tcgen05 cta_group::2, M = 256, N = 128).
 //
 // Same statement, same barriers and same select code as scan_mma256.cuh; what changes is the shape of one MMA.
-// Measured on the 64-row kernel (r1q, idesc N overridden, 10M x 768, 256 queries): one MMA costs ~54 cycles plus
-// ~0.33 cycles per row (N = 16 / 32 / 64 / 128: <= 52 / 55 / 75 / 96 cycles), i.e. most of a 64-row MMA is a fixed
-// cost, and the pair needs <= 44 cycles per 64 rows and k-slice to keep up with HBM.  Twice the rows per MMA halves
-// that fixed cost per corpus byte:
+// Measured on the 64-row kernel (r1q, idesc N overridden, results discarded, 10M x 768, 256 queries): a pass takes
+// 2.8 / 2.9 / 3.96 ms at N = 16 / 32 / 64 and 5.1 ms at N = 128 for TWICE the rows, i.e. most of a 64-row MMA is a
+// fixed cost and the pair cannot keep up with HBM (2.35 ms per pass).  Twice the rows per MMA halves that fixed cost
+// per corpus byte:
 //     D[256 queries x 128 rows] += A[256 x 16] * B[128 x 16]^T        each CTA streams 64 rows of every tile
 // Two 128-column accumulators (MMAs of tile t+1 overlap the read-out of tile t: with a single accumulator the
 // tensor cores idled ~2000 cycles per tile, measured) leave 256 tensor-memory columns = 8 k-blocks for the queries.
@@ -14,6 +14,8 @@
 // EIGHT select warps per CTA -- two per lane quarter, one for accumulator columns 0..63 and one for 64..127 -- so a
 // query has two threads (two candidate lists, two partial results: P = 2 * pairs).  Candidate buffers live in global
 // memory (2 x 128 x cap keys per CTA).
+// Result (profiles/r1q_*): 48 MMAs per 128-row tile at ~52 SM cycles each, tensor pipe 96 % active, 2.88 ms per pass
+// at the ~1.17 GHz the SMs hold under this load = 1365 TFLOP/s, 0.98 of the sustained cuBLAS bf16 rate on this pool.
 #pragma once
 #include "scan_mma256.cuh"
 
