@@ -14,7 +14,8 @@
 // EIGHT select warps per CTA -- two per lane quarter, one for accumulator columns 0..63 and one for 64..127 -- so a
 // query has two threads (two candidate lists, two partial results: P = 2 * pairs).  Candidate buffers live in global
 // memory (2 x 128 x cap keys per CTA).
-// Result (profiles/r1q_*): 48 MMAs per 128-row tile at ~52 SM cycles each, tensor pipe 96 % active, 2.88 ms per pass
+// Result (profiles/r1q_*): 3113 SM cycles per 128-row tile for 48 MMAs of 64 cycles (128 x 128 x 16 MACs per SM at
+// 4096 MAC/clk), tensor pipe 96 % active, 2.88 ms per pass
 // at the ~1.17 GHz the SMs hold under this load = 1365 TFLOP/s, 0.98 of the sustained cuBLAS bf16 rate on this pool.
 #pragma once
 #include "scan_mma256.cuh"
