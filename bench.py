@@ -32,7 +32,64 @@ if ROOT not in sys.path:
 
 METRIC = "QPS exact cosine top-10, 10Mx768 corpus"
 DEFAULT_BATCH = 64         # queries per step (see DESIGN.md "Measurement")
-CHUNK = 1 << 16            # rows generated per chunk; shard cuts fall on chunk boundaries (fine enough to balance 8 ranks within 1 %)
+CHUNK = 1 << 16            # rows generated per chunk (the generator's unit; shard cuts fall on DOCUMENT boundaries, not here)
+PARITY_QUERIES = 4         # queries of the timed batch re-checked against the CPU oracle over the whole corpus, at every N
+
+
+def doc_layout(rows: int, seed: int = 77) -> np.ndarray:
+    """Ragged documents: 8..120 chunks each (mean 64), rows doc-contiguous as publish writes them (publish.py:310-313).
+    Returns ends[d] = first row after document d."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(8, 121, size=rows // 8 + 2)
+    ends = np.cumsum(lens)
+    n_docs = int(np.searchsorted(ends, rows, side="left")) + 1
+    ends = ends[:n_docs].copy()
+    ends[-1] = rows
+    return ends
+
+
+def docs_of(ends: np.ndarray, first: int, m: int) -> np.ndarray:
+    return np.searchsorted(ends, np.arange(first, first + m), side="right").astype(np.uint32)
+
+
+def shard_cuts(ends: np.ndarray, rows: int, world: int) -> list[int]:
+    """Row-shard boundaries: the document boundary at or after r * rows / world (a document stays on one rank; the
+    shards differ by less than one document, < 120 rows)."""
+    cuts = [0]
+    for r in range(1, world):
+        t = (rows * r) // world
+        cuts.append(int(ends[np.searchsorted(ends, t, side="left")]) if t > 0 else 0)
+    cuts.append(rows)
+    return cuts
+
+
+def filter_spec(args, ends: np.ndarray):
+    """The WHERE of the workload as (pool array or None, callable doc ids -> bool pass array)."""
+    n_docs = len(ends)
+    pool = None
+    if args.doc_pool:
+        pool = np.random.default_rng(5).choice(n_docs, size=min(args.doc_pool, n_docs), replace=False).astype(np.uint32)
+
+    def passes(docs: np.ndarray) -> np.ndarray:
+        ok = np.ones(docs.shape[0], dtype=bool)
+        if args.tag_filter:
+            ok &= (docs % args.tag_filter) == 0
+        if pool is not None:
+            ok &= np.isin(docs, pool)
+        if args.payer_filter:
+            ok &= (docs % args.payer_filter) == (3 % args.payer_filter)
+        return ok
+    return pool, passes
+
+
+def result_digest(rows_t, counts_t) -> str:
+    """sha256 over the returned row ids (+ counts) of the timed batch: must be equal at every N (ties are broken by
+    ascending global row, so the answer does not depend on the sharding)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(rows_t.cpu().numpy()).tobytes())
+    h.update(np.ascontiguousarray(counts_t.cpu().numpy()).tobytes())
+    return h.hexdigest()[:16]
 
 
 def parse_args():
@@ -50,6 +107,10 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=200_000, help="rows of the CPU baseline sample")
     ap.add_argument("--cpu-queries", type=int, default=8, help="queries of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-scan", type=int, default=1, help="--impl reference: also scan the full row count once, streamed, to validate the extrapolation (0 = skip)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle re-check of the timed batch over the whole corpus")
+    ap.add_argument("--also-f32", type=int, default=-1,
+                    help="1: after the bf16 run, store the same corpus as float4 and measure the same batch (default: on for the headline workload)")
     ap.add_argument("--threads", type=int, default=32, help="host threads of the concurrent single-query measurement (0 = skip)")
     ap.add_argument("--tag-filter", type=int, default=0, metavar="M",
                     help="document-tag filter passing every M-th document (0 = no filter); C2 uses 10")
@@ -195,10 +256,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restatement of the reference's pgvector path) on this box's cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_qps(args, steps: int, warmup: int) -> dict:
+def cpu_reference_qps(args, steps: int, warmup: int, extras: bool = False) -> dict:
     """Times oracle.search (C restatement of pgvector cosine_distance + ORDER BY/LIMIT, all host
     threads) on a bounded sample: `cpu_rows` rows x `cpu_queries` queries per step, and scales the
-    per-query time linearly in the row count to the full corpus (the scan is linear in rows)."""
+    per-query time linearly in the row count to the full corpus (the scan is linear in rows).
+    extras: also (a) the single-thread "pgvector model" figure (one backend process per statement) and (b) ONE pass over
+    the FULL row count, streamed chunk by chunk, to validate the linear extrapolation."""
     from oracle import oracle
     from mrag_b200 import synth
     cores = os.cpu_count() or 1
@@ -209,37 +272,68 @@ def cpu_reference_qps(args, steps: int, warmup: int) -> dict:
         X = oracle.round_bf16(X)
     Q = synth.make_queries(X, nq_s, seed=4321)
     mask = valid.astype(bool)
-    for _ in range(max(1, min(warmup, 1))):
-        oracle.search(X, Q[:1], args.k, mask)
+    for _ in range(max(0, warmup)):
+        oracle.search(X, Q, args.k, mask)
     t0 = time.perf_counter()
     for _ in range(steps):
         oracle.search(X, Q, args.k, mask)
     dt = time.perf_counter() - t0
     per_query_sample = dt / (steps * nq_s)
-    per_query_full = per_query_sample * (args.rows / n_s)
-    return {
+    scale = args.rows / n_s
+    per_query_full = per_query_sample * scale
+    out = {
         "value": 1.0 / per_query_full, "unit": "queries/s", "cores": cores, "kind": "port",
         "sample": f"{n_s} rows x {args.dim} ({args.dtype} rows upcast to fp32, as pgvector stores float4) x {nq_s} queries x "
-                  f"{steps} steps, {cores} scan threads; per-query time scaled x{args.rows / n_s:.0f} to {args.rows} rows",
+                  f"{steps} steps, {cores} scan threads; per-query time scaled x{scale:.0f} to {args.rows} rows",
         "seconds": dt, "ms_per_query_sample": per_query_sample * 1e3,
     }
+    if extras:
+        # (a) one Postgres backend executes one statement: the same scan on ONE thread
+        oracle.set_threads(1)
+        oracle.search(X, Q[:1], args.k, mask)
+        t1 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            oracle.search(X, Q[:2], args.k, mask)
+        st = (time.perf_counter() - t1) / (reps * 2) * scale
+        out["single_thread"] = {"value": 1.0 / st, "unit": "queries/s", "cores": 1,
+                                "note": "one scan thread = one Postgres backend per statement (pgvector runs a query on one process)"}
+        oracle.set_threads(cores)
+        # (b) the full row count once, streamed: same kernel over `rows` rows in chunks of the sample size (fresh random
+        #     rows per chunk, generation not timed), per-chunk top-k merged on the host like a parallel seq scan's gather
+        import torch
+        g = torch.Generator().manual_seed(99)
+        scan_s, done = 0.0, 0
+        while done < args.rows and args.full_scan:
+            m_rows = min(n_s, args.rows - done)
+            Xc = torch.randn((m_rows, args.dim), generator=g, dtype=torch.float32).numpy()
+            t2 = time.perf_counter()
+            r, sm, c = oracle.search(Xc, Q, args.k, None)
+            scan_s += time.perf_counter() - t2
+            done += m_rows
+        if args.full_scan:
+            out["full_scan_validation"] = {"rows": args.rows, "queries": nq_s, "ms_per_query": scan_s / nq_s * 1e3,
+                                       "extrapolated_ms_per_query": per_query_full * 1e3,
+                                       "ratio_measured_over_extrapolated": (scan_s / nq_s) / per_query_full}
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    base = cpu_reference_qps(args, steps, args.warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base = cpu_reference_qps(args, steps, warmup, extras=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["seconds"] / steps * 1e3,
+        "steps": steps, "warmup": warmup, "ms_per_step": base["seconds"] / steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.batch),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "single_thread": base.get("single_thread"), "full_scan_validation": base.get("full_scan_validation"),
         "note": "reference = Postgres+pgvector, not runnable here (no Postgres, extension not vendored): this arm "
-                "is the CPU oracle port of its exact-scan plan, all host threads",
+                "is the CPU oracle port of its exact-scan plan, all host threads; each step = the bounded sample in cpu_baseline.sample",
     }
     print(json.dumps(line), flush=True)
 
@@ -350,6 +444,45 @@ def run_c5(args, idx, plant, dev, n_local, world, rank, hbm_peak, peak_src, t_bu
 
 
 # ---------------------------------------------------------------------------------------------
+# parity of the timed batch against the CPU oracle over the whole corpus (rank 0, every N)
+# ---------------------------------------------------------------------------------------------
+def parity_check(args, dev, ends, passes, checks) -> dict:
+    """checks: [(corpus dtype, Q cuda [B, dim], (scores, rows, counts) cuda = the GLOBAL result of the timed batch)].
+    Re-generates the seeded corpus chunk by chunk on the GPU (the generator IS the corpus definition), copies each chunk
+    to the host and runs the C restatement of pgvector's cosine_distance for PARITY_QUERIES queries of every check; then
+    oracle.check_topk (ids and order identical up to ties within 1e-6; scores within 1e-4 relative for float4 rows,
+    1e-2 for the bf16 storage mode, whose oracle sees the bf16-rounded rows)."""
+    import torch
+    from oracle import oracle
+    from mrag_b200 import synth
+    t0 = time.perf_counter()
+    oracle.set_threads(os.cpu_count() or 1)
+    B = int(checks[0][1].shape[0])
+    # two of the random-direction half and two of the planted-neighbour half of the batch
+    sel = sorted({0, B // 2 - 1, B // 2, B - 1} & set(range(B))) if B >= PARITY_QUERIES else list(range(B))
+    streams = [oracle.StreamCheck(args.rows, Q[sel].cpu().numpy()) for _, Q, _ in checks]
+    for first, X in synth.cuda_corpus_chunks(args.rows, args.dim, dev, seed=1234, chunk=CHUNK):
+        Xf = X.cpu().numpy() if any(dt == "f32" for dt, _, _ in checks) else None
+        Xb = X.to(torch.bfloat16).to(torch.float32).cpu().numpy() if any(dt == "bf16" for dt, _, _ in checks) else None
+        for (dt, _, _), sc in zip(checks, streams):
+            sc.feed(first, Xb if dt == "bf16" else Xf)
+    mask = passes(docs_of(ends, 0, args.rows)) if (args.tag_filter or args.doc_pool or args.payer_filter) else None
+    out = {"status": "ok", "queries_checked": len(sel) * len(checks), "query_indices": sel, "rows": args.rows,
+           "oracle": "oracle/pgv_oracle.c (restated pgvector cosine_distance) + ORDER BY/LIMIT, tie-aware check_topk over the whole corpus",
+           "rtol": {"f32": 1e-4, "bf16": 1e-2}, "checked": [dt for dt, _, _ in checks]}
+    for (dt, _, res), sc in zip(checks, streams):
+        s, r, c = (t.cpu().numpy() for t in res)
+        for j, qi in enumerate(sel):
+            try:
+                sc.check(j, r[qi], s[qi], int(c[qi]), mask, args.k, rtol=1e-4 if dt == "f32" else 1e-2)
+            except AssertionError as e:
+                out["status"] = "FAILED"
+                out.setdefault("failures", []).append(f"{dt} query {qi}: {e}")
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -369,6 +502,8 @@ def main():
         args.doc_pool = args.doc_pool or 50
     elif args.workload == "c5":
         args.rows, args.dim, args.dtype, args.k, args.batch, args.sweep = 10_000_000, 768, "bf16", 50, 22, ""
+    if args.also_f32 < 0:
+        args.also_f32 = 1 if (args.workload == "" and args.dtype == "bf16" and args.dim == 768 and not (args.tag_filter or args.payer_filter or args.doc_pool)) else 0
     if args.impl == "reference":
         run_reference(args)
         return
@@ -391,48 +526,55 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
-    # ---- build this rank's shard (chunk-aligned contiguous row block; 64 rows per document)
-    n_chunks = (args.rows + CHUNK - 1) // CHUNK
-    c_lo, c_hi = (n_chunks * rank) // world, (n_chunks * (rank + 1)) // world
-    lo, hi = min(c_lo * CHUNK, args.rows), min(c_hi * CHUNK, args.rows)
+    # ---- build this rank's shard: contiguous row block cut at document boundaries, ragged documents
+    ends = doc_layout(args.rows)
+    n_docs_all = len(ends)
+    cuts = shard_cuts(ends, args.rows, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
     n_local = hi - lo
-    idx = mi.Index(args.dim, args.dtype, local_rank, max(n_local, 1))
-    idx.set_row_base(lo)
-    t_build = time.perf_counter()
-    plant = None
-    for first, X in synth.cuda_corpus_chunks(args.rows, args.dim, dev, seed=1234, chunk=CHUNK):
-        if first == 0:
-            plant = X[:4096].clone()                      # queries are planted near rows of chunk 0 on every rank
-        if first < lo:
-            if rank == 0 or first > 0:
-                pass
-            continue
-        if first >= hi:
-            break
-        m = X.shape[0]
-        docs = (np.arange(first, first + m) // 64).astype(np.uint32)
-        meta = mi.make_meta(m, doc_idx=docs, payer=(docs % max(args.payer_filter, 1)).astype(np.uint16) if args.payer_filter else None)
-        idx.append_device(X, meta)
+    pool, passes = filter_spec(args, ends)
+
+    def build_shard(dtype: str):
+        """(index, plant, seconds): this rank's rows of the seeded corpus, appended from device chunks."""
+        t0 = time.perf_counter()
+        ix = mi.Index(args.dim, dtype, local_rank, max(n_local, 1))
+        ix.set_row_base(lo)
+        pl = None
+        for first, X in synth.cuda_corpus_chunks(args.rows, args.dim, dev, seed=1234, chunk=CHUNK):
+            if first == 0:
+                pl = X[:4096].clone()                     # queries are planted near rows of chunk 0 on every rank
+            a, b = max(first, lo), min(first + X.shape[0], hi)
+            if first >= hi:
+                break
+            if a >= b:
+                continue
+            docs = docs_of(ends, a, b - a)
+            meta = mi.make_meta(b - a, doc_idx=docs,
+                                payer=(docs % args.payer_filter).astype(np.uint16) if args.payer_filter else None)
+            ix.append_device(X[a - first:b - first], meta)
+        if args.tag_filter:
+            bits = np.zeros((n_docs_all, 8), dtype=np.uint64)
+            bits[::args.tag_filter, 0] = 1                   # tag bit 0 on every M-th document
+            ix.set_doc_tags(0, bits)
+        torch.cuda.synchronize()
+        assert len(ix) == n_local
+        return ix, pl, time.perf_counter() - t0
+
+    idx, plant, t_build = build_shard(args.dtype)
     flt = None
-    pass_frac = 1.0
     if args.tag_filter:
-        n_docs = (args.rows + 63) // 64
-        bits = np.zeros((n_docs, 8), dtype=np.uint64)
-        bits[::args.tag_filter, 0] = 1                       # tag bit 0 on every M-th document
-        idx.set_doc_tags(0, bits)
         flt = mi.Filter().tag_relaxed([0])
-        pass_frac = float(np.ceil(n_docs / args.tag_filter) / n_docs)
-    if args.doc_pool:
-        n_docs_all = (args.rows + 63) // 64
-        pool = np.random.default_rng(5).choice(n_docs_all, size=min(args.doc_pool, n_docs_all), replace=False).astype(np.uint32)
+    if pool is not None:
         flt = (flt or mi.Filter()).doc_pool(pool)
-        pass_frac *= len(pool) / n_docs_all
     if args.payer_filter:
         flt = (flt or mi.Filter()).payer_in([3 % args.payer_filter])
-        pass_frac *= 1.0 / args.payer_filter
-    torch.cuda.synchronize()
-    t_build = time.perf_counter() - t_build
-    assert len(idx) == n_local
+    local_pass = passes(docs_of(ends, lo, n_local)) if flt is not None else None
+    n_pass_local = int(local_pass.sum()) if local_pass is not None else n_local
+    tile_rows_local = n_local
+    if local_pass is not None:                               # rows of the 64-row tiles that hold a passing row
+        padded = np.zeros((n_local + 63) // 64 * 64, dtype=bool)
+        padded[:n_local] = local_pass
+        tile_rows_local = int(padded.reshape(-1, 64).any(axis=1).sum()) * 64
 
     elem = 2 if args.dtype == "bf16" else 4
     hbm_peak, peak_src = load_peaks()
@@ -441,16 +583,16 @@ def main():
         idx.close()
         return
 
-    def make_searcher():
-        if world > 1:
-            return sharded.ShardedSearcher(index=idx, exchange=os.environ.get("MRAG_EXCHANGE", "auto"))
-        return None
-    ss = make_searcher()
+    class Arm:
+        """One resident shard + (N > 1) its cross-rank searcher; everything measured below goes through it."""
+        def __init__(self, ix, dtype):
+            self.idx, self.dtype = ix, dtype
+            self.ss = sharded.ShardedSearcher(index=ix, exchange=os.environ.get("MRAG_EXCHANGE", "auto")) if world > 1 else None
 
-    def one_step(qd, k, out=None):
-        if ss is not None:
-            return ss.search(qd, k, flt)
-        return idx.search_device(qd, k, flt, out=out, sync=False)
+        def step(self, qd, k, out=None):
+            if self.ss is not None:
+                return self.ss.search(qd, k, flt)
+            return self.idx.search_device(qd, k, flt, out=out, sync=False)
 
     def barrier():
         if world > 1:
@@ -464,15 +606,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def measure(batch: int, steps: int, warmup: int, sample_clocks: bool):
+    def measure(arm, batch: int, steps: int, warmup: int, sample_clocks: bool):
         Q = synth.cuda_queries(plant, batch, args.dim, dev, seed=4321)
         out = None
-        if ss is None:
+        if arm.ss is None:
             out = (torch.empty((batch, args.k), dtype=torch.float32, device=dev),
                    torch.empty((batch, args.k), dtype=torch.int64, device=dev),
                    torch.empty((batch,), dtype=torch.int32, device=dev))
         for _ in range(max(warmup, 3)):
-            res = one_step(Q, args.k, out)
+            res = arm.step(Q, args.k, out)
         barrier()
         clocks = ClockSampler(local_rank) if sample_clocks else None
         if clocks:
@@ -483,7 +625,7 @@ def main():
         barrier()
         e0.record()
         for _ in range(steps):
-            res = one_step(Q, args.k, out)
+            res = arm.step(Q, args.k, out)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
@@ -494,11 +636,11 @@ def main():
         mi.profile_begin(0)
         clk = clocks.stop() if clocks else None
         return {"batch": batch, "ms": ms, "steps": steps, "launches": launches, "scan_ms": scan_ms, "prep_ms": prep_ms,
-                "merge_ms": merge_ms, "clocks": clk, "result": res, "Q": Q}
+                "merge_ms": merge_ms, "clocks": clk, "result": tuple(t.clone() for t in res), "Q": Q}
 
-    def roofline_of(m, batch):
-        kind = idx.last_scan_kind()
-        group = {"gemv": 4, "gemv_shadow": 4, "mma": 64, "mma128": 128}[kind]      # queries per scan launch
+    def roofline_of(arm, m, batch):
+        kind = arm.idx.last_scan_kind()
+        group = {"gemv": 4, "gemv_shadow": 4, "mma": 64, "mma_ks": 64, "mma128": 128}[kind]      # queries per scan launch
         if kind == "mma128" and batch > 128:
             group = 256                                                             # CTA pairs: 256 queries per pass
         scan_launches = (batch + group - 1) // group
@@ -506,31 +648,49 @@ def main():
             return None
         per_launch_ms = float(np.mean(m["scan_ms"])) / scan_launches
         q_per_launch = min(batch, group)
-        # bytes the scan kernel has to stream: the rows that pass the filter in the storage it reads (the
-        # tensor-core kernels read bf16 rows -- for an fp32 corpus its bf16 shadow; the rows are 64-row tiles,
-        # so with a document filter whole passing tiles are read), the mask, 1/|x|, queries in, lists out
-        scan_elem = 2 if kind in ("mma", "mma128", "gemv_shadow") else elem
-        n_pass = int(n_local * pass_frac)
-        bytes_launch = (n_pass * args.dim * scan_elem + (n_local + 7) // 8 + (n_pass * 4 if kind in ("mma", "mma128") else 0)
+        # bytes = n_pass * D * s + ceil(N/8) + N*4 (1/|x|, tensor-core paths) + q*D*4 + q*k*12, with
+        # n_pass = rows passing the filter and s = the element size of the storage the kernel streams (the tensor-core
+        # kernels stream bf16 rows -- for an fp32 corpus its bf16 shadow).  The tensor-core kernels fetch whole 64-row
+        # tiles, so with a filter they read `tile_rows_streamed` >= n_pass rows: that shows up as frac < 1, not here.
+        tensor_kind = kind in ("mma", "mma_ks", "mma128")
+        scan_elem = 2 if (tensor_kind or kind == "gemv_shadow") else (2 if arm.dtype == "bf16" else 4)
+        bytes_launch = (n_pass_local * args.dim * scan_elem + (n_local + 7) // 8 + (n_pass_local * 4 if tensor_kind else 0)
                         + q_per_launch * args.dim * 4 + q_per_launch * args.k * 12)
         ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
-        traffic = load_traffic(f"scan_{idx.last_scan_kind()}", args, n_local, q_per_launch)
+        traffic = load_traffic(f"scan_{kind}", args, n_local, q_per_launch) if arm.dtype == args.dtype else None
         out = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-               "kernel": f"scan_{idx.last_scan_kind()}", "launches_per_step": scan_launches,
-               "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src}
-        if kind in ("mma", "mma128"):
-            # the tensor-core view of the same launch: 2 flops per (query, row, dimension); the exact 64-query kernel
-            # multiplies the hi and lo halves of every query (128 tensor-memory lanes)
-            lanes = 2 * q_per_launch if kind == "mma" else q_per_launch
-            tf = 2.0 * lanes * n_pass * args.dim / (per_launch_ms * 1e-3) / 1e12
+               "kernel": f"scan_{kind}", "launches_per_step": scan_launches,
+               "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src,
+               "rows_passing_filter": n_pass_local, "tile_rows_streamed": tile_rows_local if tensor_kind else n_pass_local}
+        if tensor_kind:
+            # the tensor-core view of the same launch: 2 flops per (query, row, dimension); the exact 64-query kernels
+            # multiply the hi and lo halves of every query (128 tensor-memory lanes)
+            lanes = 2 * q_per_launch if kind in ("mma", "mma_ks") else q_per_launch
+            tf = 2.0 * lanes * n_pass_local * args.dim / (per_launch_ms * 1e-3) / 1e12
             tpeak, tsrc = load_tensor_peak()
             out["tensor"] = {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc}
         return out
 
     # ---- headline
-    m = measure(args.batch, args.steps, args.warmup, sample_clocks=True)
+    arm = Arm(idx, args.dtype)
+    ss = arm.ss
+    exchange_name = None
+    if ss is not None:
+        ss.search(synth.cuda_queries(plant, args.batch, args.dim, dev, seed=4321), args.k, flt)     # decides p2p vs NCCL
+        exchange_name = ("peer stores inside the merge kernel (symmetric memory)" if ss.exchange != "nccl" and ss._p2p
+                         else "NCCL all_gather_into_tensor + merge kernel")
+    m = measure(arm, args.batch, args.steps, args.warmup, sample_clocks=True)
     qps = args.batch * args.steps / (m["ms"] * 1e-3)
-    roof = roofline_of(m, args.batch)
+    roof = roofline_of(arm, m, args.batch)
+    # whole-step fractions (everything between the step's first and last kernel, not the scan launch alone)
+    step_s = m["ms"] / args.steps * 1e-3
+    step_view = None
+    if roof:
+        step_view = {"hbm_frac": roof["algorithmic_bytes_per_launch"] * roof["launches_per_step"] / step_s / 1e9 / hbm_peak}
+        if "tensor" in roof:
+            tpeak, _ = load_tensor_peak()
+            lanes = 2 if roof["kernel"] in ("scan_mma", "scan_mma_ks") else 1
+            step_view["tensor_frac"] = 2.0 * lanes * args.batch * n_pass_local * args.dim / step_s / 1e12 / tpeak
 
     # ---- end to end through the host-buffer API: pinned host queries in, host results out, every step
     Qh = m["Q"].cpu().pin_memory()
@@ -557,10 +717,9 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_qps = args.batch * args.steps / e2e_s
     # the e2e path must return what the device path returned
-    if ss is None:
-        assert torch.equal(hr, m["result"][1].cpu()), "e2e result differs from device-resident result"
+    assert torch.equal(hr, m["result"][1].cpu()), "e2e result differs from device-resident result"
 
-    # ---- where a sharded step spends its time: local search / allgather / k-way merge (rank 0's view)
+    # ---- where a sharded step spends its time on the path that was timed (rank 0's view)
     shard_phases = None
     if ss is not None:
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
@@ -568,8 +727,8 @@ def main():
         for i in range(args.steps):
             ss.search(m["Q"], args.k, flt, events=evs[i])
         barrier()
-        shard_phases = {name: float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs]))
-                        for j, name in enumerate(("local_search", "allgather", "kway_merge"))}
+        names = ss.phase_names()
+        shard_phases = {name: float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j, name in enumerate(names)}
 
     # ---- brief sweep over other batch sizes (N=1 only, not the headline)
     sweep = []
@@ -577,12 +736,19 @@ def main():
         for b in [int(x) for x in args.sweep.split(",") if x.strip()]:
             if b == args.batch:
                 continue
-            mm = measure(b, 5, 3, sample_clocks=False)
-            rr = roofline_of(mm, b)
-            sweep.append({"batch": b, "qps": b * mm["steps"] / (mm["ms"] * 1e-3), "ms_per_step": mm["ms"] / mm["steps"],
-                          "scan_frac_of_hbm_peak": rr["frac"] if rr else None,
-                          "scan_frac_of_tensor_peak": rr["tensor"]["frac"] if rr and "tensor" in rr else None,
-                          "kernel": f"scan_{idx.last_scan_kind()}"})
+            mm = measure(arm, b, 5, 3, sample_clocks=False)
+            rr = roofline_of(arm, mm, b)
+            st_s = mm["ms"] / mm["steps"] * 1e-3
+            ent = {"batch": b, "qps": b * mm["steps"] / (mm["ms"] * 1e-3), "ms_per_step": mm["ms"] / mm["steps"],
+                   "scan_frac_of_hbm_peak": rr["frac"] if rr else None,
+                   "scan_frac_of_tensor_peak": rr["tensor"]["frac"] if rr and "tensor" in rr else None,
+                   "kernel": f"scan_{idx.last_scan_kind()}"}
+            if rr and "tensor" in rr:
+                lanes = 2 if rr["kernel"] in ("scan_mma", "scan_mma_ks") else 1
+                ent["step_frac_of_tensor_peak"] = 2.0 * lanes * b * n_pass_local * args.dim / st_s / 1e12 / load_tensor_peak()[0]
+            if rr:
+                ent["step_frac_of_hbm_peak"] = rr["algorithmic_bytes_per_launch"] * rr["launches_per_step"] / st_s / 1e9 / hbm_peak
+            sweep.append(ent)
 
     # ---- serving view: T host threads issuing single-query searches through the host-buffer C ABI, with and
     #      without request coalescing (concurrent requests share one pass over the corpus)
@@ -611,6 +777,34 @@ def main():
                       "qps_coalesced_calls": serve(N.OPT_COALESCE) if flt is None else None,
                       "note": "single-query mrag_search calls from host threads, host buffers; coalesced = MRAG_OPT_COALESCE"}
 
+    # ---- the same corpus stored as float4 (the reference's own precision, add_pgvector_columns.py:49), same batch
+    checks = [(args.dtype, m["Q"], m["result"])]
+    f32_line = None
+    if args.also_f32 and args.dtype == "bf16":
+        idx.close()
+        arm = ss = None
+        torch.cuda.empty_cache()
+        idx32, _, t_build32 = build_shard("f32")
+        arm32 = Arm(idx32, "f32")
+        m32 = measure(arm32, args.batch, max(3, args.steps // 2), 3, sample_clocks=False)
+        r32 = roofline_of(arm32, m32, args.batch)
+        f32_line = {"value": args.batch * m32["steps"] / (m32["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": m32["ms"] / m32["steps"],
+                    "corpus_dtype": "f32", "kernel": f"scan_{idx32.last_scan_kind()}", "steps": m32["steps"],
+                    "scan_frac_of_hbm_peak": r32["frac"] if r32 else None, "build_s": t_build32,
+                    "result_digest": result_digest(m32["result"][1], m32["result"][2]),
+                    "note": "same rows stored as float4 (30.7 GB + a 15.4 GB bf16 shadow for candidate generation); results are "
+                            "exact fp32 (nominees rescored from the float4 rows, certificate, exact rescan on failure)"}
+        checks.append(("f32", m32["Q"], m32["result"]))
+        idx32.close()
+    else:
+        idx.close()
+
+    # ---- parity: rank 0 re-checks PARITY_QUERIES queries of each timed batch against the CPU oracle (C restatement of
+    #      pgvector's `<=>` + ORDER BY / LIMIT) over the WHOLE corpus, streamed chunk by chunk from the same seeded generator
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(args, dev, ends, passes, checks)
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -631,23 +825,27 @@ def main():
                     "d2h_bytes_per_step": args.batch * args.k * 12 + args.batch * 4},
             "gpu_launches": int(m["launches"]),
             "roofline": roof, "cpu_baseline": cpu, "clocks": m["clocks"],
+            "parity": parity, "result_digest": result_digest(m["result"][1], m["result"][2]),
             "phases_ms": {"prepare": float(np.mean(m["prep_ms"])) if m["prep_ms"] else None,
                           "scan": float(np.mean(m["scan_ms"])) if m["scan_ms"] else None,
                           "merge": float(np.mean(m["merge_ms"])) if m["merge_ms"] else None},
+            "step_frac": step_view,
             "rows_per_gpu": n_local, "build_s": t_build, "sweep": sweep,
         }
+        if f32_line:
+            line["f32_corpus"] = f32_line
         if shard_phases:
             line["shard_phases_ms"] = shard_phases
-        if ss is not None:
-            line["config"]["exchange"] = ("peer stores inside the merge kernel (symmetric memory)" if ss.exchange != "nccl" and ss._p2p
-                                          else "NCCL all_gather_into_tensor + merge kernel")
+        if world > 1:
+            line["config"]["exchange"] = exchange_name
         if concurrent:
             line["concurrent_single_query"] = concurrent
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    idx.close()
+    if parity and parity.get("status") != "ok":
+        sys.exit(1)
 
 
 if __name__ == "__main__":

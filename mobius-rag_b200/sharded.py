@@ -131,7 +131,7 @@ class ShardedSearcher:
             self._p2p = None
         return self._p2p
 
-    def _search_p2p(self, st, q, k: int, flt):
+    def _search_p2p(self, st, q, k: int, flt, events=None):
         import torch
         from . import _native as N
         nq = int(q.shape[0])
@@ -139,7 +139,11 @@ class ShardedSearcher:
         self._epoch += 1
         area = (self._epoch & 1) * self.world * lay["size"]
         slot = buf[area + self.rank * lay["size"]: area + (self.rank + 1) * lay["size"]]
+        if events:
+            events[0].record()
         self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        if events:
+            events[1].record()
         out = (torch.empty((nq, k), dtype=torch.float32, device=buf.device),
                torch.empty((nq, k), dtype=torch.int64, device=buf.device),
                torch.empty((nq,), dtype=torch.int32, device=buf.device))
@@ -147,18 +151,26 @@ class ShardedSearcher:
         N.check(N.load().mrag_exchange_merge(self.index.device, self.world, self.rank, nq, int(k), st["ptrs"],
                                              lay["size"], lay["scores_off"], lay["counts_off"], self._epoch,
                                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stream))
+        if events:
+            events[2].record()
         return out
+
+    def phase_names(self) -> tuple:
+        """Names of the intervals between the events `search(..., events=)` records, for the exchange in use."""
+        if self.exchange != "nccl" and self._p2p is not None:
+            return ("local_search", "exchange+kway_merge (one kernel, peer stores)")
+        return ("local_search", "allgather", "kway_merge")
 
     # -- the search --------------------------------------------------------------------------
     def search(self, q, k: int, flt=None, events=None):
         """q: [nq, dim] float32 on this rank's device, identical on every rank.
         Returns (scores [nq,k], rows [nq,k] global ids, counts [nq]) on every rank.
-        events: optional list of 4 torch.cuda.Event (timing enabled) recorded around the three phases."""
+        events: optional list of 4 torch.cuda.Event (timing enabled) recorded around the phases (see phase_names)."""
         nq = int(q.shape[0])
-        if self._local == self._cuda_local and self._merge == self._cuda_merge and not events:
+        if self._local == self._cuda_local and self._merge == self._cuda_merge:
             st = self._p2p_state(nq, k)
             if st is not None:
-                return self._search_p2p(st, q, k, flt)
+                return self._search_p2p(st, q, k, flt, events)
         lay, slot, gathered = self._buffers(nq, k)
         if events:
             events[0].record()

@@ -10,8 +10,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(*extra, env=None):
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-           "--cpu-rows", "20000", "--cpu-queries", "2", *extra]
+    base = ["--steps", "1", "--warmup", "1", "--full-scan", "0"]
+    for flag in ("--steps", "--warmup", "--full-scan"):
+        if flag in extra:
+            i = base.index(flag)
+            del base[i:i + 2]
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *base, "--cpu-rows", "20000", "--cpu-queries", "2", *extra]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -33,6 +37,14 @@ def test_reference_arm_line():
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+    assert d["single_thread"]["cores"] == 1 and d["single_thread"]["value"] > 0
+
+
+def test_reference_arm_honours_steps_and_validates_the_extrapolation():
+    d = _run("--rows", "60000", "--full-scan", "1", "--steps", "3", "--warmup", "2")
+    assert d["steps"] == 3 and d["warmup"] == 2
+    v = d["full_scan_validation"]
+    assert v["rows"] == 60000 and 0.2 < v["ratio_measured_over_extrapolated"] < 5.0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
