@@ -270,6 +270,12 @@ int mrag_dtag_mask(mrag_index* idx, const mrag_filter* filter, const uint16_t* d
 
 /* Global row id offset added to every returned row (shard base for row-sharded corpora). */
 int mrag_set_row_base(mrag_index* idx, int64_t row_base);
+/* Explicit ids for rows [first_row, first_row + n) (HOST array; may be set before those rows are appended, up to the
+ * capacity): a search returns ids[row] instead of row + row_base.  Used when ONE process owns several shards of one
+ * table (a FastAPI worker holding all 8 GPUs of a box, vector_store.py:181-226 behind one store object): the id is the
+ * row's position in the host table, so the k-way merge of the shards' lists (mrag_merge_topk: score DESC, id ASC)
+ * breaks ties exactly as an unsharded table would.  Within a shard the ids must increase with the row. */
+int mrag_set_row_ids(mrag_index* idx, int64_t first_row, const int64_t* ids, int64_t n);
 
 /* K4: k-way merge of `n_lists` per-shard results into one nq*k result on `device`.
  * This is the step that follows the allgather across row shards.  List l lives at

@@ -29,6 +29,7 @@ EXPORTS = [
     "mrag_profile_begin", "mrag_profile_read", "mrag_launch_count", "mrag_last_scan_kind",
     "mrag_last_error", "mrag_version",
     "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge", "mrag_save", "mrag_load",
+    "mrag_set_row_ids",
 ]
 
 
@@ -132,6 +133,8 @@ def load(build_if_missing: bool = True):
     lib.mrag_search.argtypes = [vp, vp, i32, i32, C.POINTER(FilterStruct), vp, vp, vp, u32, vp]
     lib.mrag_set_row_base.restype = i32
     lib.mrag_set_row_base.argtypes = [vp, i64]
+    lib.mrag_set_row_ids.restype = i32
+    lib.mrag_set_row_ids.argtypes = [vp, i64, vp, i64]
     lib.mrag_merge_topk.restype = i32
     lib.mrag_merge_topk.argtypes = [i32, i32, i32, i32, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]
     lib.mrag_filter_mask.restype = i32

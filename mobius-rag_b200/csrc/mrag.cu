@@ -147,6 +147,7 @@ struct mrag_index {
     uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
     int64_t n_tag_docs = 0, tag_docs_cap = 0;
     mrag_chunkfeat* feat = nullptr;     // [capacity] text features of the hybrid rerank (allocated on first use, zero = none)
+    int64_t* row_ids = nullptr;         // [capacity] caller-assigned id of every row (mrag_set_row_ids), nullptr = row + row_base
     uint64_t* doc_jtags = nullptr;      // [jtag_docs_cap][MRAG_JTAG_WORDS]
     int64_t n_jtag_docs = 0, jtag_docs_cap = 0;
     CUtensorMap tmap;                   // bf16 rows (or the shadow) as a 2-D tensor, 64x64 boxes, SWIZZLE_128B
@@ -280,7 +281,9 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
         cudaError_t es = cudaMalloc(&x->shadow, size_t(cap32) * x->ld * 2 + (2u << 20));
         if (es != cudaSuccess) { x->shadow = nullptr; cudaGetLastError(); }   // not fatal: exact scan only
     }
-    if ((dtype == MRAG_BF16 || x->shadow) && x->ld <= kMmaMaxLd) {
+    // bf16 rows of up to 1536 elements feed the tensor-core scans (one CTA up to 768, k-split CTA pairs beyond); the bf16
+    // shadow of an fp32 shard only the candidate scans (<= 768)
+    if ((dtype == MRAG_BF16 && x->ld <= kMmaKsMaxLd) || (x->shadow && x->ld <= kMmaMaxLd)) {
         // rows past `capacity` inside the allocation are never selected (mask bits are zero)
         void* tbase = dtype == MRAG_BF16 ? x->rows : static_cast<void*>(x->shadow);
         if (make_corpus_tmap(x, &x->tmap, tbase, cap32 + 64, kMmaTileRows) != MRAG_OK ||
@@ -314,6 +317,7 @@ extern "C" int mrag_destroy(mrag_index* x) {
     if (x->cols.live) cudaFree(x->cols.live);
     if (x->doc_tags) cudaFree(x->doc_tags);
     if (x->feat) cudaFree(x->feat);
+    if (x->row_ids) cudaFree(x->row_ids);
     if (x->doc_jtags) cudaFree(x->doc_jtags);
     if (x->wstream) cudaStreamDestroy(x->wstream);
     t_last_valid = false;
@@ -331,6 +335,39 @@ extern "C" int mrag_set_row_base(mrag_index* x, int64_t row_base) {
     if (!x) return fail(MRAG_ERR_ARG, "mrag_set_row_base: null index");
     std::unique_lock<std::shared_mutex> wl(x->lock);
     x->row_base = row_base;
+    return MRAG_OK;
+}
+
+// returned row = ids[row] instead of row + row_base (several shards of ONE table in one process: the id is the row's
+// position in the host table, so ties break exactly as in an unsharded table)
+__global__ void remap_rows_kernel(int64_t* __restrict__ rows, size_t count, const int64_t* __restrict__ ids, int64_t row_base) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const int64_t r = rows[i];
+        if (r >= 0) rows[i] = ids[r - row_base];
+    }
+}
+
+extern "C" int mrag_set_row_ids(mrag_index* x, int64_t first_row, const int64_t* ids, int64_t n) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_row_ids: null index");
+    if (first_row < 0 || n < 0 || first_row + n > x->capacity)
+        return fail(MRAG_ERR_ARG, "mrag_set_row_ids: rows [%lld, %lld) outside the capacity %lld", (long long)first_row,
+                    (long long)(first_row + n), (long long)x->capacity);
+    if (n == 0) return MRAG_OK;
+    if (!ids) return fail(MRAG_ERR_ARG, "mrag_set_row_ids: ids is null");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_set_row_ids: cudaSetDevice failed");
+    if (!x->row_ids) {
+        // rows without an explicit id keep the default (row + row_base): fill the identity first
+        std::vector<int64_t> ident(size_t(x->capacity));
+        for (int64_t i = 0; i < x->capacity; ++i) ident[size_t(i)] = i + x->row_base;
+        CU(cudaMalloc(&x->row_ids, size_t(x->capacity) * 8));
+        CU(cudaMemcpyAsync(x->row_ids, ident.data(), size_t(x->capacity) * 8, cudaMemcpyHostToDevice, x->wstream));
+        CU(cudaStreamSynchronize(x->wstream));
+    }
+    CU(cudaMemcpyAsync(x->row_ids + first_row, ids, size_t(n) * 8, cudaMemcpyHostToDevice, x->wstream));
+    CU(cudaStreamSynchronize(x->wstream));
     return MRAG_OK;
 }
 
@@ -614,28 +651,40 @@ static int run_scan_gemv(mrag_index* x, ScanArgs a, int nq, int grid, cudaStream
     return MRAG_OK;
 }
 
-static int mma_stages_for(int cap) {
-    const size_t fixed = mma_smem_bytes(0, cap);
+static int mma_stages_for(int cap, bool ksplit = false) {
+    const size_t fixed = mma_smem_bytes(0, cap, ksplit);
     if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return 0;
     return int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
 }
 
-template <int KREG, bool SO = false>
+// KS: the k-split pair kernel (rows of 769 .. 1536 elements): `grid` counts CTAs and is even, clusters of 2
+template <int KREG, bool SO = false, bool KS = false>
 static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        CU(cudaFuncSetAttribute((scan_mma_kernel<KREG, SO>), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute((scan_mma_kernel<KREG, SO, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set[dev] = true;
     }
     if (KREG > 0) a.cap = 0;                   // candidates live in registers: no shared-memory buffers
-    a.stages = mma_stages_for(a.cap);
-    const size_t smem = mma_smem_bytes(a.stages, a.cap);
+    a.stages = mma_stages_for(a.cap, KS);
+    if (a.stages < 4) return fail(MRAG_ERR_ARG, "scan_mma: candidate buffers of k = %d leave no room for the TMA ring", a.k);
+    const size_t smem = mma_smem_bytes(a.stages, a.cap, KS);
     for (int q0 = 0; q0 < nq; q0 += kMmaQueries) {
         a.q0 = q0;
         a.nq = std::min(kMmaQueries, nq - q0);
-        scan_mma_kernel<KREG, SO><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        if constexpr (KS) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kMmaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, scan_mma_kernel<KREG, SO, KS>, x->tmap, a));
+        } else {
+            scan_mma_kernel<KREG, SO, KS><<<grid, kMmaThreads, smem, s>>>(x->tmap, a);
+        }
         LAUNCHED();
     }
     return MRAG_OK;
@@ -645,6 +694,9 @@ static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStrea
 // are still candidates (short streams: small shards and the sampling pass), because all 32 queries
 // of a warp insert in lock step; on long streams the shared-memory buffers + a sampled bound win.
 static int run_scan_mma(mrag_index* x, const MmaArgs& a, int nq, int grid, bool reg_topk, cudaStream_t s) {
+    if (a.ld > kMmaMaxLd)
+        return (reg_topk && a.k <= kMmaRegK) ? launch_scan_mma<kMmaRegK, false, true>(x, a, nq, grid, s)
+                                             : launch_scan_mma<0, false, true>(x, a, nq, grid, s);
     return (reg_topk && a.k <= kMmaRegK) ? launch_scan_mma<kMmaRegK>(x, a, nq, grid, s)
                                          : launch_scan_mma<0>(x, a, nq, grid, s);
 }
@@ -1038,14 +1090,16 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     //           mma128 tcgen05 candidate generation, 128 queries per pass over bf16 rows / the bf16 shadow,
     //                  + exact rescoring with certificate (k <= 32)
     const bool can_mma = x->has_tmap && x->dtype == MRAG_BF16 && n > 0;
-    const bool can_mma128 = x->has_tmap && n > 0 && k <= kMma128MaxK;
+    const bool can_mma128 = x->has_tmap && ld <= kMmaMaxLd && n > 0 && k <= kMma128MaxK;
+    const bool ksplit = ld > kMmaMaxLd;                  // rows of 769 .. 1536 elements: k-split CTA pairs
+    const int mma_units = ksplit ? std::max(1, x->num_sms / 2) : x->num_sms;     // CTAs (pairs) that share the tiles
     // a single query also goes to the tensor-core scan (it streams faster than the CUDA-core kernel) unless a
     // filter is active: the CUDA-core scan skips masked rows one by one, the tensor-core scan only 64-row tiles
     bool use_mma = can_mma && (nq >= 2 || !(filter && filter->flags));
     bool use_mma128 = can_mma128 && (x->dtype == MRAG_BF16 ? nq > kMmaQueries : nq >= approx_min_nq());
     if (options & MRAG_OPT_FORCE_GEMV) use_mma = use_mma128 = false;
     if (options & MRAG_OPT_FORCE_MMA) {
-        if (!can_mma) return fail(MRAG_ERR_STATE, "mrag_search: the tensor-core scan needs a bf16 index with dim <= %d", kMmaMaxLd);
+        if (!can_mma) return fail(MRAG_ERR_STATE, "mrag_search: the tensor-core scan needs a bf16 index with dim <= %d", kMmaKsMaxLd);
         use_mma = true; use_mma128 = false;
     }
     if (options & MRAG_OPT_FORCE_MMA128) {
@@ -1065,7 +1119,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         t_last_kind = use_mma128 ? "mma128" : "gemv_shadow";
     }
     const int grid = use_mma
-        ? int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))))
+        ? int(std::max<int64_t>(1, std::min<int64_t>(mma_units, ceil_div(n, kMmaTileRows)))) * (ksplit ? 2 : 1)
         : int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
     if (rounds > 1 && w->ub.reserve(size_t(nq))) return MRAG_ERR_OOM;
     // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
@@ -1098,7 +1152,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 t_stats_ptr = w->stats.p;
             }
             const int64_t tiles = ceil_div(n, kMmaTileRows);
-            const bool sampled = tiles >= sample_min_tiles(x->num_sms);
+            const bool sampled = tiles >= sample_min_tiles(mma_units);
             if (sampled) {
                 // always the register top-k kernel: each CTA keeps the 16 best of a few tiles per query and
                 // the merge takes the k-th best of the union (k known rows reach it, so it is a valid bound;
@@ -1111,14 +1165,15 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 // a sample sits lower the larger k is (measured r1q, 10M rows, k = 100: 3 -> 12 tiles per CTA = -0.18 ms)
                 static const int per_cta_env = [] { const char* e = getenv("MRAG_SAMPLE_PER_CTA"); return (e && *e) ? atoi(e) : 0; }();
                 const int per_cta = per_cta_env > 0 ? per_cta_env :
-                    int(std::max<int64_t>(1, kr <= 64 ? std::min<int64_t>(4, ceil_div(tiles, 256 * int64_t(x->num_sms)))
-                                                      : std::min<int64_t>(12, ceil_div(tiles, 48 * int64_t(x->num_sms)))));
-                sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
-                const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
+                    int(std::max<int64_t>(1, kr <= 64 ? std::min<int64_t>(4, ceil_div(tiles, 256 * int64_t(mma_units)))
+                                                      : std::min<int64_t>(12, ceil_div(tiles, 48 * int64_t(mma_units)))));
+                sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * mma_units)));
+                const int sgrid = int(std::min<int64_t>(mma_units, ceil_div(tiles, sa.tile_mul))) * (ksplit ? 2 : 1);
                 sa.P = sgrid;
                 sa.k = std::min(kr, kMmaRegK);
                 sa.kp = kMmaRegK;
-                int rc = launch_scan_mma<kMmaRegK, true>(x, sa, nq, sgrid, s);     // scores only
+                int rc = ksplit ? launch_scan_mma<kMmaRegK, true, true>(x, sa, nq, sgrid, s)
+                                : launch_scan_mma<kMmaRegK, true>(x, sa, nq, sgrid, s);     // scores only
                 if (rc != MRAG_OK) return rc;
                 MergeArgs sm{};
                 sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kr; sm.lk = sa.k; sm.k_total = k; sm.k_off = k_off;
@@ -1128,7 +1183,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             }
             int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!sampled, s);
             if (rc != MRAG_OK) return rc;
-            t_last_kind = "mma";
+            t_last_kind = ksplit ? "mma_ks" : "mma";
         } else if (n > 0) {
             ScanArgs a{};
             a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p;
@@ -1157,6 +1212,10 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         t.scores = d_scores; t.rows = d_rows; t.counts = d_counts; t.row_base = x->row_base;
         t.need_tail = w->flags.p;
         nan_tail_kernel<<<nq, 256, 0, s>>>(t);
+        LAUNCHED();
+    }
+    if (x->row_ids && n > 0) {
+        remap_rows_kernel<<<unsigned(ceil_div(int64_t(nk), 256)), 256, 0, s>>>(d_rows, nk, x->row_ids, x->row_base);
         LAUNCHED();
     }
     if (!dev_io) {
@@ -1448,6 +1507,10 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (x->dtype == MRAG_BF16) cos_rows_kernel<1><<<cb, 256, 0, s>>>(ca);
         else cos_rows_kernel<0><<<cb, 256, 0, s>>>(ca);
         LAUNCHED();
+        if (x->row_ids) {
+            remap_rows_kernel<<<unsigned(ceil_div(int64_t(nk), 256)), 256, 0, s>>>(w->rows.p, nk, x->row_ids, x->row_base);
+            LAUNCHED();
+        }
     }
     CU(cudaMemcpyAsync(scores, w->scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(rows, w->rows.p, nk * 8, cudaMemcpyDeviceToHost, s));
@@ -1593,6 +1656,7 @@ extern "C" int mrag_save(mrag_index* x, const char* path, int64_t user_version) 
     memcpy(h.magic, "MRAGSNP1", 8);
     h.dim = x->dim; h.ld = x->ld; h.dtype = x->dtype; h.size = x->size; h.n_docs = x->n_docs; h.n_tag_docs = x->n_tag_docs;
     h.n_jtag_docs = x->n_jtag_docs; h.has_feat = x->feat ? 1 : 0; h.row_base = x->row_base; h.user_version = user_version;
+    h.reserved = x->row_ids ? 1 : 0;                       // explicit row ids follow the features
     if (fwrite(&h, sizeof h, 1, io.f) != 1) return fail(MRAG_ERR_ARG, "mrag_save: short write");
     const size_t n = size_t(x->size), words = (n + 31) / 32;
     if ((rc = io.put(x->rows, n * x->ld * elem_size(x->dtype))) || (rc = io.put(x->inv_norm, n * 4)) ||
@@ -1603,6 +1667,7 @@ extern "C" int mrag_save(mrag_index* x, const char* path, int64_t user_version) 
     if (x->n_tag_docs && (rc = io.put(x->doc_tags, size_t(x->n_tag_docs) * MRAG_TAG_WORDS * 8))) return rc;
     if (x->n_jtag_docs && (rc = io.put(x->doc_jtags, size_t(x->n_jtag_docs) * MRAG_JTAG_WORDS * 8))) return rc;
     if (x->feat && (rc = io.put(x->feat, n * sizeof(mrag_chunkfeat)))) return rc;
+    if (x->row_ids && (rc = io.put(x->row_ids, n * 8))) return rc;
     return MRAG_OK;
 }
 
@@ -1653,6 +1718,13 @@ extern "C" int mrag_load(mrag_index** out, const char* path, int device, int64_t
             cudaMemsetAsync(x->feat, 0, size_t(cap32) * sizeof(mrag_chunkfeat), x->wstream);
             rc = io.get(x->feat, n * sizeof(mrag_chunkfeat));
         }
+    }
+    if (rc == MRAG_OK && h.reserved == 1) {
+        std::vector<int64_t> ident(size_t(x->capacity));
+        for (int64_t i = 0; i < x->capacity; ++i) ident[size_t(i)] = i + h.row_base;
+        if (cudaMalloc(&x->row_ids, size_t(x->capacity) * 8) != cudaSuccess) rc = fail(MRAG_ERR_OOM, "mrag_load: row ids");
+        else if (cudaMemcpy(x->row_ids, ident.data(), size_t(x->capacity) * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_load: row ids");
+        else rc = io.get(x->row_ids, n * 8);
     }
     if (rc == MRAG_OK && x->shadow && n) {                   // the bf16 shadow is derived data: rebuilt, not stored
         const size_t count = n * size_t(h.ld);

@@ -24,6 +24,17 @@
 //               The two heavy warps sit alone on scheduler partitions 2 and 3 (warp % 4); the
 //               waiting roles share partitions 0 and 1.
 // Tiles whose 64 mask bits are all clear are skipped by every role (never loaded).
+//
+// KS = true ("k-split", rows of 769 .. 1536 elements, kind "mma_ks"): the queries of such rows need ld/2 > 384 tensor-
+// memory columns, so TWO CTAs of a thread-block cluster share every row tile along K: CTA c keeps the k-blocks
+// [c * ceil(kb/2), ...) of the 64 hi/lo queries in ITS tensor memory, streams only those columns of the tile (a TMA box
+// is a column block, so each corpus byte is still read once, by one CTA) and accumulates a PARTIAL dot product.  The
+// two CTAs alternate as "leader" tile by tile: the helper's hi warps add their hi + lo partials into a staging buffer
+// and ONE bulk copy (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the leader's mbarrier: 16 KB per
+// tile against 192 KB of corpus) moves the 64 x 64 sums into the leader's shared memory; the leader adds them to its
+// own partials and runs the select.  Each CTA thus selects every other tile of the pair and writes its own candidate
+// lists, exactly like a CTA of the one-CTA kernel.  (A first version stored the sums with st.shared::cluster and
+// signalled with release / acquire at cluster scope: MEMBAR.ALL.GPU + CCTL.IVALL per tile, 0.47 of the HBM rate.)
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
@@ -33,6 +44,11 @@ namespace mrag {
 
 #ifndef MRAG_SLEEP_REG
 #define MRAG_SLEEP_REG 1
+#endif
+#ifndef MRAG_QREADY_BAR
+// 1: the TMA producer starts streaming while the epilogue warps still load / split the queries into tensor memory; only
+// the MMA issuer waits for them (an mbarrier instead of a block-wide sync): hides the ring's fill behind the query load
+#define MRAG_QREADY_BAR 1
 #endif
 #ifndef MRAG_STAMPS
 // %globaltimer stamps of CTA 0's phases (tools/stats_probe.py).  OFF in the shipped build: merely
@@ -78,8 +94,10 @@ struct MmaArgs {
     unsigned long long* tstamps;   // optional [16] %globaltimer stamps of CTA 0 (debugging aid)
 };
 
-inline size_t mma_smem_bytes(int stages, int cap) {
+constexpr int kMmaKsMaxLd = 1536;         // k-split pair: two CTAs x 384 tensor-memory columns of queries
+inline size_t mma_smem_bytes(int stages, int cap, bool ksplit = false) {
     return 1024 /*align slack*/ + size_t(stages) * kMmaStageBytes + 2 * 64 * 64 * 4 /*exchange*/ +
+           (ksplit ? 2 * 64 * 64 * 4 + 2 * 64 * 4 : 0) /*partials received from / staged for the peer CTA; 1/|x| ring of 4*/ +
            2 * 64 * 4 /*1/|x| of the tile*/ + size_t(kMmaQueries) * cap * 8 + 1024 /*barriers*/;
 }
 
@@ -139,6 +157,33 @@ MRAG_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.releas
 MRAG_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 MRAG_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 MRAG_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- thread-block cluster helpers of the k-split variant
+MRAG_DEVINL uint32_t ks_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+MRAG_DEVINL void ks_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MRAG_DEVINL uint32_t ks_map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {      // shared::cluster address in a peer CTA
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+// plain remote arrive (the consumer-release of a multicast pipeline): tells the peer its send buffer may be reused
+MRAG_DEVINL void ks_arrive_remote(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+// bulk copy of `bytes` from this CTA's shared memory into a peer CTA's, completing on the PEER's mbarrier
+MRAG_DEVINL void ks_bulk_copy_to_peer(uint32_t dst_cluster_addr, const void* src, uint32_t bytes, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+                 "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
+                 : "memory");
+}
+MRAG_DEVINL void ks_bar_hi() { asm volatile("bar.sync 1, 64;" ::: "memory"); }      // the 64 threads of the two hi warps
 
 MRAG_DEVINL void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
     const uint64_t evict_first = 0x12F0000000000000ull;      // each corpus byte is used once
@@ -318,15 +363,17 @@ constexpr int kMmaRegK = 16;
 
 // SO (score only, KREG > 0): the sampling pass needs a bound, not rows: 32-bit orderable scores in the
 //           registers (half the insertion work); the lists it writes carry synthetic unique low words.
-template <int KREG, bool SO = false>
+template <int KREG, bool SO = false, bool KS = false>
 __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     // SWIZZLE_128B tiles need 1024-byte alignment; stay in the shared address space (no integer casts)
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                            // stages * 8 KB
     float* xbuf = reinterpret_cast<float*>(smem + size_t(a.stages) * kMmaStageBytes);   // [2][64 rows][64 queries] lo parts
-    float* xinv = xbuf + 2 * 64 * 64;                                            // [2][64 rows] 1/|x|, NaN = masked row
-    uint64_t* cand = reinterpret_cast<uint64_t*>(xinv + 2 * 64);                 // [64 queries][cap]
+    float* ybuf = xbuf + 2 * 64 * 64;                                            // KS: [64 rows][64 queries] partial dots received from the peer CTA,
+    float* sbuf = ybuf + 64 * 64;                                                //     followed by the staging buffer of the partials this CTA sends
+    float* xinv = ybuf + (KS ? 2 * 64 * 64 : 0);                                 // [2][64 rows] 1/|x|, NaN = masked row
+    uint64_t* cand = reinterpret_cast<uint64_t*>(xinv + (KS ? 4 : 2) * 64);      // [64 queries][cap]   (KS: 1/|x| ring of 4 tiles)
     uint64_t* bars = cand + size_t(kMmaQueries) * a.cap;
     uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
     uint64_t* empty_bar = full_bar + a.stages;       // [stages]   MMA -> TMA
@@ -334,7 +381,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
     uint64_t* xfull_bar = tempty_bar + 2;            // [2]        lo warps -> hi warps
     uint64_t* xempty_bar = xfull_bar + 2;            // [2]        hi warps -> lo warps
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xempty_bar + 2);
+    uint64_t* yfull_bar = xempty_bar + 2;            // [1]  KS:   the peer's bulk copy has landed in ybuf (expect_tx by me + complete_tx)
+    uint64_t* yempty_bar = yfull_bar + 2;            // [1]  KS:   the peer has consumed what I sent (its hi warps arrive here)
+    uint64_t* qready_bar = yempty_bar + 2;           // [1]        the queries are in tensor memory (epilogue warps -> MMA issuer)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(qready_bar + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t slp = a.sleep_ns;
@@ -346,14 +396,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     auto stamp = [&](int) {};
 #endif
     if (tid == 0) stamp(0);
-    const int kblocks = a.ld / kMmaKBlock;
+    // KS: this CTA's share of the k-blocks (the pair splits every row tile along K)
+    const uint32_t ks_rank = KS ? ks_cluster_rank() : 0u;
+    const int all_kblocks = a.ld / kMmaKBlock;
+    const int kb0 = KS ? (ks_rank ? (all_kblocks + 1) / 2 : 0) : 0;
+    const int kblocks = KS ? (ks_rank ? all_kblocks / 2 : (all_kblocks + 1) / 2) : all_kblocks;
     const int64_t all_tiles = (a.n + kMmaTileRows - 1) / kMmaTileRows;
     const int64_t nwords = (a.n + 31) >> 5;
-    // tile index space of this launch: t = 0, tile_mul, 2*tile_mul, ...; CTA b takes every gridDim-th of them
+    // tile index space of this launch: t = 0, tile_mul, 2*tile_mul, ...; CTA b (KS: pair b) takes every gridDim-th of them
     const int64_t tmul = a.tile_mul;
     const int64_t num_tiles = all_tiles;
-    const int64_t G = int64_t(gridDim.x) * tmul;
-    const int64_t t_first = int64_t(blockIdx.x) * tmul;
+    const int64_t G = int64_t(KS ? gridDim.x / 2 : gridDim.x) * tmul;
+    const int64_t t_first = int64_t(KS ? blockIdx.x / 2 : blockIdx.x) * tmul;
 
     // 64 mask bits of tile t (zero past the end); every role skips a tile whose bits are all clear
     auto tile_mask = [&](int64_t t) -> uint2 {
@@ -372,13 +426,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             mbar_init(&tempty_bar[i], 128);
             mbar_init(&xfull_bar[i], 64);
             mbar_init(&xempty_bar[i], 64);
+            if constexpr (KS) { mbar_init(&yfull_bar[i], 1); mbar_init(&yempty_bar[i], 2); }   // [0] used; yempty: one arrival per peer hi warp
         }
+        mbar_init(qready_bar, 128);
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_holder, kMmaTmemCols);
     tc_fence_before();
     __syncthreads();
+    if constexpr (KS) ks_cluster_sync();               // the peer's barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     if (tid == 0) stamp(1);
@@ -392,8 +449,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     if (warp >= 2) {
         const bool live = qi < nq_eff;
         const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
-        const float* qrow = a.q + size_t(qsrc) * a.ld;
-        for (int c0 = 0; c0 < a.ld / 2; c0 += 32) {         // 32 columns = 64 elements per store
+        const float* qrow = a.q + size_t(qsrc) * a.ld + size_t(kb0) * kMmaKBlock;
+        for (int c0 = 0; c0 < kblocks * (kMmaKBlock / 2); c0 += 32) {     // 32 columns = 64 elements per store
             uint32_t r[32];
 #pragma unroll
             for (int v = 0; v < 16; ++v) {
@@ -411,10 +468,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
             MRAG_TMEM_ST32(taddr, r);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#if MRAG_QREADY_BAR
+        tc_fence_before();
+        mbar_arrive(qready_bar);
+#endif
     }
+#if !MRAG_QREADY_BAR
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#endif
     if (tid == 0) stamp(2);
 
     if (warp == 0) {
@@ -429,7 +492,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                     mbar_wait(&empty_bar[s], ph ^ 1u, slp);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], kMmaStageBytes);
-                        tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, kb * kMmaKBlock, int(t * kMmaTileRows),
+                        tma_load_2d(stage_base + size_t(s) * kMmaStageBytes, &tmap, (kb0 + kb) * kMmaKBlock, int(t * kMmaTileRows),
                                     &full_bar[s]);
                     }
                     __syncwarp();
@@ -446,6 +509,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         if (elect_one()) {
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
+#if MRAG_QREADY_BAR
+            mbar_wait(qready_bar, 0u, slp);
+            tc_fence_after();
+#endif
             const uint64_t bdesc0 = make_sw128_desc(smem_u32(stage_base));
             uint2 m = tile_mask(t_first);
             for (int64_t t = t_first; t < num_tiles; t += G) {
@@ -480,6 +547,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         int as = 0, xs = 0;
         uint32_t aph = 0, xph = 0;
+        [[maybe_unused]] uint32_t vs = 0;                   // KS: slot of the 1/|x| ring (4 tiles: the leader keeps reading it after it released xbuf)
         uint2 m = tile_mask(t_first);
         for (int64_t t = t_first; t < num_tiles; t += G) {
             const uint2 mn = tile_mask(t + G);
@@ -505,9 +573,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
 #pragma unroll
                 for (int c = 0; c < 64; ++c) xb[c * 64 + qi] = __uint_as_float(d[c]);
                 if (quarter == 0) {
-                    xinv[xs * 64 + lane] = in0;
-                    xinv[xs * 64 + 32 + lane] = in1;
+                    const int vslot = KS ? int(vs) : xs;
+                    xinv[vslot * 64 + lane] = in0;
+                    xinv[vslot * 64 + 32 + lane] = in1;
                 }
+                if constexpr (KS) vs = (vs + 1u) & 3u;
                 mbar_arrive(&xfull_bar[xs]);
                 if (++xs == 2) { xs = 0; xph ^= 1u; }
             }
@@ -547,12 +617,51 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         // admits s >= g, i.e. s > prev(g).  Read relaxed once per tile, raised after each compaction.
         uint32_t* gslot = a.gthr + qsrc;
         unsigned long long n_tiles = 0, n_slow = 0, n_keys = 0, n_compact = 0, n_retry = 0;
+        uint32_t it = 0;                                         // KS: tiles this pair has processed (leader = it & 1)
 
         uint2 m = tile_mask(t_first);
         for (int64_t t = t_first; t < num_tiles; t += G) {
             const uint2 mn = tile_mask(t + G);
             if ((m.x | m.y) != 0u) {
                 const int64_t r0 = t * kMmaTileRows;
+                // KS: this CTA sends (helper) or receives (leader) its (it / 2)-th partial
+                const uint32_t yj = it >> 1;
+                if constexpr (KS) {
+                    if ((it & 1u) != ks_rank) {
+                        // ---- helper of this tile: hi + lo partials of my k-blocks -> staging buffer -> the leader's shared memory
+                        mbar_wait(&tfull_bar[as], aph, slp);
+                        tc_fence_after();
+                        mbar_wait(&xfull_bar[xs], xph, slp);
+                        const float* xb = xbuf + size_t(xs) * 64 * 64;
+                        float part[64];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t d[32];
+                            MRAG_TMEM_LD32(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows + h * 32));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) part[h * 32 + c] = __uint_as_float(d[c]) + xb[(h * 32 + c) * 64 + qi];
+                        }
+                        // the accumulator and the exchange slot go back BEFORE anything that depends on the peer
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[as]);
+                        if (++as == 2) { as = 0; aph ^= 1u; }
+                        mbar_arrive(&xempty_bar[xs]);
+                        if (++xs == 2) { xs = 0; xph ^= 1u; }
+                        if (yj > 0) mbar_wait(&yempty_bar[0], (yj - 1u) & 1u, slp);      // the leader has consumed my previous send: sbuf and its ybuf are free
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) sbuf[c * 64 + qi] = part[c];
+                        fence_proxy_async();                                     // my stores -> visible to the bulk copy engine
+                        ks_bar_hi();
+                        if (warp == 2 && lane == 0)
+                            ks_bulk_copy_to_peer(ks_map_to_cta(smem_u32(ybuf), ks_rank ^ 1u), sbuf, 64 * 64 * 4,
+                                                 ks_map_to_cta(smem_u32(&yfull_bar[0]), ks_rank ^ 1u));
+                        ++it;
+                        m = mn;
+                        continue;
+                    }
+                    if (warp == 2 && lane == 0) mbar_expect_tx(&yfull_bar[0], 64 * 64 * 4);       // leader: the peer's partials of this tile
+                }
                 float sc[64];
                 float bestg[8];                                      // max of each group of 8 rows
 #pragma unroll
@@ -562,6 +671,42 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 mbar_wait(&tfull_bar[as], aph, slp);
                 tc_fence_after();
                 mbar_wait(&xfull_bar[xs], xph, slp);
+                if constexpr (KS) {
+                    // ---- leader of this tile.  Phase 1: my own hi + lo partials into registers, then the accumulator and
+                    //      the exchange slot go back at once -- the MMA pipeline must not wait for the peer
+                    const float* xb = xbuf + size_t(xs) * 64 * 64;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t d[32];
+                        MRAG_TMEM_LD32(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows + h * 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) sc[h * 32 + c] = __uint_as_float(d[c]) + xb[(h * 32 + c) * 64 + qi];
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                    if (++as == 2) { as = 0; aph ^= 1u; }
+                    mbar_arrive(&xempty_bar[xs]);
+                    // ---- phase 2: the peer's partials of this tile (its k-blocks), 1/|x| from the 4-deep ring
+                    mbar_wait(&yfull_bar[0], yj & 1u, slp);
+                    if (warp_live) {
+                        const float4* inv4 = reinterpret_cast<const float4*>(xinv + (it & 3u) * 64);
+#pragma unroll
+                        for (int c4 = 0; c4 < 16; ++c4) {
+                            const float4 iv = inv4[c4];                          // broadcast
+                            const float ivv[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = c4 * 4 + i;
+                                sc[c] = (sc[c] + ybuf[c * 64 + qi]) * ivv[i] * qinv;
+                                bestg[c >> 3] = fmaxf(bestg[c >> 3], sc[c]);     // fmaxf drops NaN
+                            }
+                        }
+                    }
+                    __syncwarp();                                   // every lane has consumed its column of ybuf
+                    if (lane == 0) ks_arrive_remote(ks_map_to_cta(smem_u32(&yempty_bar[0]), ks_rank ^ 1u));
+                    ++it;
+                } else {
                 if (warp_live) {
                     const float* xb = xbuf + size_t(xs) * 64 * 64;
                     const float4* inv4 = reinterpret_cast<const float4*>(xinv + xs * 64);
@@ -589,8 +734,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);
                 if (++as == 2) { as = 0; aph ^= 1u; }
+                }
                 if (warp_live) {
-                    mbar_arrive(&xempty_bar[xs]);
+                    if constexpr (!KS) mbar_arrive(&xempty_bar[xs]);
                     // ---- rows arrive in increasing order, so a later row never beats an equal score:
                     //      only scores strictly above the threshold can enter
                     float thr = fmaxf(st.thr_s, gord ? ord2f(gord - 1u) : -CUDART_INF_F);
@@ -657,7 +803,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                         }
                     }
                 } else {
-                    mbar_arrive(&xempty_bar[xs]);
+                    if constexpr (!KS) mbar_arrive(&xempty_bar[xs]);
                 }
                 if (++xs == 2) { xs = 0; xph ^= 1u; }
             }
@@ -724,6 +870,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     if (warp == 2) stamp(7);
     tc_fence_before();
     __syncthreads();
+    if constexpr (KS) ks_cluster_sync();               // nobody leaves while the peer may still store into this CTA
     if (tid == 0) stamp(8);
     if (warp == 1) {
         tc_fence_after();

@@ -1,0 +1,212 @@
+"""MultiIndex: several row shards of ONE table owned by ONE process (a FastAPI worker that holds all GPUs of a box).
+
+The SPMD path (sharded.ShardedSearcher, one process per GPU under torchrun) is what the benchmark scales; the
+reference's callers, however, are a single Python process that calls ``store.asearch(...)`` / ``_vector_arm(...)``
+(vector_store.py:181-226, corpus_search.py:1427-1438).  This class gives that process the same row-sharded scan:
+
+  * every shard is an ``Index`` (its own ``mrag_index`` handle, device, streams);  ``devices`` may name a GPU more
+    than once (two shards on one GPU), which is how the 1-GPU test box exercises the code;
+  * a DOCUMENT lives on one shard (doc_idx filters and tombstones stay local); new documents go to the shard with
+    the fewest rows;
+  * a row's id is its position in the host table (``mrag_set_row_ids``), so the k-way merge of the shards' lists
+    (``mrag_merge_topk``: score DESC, NaN last, id ASC) returns exactly what one unsharded index would;
+  * one search = the queries copied to every device, ``mrag_search`` enqueued on one stream per shard (all GPUs
+    scan concurrently, nothing blocks the host until the end), the per-shard lists peer-copied to the first
+    device, the K4 merge kernel there, one device-to-host copy.
+
+torch is plumbing here (device buffers, streams, peer copies); every kernel is libmrag.so's.
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import _native as N
+from .index import Filter, Index, merge_topk
+
+
+class MultiIndex:
+    def __init__(self, dim: int, dtype: str | int, devices: Sequence[int], capacity: int):
+        if not devices:
+            raise ValueError("MultiIndex needs at least one device")
+        self.devices = [int(d) for d in devices]
+        s = len(self.devices)
+        per = (int(capacity) * 11 // 10 + s - 1) // s + 1024           # least-loaded routing keeps shards within a document of each other
+        self.shards = [Index(dim, dtype, d, per) for d in self.devices]
+        self.dim, self.dtype, self.device, self.capacity = int(dim), self.shards[0].dtype, self.devices[0], int(capacity)
+        self._n = 0
+        self.pos_shard = np.zeros(1024, dtype=np.uint8)                 # host position -> shard
+        self.pos_local = np.zeros(1024, dtype=np.int64)                 # host position -> row inside that shard
+        self.doc_home: dict[int, int] = {}                              # doc_idx -> shard
+        self._last_kind = "none"
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        for ix in self.shards:
+            ix.close()
+
+    def __len__(self) -> int:
+        return self._n
+
+    def shard_sizes(self) -> list[int]:
+        return [len(ix) for ix in self.shards]
+
+    # -- write side --------------------------------------------------------------------------
+    def append(self, X: np.ndarray, meta: np.ndarray | None = None) -> int:
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        n = X.shape[0]
+        first = self._n
+        if n == 0:
+            return first
+        if meta is None:
+            from .index import make_meta
+            meta = make_meta(n, doc_idx=np.arange(first, first + n, dtype=np.uint32))
+        docs = np.asarray(meta["doc_idx"], dtype=np.int64)
+        sizes = self.shard_sizes()
+        target = np.empty(n, dtype=np.int64)
+        uniq, inv, counts = np.unique(docs, return_inverse=True, return_counts=True)
+        home = np.empty(uniq.shape[0], dtype=np.int64)
+        for j in np.argsort(np.unique(docs, return_index=True)[1]):   # documents in order of first appearance
+            d = int(uniq[j])
+            s = self.doc_home.get(d)
+            if s is None:
+                s = int(np.argmin(sizes))
+                self.doc_home[d] = s
+            sizes[s] += int(counts[j])
+            home[j] = s
+        target = home[inv]
+        need = first + n
+        if need > self.pos_shard.shape[0]:
+            cap = max(need, 2 * self.pos_shard.shape[0])
+            self.pos_shard = np.concatenate([self.pos_shard, np.zeros(cap - self.pos_shard.shape[0], dtype=np.uint8)])
+            self.pos_local = np.concatenate([self.pos_local, np.zeros(cap - self.pos_local.shape[0], dtype=np.int64)])
+        for s, ix in enumerate(self.shards):
+            sel = np.flatnonzero(target == s)
+            if sel.size == 0:
+                continue
+            base = len(ix)
+            ids = (first + sel).astype(np.int64)
+            N.check(ix._lib.mrag_set_row_ids(ix._h, base, ids.ctypes.data, ids.shape[0]))    # ids first: rows become searchable with ids in place
+            got = ix.append(X[sel], np.ascontiguousarray(meta[sel]))
+            assert got == base
+            self.pos_shard[first + sel] = s
+            self.pos_local[first + sel] = base + np.arange(sel.size)
+        self._n = need
+        return first
+
+    def set_doc_tags(self, first_doc: int, bits: np.ndarray) -> None:
+        for ix in self.shards:                                         # the per-document tables are small: every shard holds all of them
+            ix.set_doc_tags(first_doc, bits)
+
+    def set_doc_jtags(self, first_doc: int, bits: np.ndarray) -> None:
+        for ix in self.shards:
+            ix.set_doc_jtags(first_doc, bits)
+
+    def set_chunk_features(self, first_row: int, feat: np.ndarray) -> None:
+        n = feat.shape[0]
+        sh, lo = self.pos_shard[first_row:first_row + n], self.pos_local[first_row:first_row + n]
+        for s, ix in enumerate(self.shards):
+            sel = np.flatnonzero(sh == s)
+            if sel.size == 0:
+                continue
+            loc = lo[sel]
+            # rows of one shard inside a host range are consecutive there as well (both orders are append order)
+            assert (np.diff(loc) == 1).all()
+            ix.set_chunk_features(int(loc[0]), np.ascontiguousarray(feat[sel]))
+
+    def tombstone_doc(self, doc_idx: int) -> int:
+        s = self.doc_home.get(int(doc_idx))
+        if s is None:
+            return 0
+        return self.shards[s].tombstone_doc(doc_idx)
+
+    # -- read side ---------------------------------------------------------------------------
+    def search(self, Q: np.ndarray, k: int, flt: Filter | None = None, options: int = 0):
+        """Host-buffer search over all shards.  Returns (scores f32 [nq,k], ids i64 [nq,k], counts i32 [nq])."""
+        import torch
+        Q = np.ascontiguousarray(np.atleast_2d(np.asarray(Q, dtype=np.float32)))
+        if Q.shape[1] != self.dim:
+            raise ValueError(f"query dim {Q.shape[1]} != index dim {self.dim}")
+        nq, k, S = Q.shape[0], int(k), len(self.shards)
+        options = int(options) & ~N.OPT_COALESCE                        # coalescing is per handle; the fan-out has its own batching
+        Qh = torch.from_numpy(Q)
+        dev0 = torch.device(f"cuda:{self.devices[0]}")
+        parts, events = [], []
+        for ix in self.shards:
+            dev = torch.device(f"cuda:{ix.device}")
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.device(dev), torch.cuda.stream(st):
+                qd = Qh.to(dev, non_blocking=False)
+                out = ix.search_device(qd, k, flt, sync=False, options=options)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            parts.append(out)
+            events.append(ev)
+        self._last_kind = self.shards[0].last_scan_kind()
+        with torch.cuda.device(dev0):
+            st0 = torch.cuda.Stream(device=dev0)
+            with torch.cuda.stream(st0):
+                for ev in events:
+                    st0.wait_event(ev)
+                sc = torch.empty((S, nq, k), dtype=torch.float32, device=dev0)
+                ro = torch.empty((S, nq, k), dtype=torch.int64, device=dev0)
+                co = torch.empty((S, nq), dtype=torch.int32, device=dev0)
+                for s, (a, b, c) in enumerate(parts):                  # peer copies (device-to-device over NVLink)
+                    sc[s].copy_(a, non_blocking=True)
+                    ro[s].copy_(b, non_blocking=True)
+                    co[s].copy_(c, non_blocking=True)
+                if S * k <= 16384:
+                    m = merge_topk(self.devices[0], sc, ro, co, S, nq, k, (nq * k, nq * k, nq))
+                else:                                                  # very wide LIMITs: merge pairwise
+                    m = (sc[0], ro[0], co[0])
+                    for s in range(1, S):
+                        a = torch.stack([m[0], sc[s]]).contiguous()
+                        b = torch.stack([m[1], ro[s]]).contiguous()
+                        c = torch.stack([m[2], co[s]]).contiguous()
+                        m = merge_topk(self.devices[0], a, b, c, 2, nq, k, (nq * k, nq * k, nq))
+                res = tuple(t.cpu() for t in m)
+            st0.synchronize()
+        for (a, b, c) in parts:
+            del a, b, c
+        return res[0].numpy(), res[1].numpy(), res[2].numpy()
+
+    def last_scan_kind(self) -> str:
+        return self._last_kind
+
+    def last_kernel_ms(self, what: int) -> float:
+        return float("nan")
+
+    # -- host position <-> shard rows --------------------------------------------------------
+    def locate(self, rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        rows = np.asarray(rows, dtype=np.int64)
+        return self.pos_shard[rows], self.pos_local[rows]
+
+    # -- snapshot ----------------------------------------------------------------------------
+    def save(self, path: str, version: int = 0) -> None:
+        for s, ix in enumerate(self.shards):
+            ix.save(f"{path}.{s}", version)
+        np.savez(path + ".routing.npz", pos_shard=self.pos_shard[:self._n], pos_local=self.pos_local[:self._n],
+                 doc_home=np.asarray(sorted(self.doc_home.items()), dtype=np.int64).reshape(-1, 2), n=np.int64(self._n))
+
+    @classmethod
+    def load(cls, path: str, devices: Sequence[int], capacity: int = 0) -> tuple["MultiIndex", int]:
+        self = cls.__new__(cls)
+        self.devices = [int(d) for d in devices]
+        z = np.load(path + ".routing.npz")
+        self._n = int(z["n"])
+        self.pos_shard, self.pos_local = z["pos_shard"].copy(), z["pos_local"].copy()
+        self.doc_home = {int(a): int(b) for a, b in z["doc_home"]}
+        s = len(self.devices)
+        per = 0 if capacity <= 0 else (int(capacity) * 11 // 10 + s - 1) // s + 1024
+        self.shards, ver = [], 0
+        for i, d in enumerate(self.devices):
+            if not os.path.exists(f"{path}.{i}"):
+                raise ValueError(f"snapshot has no shard {i}: it was written with fewer shards")
+            ix, ver = Index.load(f"{path}.{i}", d, per)
+            self.shards.append(ix)
+        self.dim, self.dtype, self.device = self.shards[0].dim, self.shards[0].dtype, self.devices[0]
+        self.capacity = sum(ix.capacity for ix in self.shards)
+        self._last_kind = "none"
+        return self, ver

@@ -1,17 +1,27 @@
 """PublishedTable: the host-side half of ``rag_published_embeddings`` + ``document_tags``.
 
-The GPU index (Index) holds the vectors and the coded filter columns; this object holds what
-the reference hydrates from the same SELECT (`_BM25_COLS`, corpus_search.py:621-640): ids,
-text, page numbers, tags -- plus the string->code vocabularies and the document_id -> doc_idx map.
+The GPU index (Index, or MultiIndex when one process owns several shards) holds the vectors and the coded filter
+columns; this object holds what the reference hydrates from the same SELECT (`_BM25_COLS`,
+corpus_search.py:621-640): ids, text, page numbers, tags -- as COLUMNS (columns.py: numpy buffers, no per-row Python
+objects, snapshot = ``np.savez``) -- plus the string->code vocabularies and the document_id -> doc_idx map.
+
+Write paths (publish.py:204-362, embedding_worker.py:229-266):
+  insert(rows, embeddings)        row dicts, as the worker's batches of 50 arrive
+  insert_columns(X, columns)      bulk: an [n, dim] array + one sequence per column (a loader's path for 10M+ rows)
+Rows become visible to searches only AFTER their host columns exist (the host columns are appended first, the device
+rows second), so a concurrent search can never return a row it cannot hydrate.
 """
 from __future__ import annotations
 
+import json
+import os
 import threading
 from typing import Any, Sequence
 
 import numpy as np
 
 from . import _native as N
+from .columns import CodeCol, IntCol, JsonCol, StrCol
 from .index import Filter, Index, make_meta
 from .vocab import Vocab
 
@@ -27,42 +37,78 @@ HYDRATE_COLS = (
     "text", "page_number", "paragraph_index", "section_path", "chapter_path", "summary", "content_sha",
     "document_display_name", "document_filename", "chunk_d_tags", "chunk_p_tags", "chunk_j_tags",
 )
+_INT_COLS = ("page_number", "paragraph_index")
+_JSON_COLS = ("chunk_d_tags", "chunk_p_tags", "chunk_j_tags")
+_CODED = (("source_type", "source_type", np.uint8), ("document_payer", "payer", np.uint16), ("document_state", "state", np.uint8),
+          ("document_program", "program", np.uint8), ("document_authority_level", "authority", np.uint8))
 
 
 def to_float4(emb: Sequence[float]) -> np.ndarray:
     """The stored / queried numeric format: text repr(float(x)) parsed by pgvector's strtof
     (embedding_worker.py:53-62, vector_store.py:272) == np.float32(python float)."""
-    return np.asarray([float(x) for x in emb], dtype=np.float64).astype(np.float32)
+    return np.asarray(emb, dtype=np.float64).astype(np.float32)
+
+
+class _DocIdCol:
+    """``document_id`` of a row = the id string of its document (rows store the dense doc index)."""
+
+    def __init__(self, table: "PublishedTable"):
+        self.t = table
+
+    def __len__(self) -> int:
+        return self.t._n
+
+    def __getitem__(self, i: int) -> str:
+        i = int(i)
+        if i < 0:
+            i += self.t._n
+        if not 0 <= i < self.t._n:
+            raise IndexError(i)
+        return self.t.doc_ids[int(self.t.row_doc[i])]
 
 
 class PublishedTable:
-    def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 1 << 20):
-        self.index = Index(dim, dtype, device, capacity)
-        self.vocab = Vocab()
+    def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 1 << 20,
+                 devices: Sequence[int] | None = None):
+        """``devices``: GPUs that share the rows (one shard each; a device may be named twice).  None = one shard on
+        ``device``."""
+        if devices is not None and len(devices) > 1:
+            from .multi import MultiIndex
+            self.index = MultiIndex(dim, dtype, devices, capacity)
+        else:
+            self.index = Index(dim, dtype, device if devices is None else devices[0], capacity)
+        self._init_host(Vocab())
+
+    def _init_host(self, vocab: Vocab) -> None:
+        self.vocab = vocab
         self.lock = threading.RLock()
-        self.id: list[str] = []
-        self.document_id: list[str] = []
-        self.source_type: list[str | None] = []
-        self.source_id: list[str | None] = []
-        self.document_payer: list[str | None] = []
-        self.document_state: list[str | None] = []
-        self.document_program: list[str | None] = []
-        self.document_authority_level: list[str | None] = []
-        self.extra: dict[str, list] = {c: [] for c in HYDRATE_COLS}
-        self.doc_idx: dict[str, int] = {}
-        self._next_doc = 0          # doc_idx values are never reused (tombstoned rows keep theirs)
+        self._n = 0                                  # rows whose host columns AND device rows exist
+        self.id = StrCol()
+        self.source_id = StrCol()
+        self.row_doc = np.zeros(1024, dtype=np.uint32)
+        self.document_id = _DocIdCol(self)
+        v = vocab
+        self.source_type = CodeCol(v.source_type.values, v.source_type.none_code, np.uint8)
+        self.document_payer = CodeCol(v.payer.values, v.payer.none_code, np.uint16)
+        self.document_state = CodeCol(v.state.values, v.state.none_code, np.uint8)
+        self.document_program = CodeCol(v.program.values, v.program.none_code, np.uint8)
+        self.document_authority_level = CodeCol(v.authority.values, v.authority.none_code, np.uint8)
+        self.extra: dict[str, Any] = {c: (IntCol() if c in _INT_COLS else JsonCol() if c in _JSON_COLS else StrCol())
+                                      for c in HYDRATE_COLS}
+        self.doc_idx: dict[str, int] = {}            # live document_id -> doc index
+        self.doc_ids: list[str] = []                 # doc index -> document_id (indices are never reused)
         self.doc_d_tags: dict[str, set] = {}
         self.doc_p_tags: dict[str, set] = {}
 
     def __len__(self) -> int:
-        return len(self.id)
+        return self._n
 
     # -- write side (publish.py:204-362 / embedding_worker.py:229-266) -------------------------
     def _doc(self, document_id: str) -> int:
         d = self.doc_idx.get(document_id)
         if d is None:
-            d = self._next_doc
-            self._next_doc += 1
+            d = len(self.doc_ids)
+            self.doc_ids.append(document_id)
             self.doc_idx[document_id] = d
         return d
 
@@ -74,41 +120,77 @@ class PublishedTable:
         if len(embeddings) != n:
             raise ValueError("rows / embeddings length mismatch")
         dim = self.index.dim
-        X = np.zeros((n, dim), dtype=np.float32)
-        valid = np.ones(n, dtype=np.uint8)
-        for i, e in enumerate(embeddings):
-            if e is None:
-                valid[i] = 0
-                continue
-            v = to_float4(e)
-            if v.shape[0] != dim:
-                raise ValueError(f"expected {dim} dimensions, not {v.shape[0]}")   # pgvector's error text
-            X[i] = v
+        valid = np.fromiter((e is not None for e in embeddings), dtype=np.uint8, count=n)
+        try:
+            if valid.all():
+                X = to_float4(embeddings)
+            else:
+                X = np.zeros((n, dim), dtype=np.float32)
+                for i, e in enumerate(embeddings):
+                    if e is not None:
+                        v = to_float4(e)
+                        if v.ndim != 1 or v.shape[0] != dim:
+                            raise ValueError(f"expected {dim} dimensions, not {v.shape[0] if v.ndim == 1 else v.shape}")
+                        X[i] = v
+        except ValueError as exc:
+            if "inhomogeneous" in str(exc):
+                raise ValueError(f"expected {dim} dimensions for every embedding") from None
+            raise
+        if X.ndim != 2 or X.shape[1] != dim:
+            raise ValueError(f"expected {dim} dimensions, not {X.shape[1] if X.ndim == 2 else X.shape}")   # pgvector's error text
+        cols = {name: [r.get(name) for r in rows] for name in
+                ("id", "document_id", "source_type", "source_id", "document_payer", "document_state", "document_program",
+                 "document_authority_level", *HYDRATE_COLS)}
+        self.insert_columns(X, cols, valid)
+
+    def insert_columns(self, X: np.ndarray, columns: dict[str, Sequence], valid: np.ndarray | None = None) -> int:
+        """Bulk INSERT: X float32 [n, dim] (rows with valid[i] == 0 have no vector), ``columns`` one sequence per
+        column name (``id`` and ``document_id`` required; missing columns are NULL).  Returns the first new row."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        n = X.shape[0]
+        if n == 0:
+            return self._n
+        if X.ndim != 2 or X.shape[1] != self.index.dim:
+            raise ValueError(f"expected {self.index.dim} dimensions, not {X.shape[1] if X.ndim == 2 else X.shape}")
+        for name in ("id", "document_id"):
+            if name not in columns or len(columns[name]) != n:
+                raise ValueError(f"column {name!r} is required, one value per row")
+        none = [None] * n
         with self.lock:
             v = self.vocab
-            meta = make_meta(
-                n,
-                doc_idx=[self._doc(str(r["document_id"])) for r in rows],
-                payer=[v.payer.encode(r.get("document_payer")) for r in rows],
-                state=[v.state.encode(r.get("document_state")) for r in rows],
-                program=[v.program.encode(r.get("document_program")) for r in rows],
-                authority=[v.authority.encode(r.get("document_authority_level")) for r in rows],
-                source_type=[v.source_type.encode(r.get("source_type")) for r in rows],
-                valid=valid,
-            )
-            first = self.index.append(X, meta)
-            assert first == len(self.id), "host table and device index out of step"
-            for r in rows:
-                self.id.append(str(r["id"]))
-                self.document_id.append(str(r["document_id"]))
-                self.source_type.append(r.get("source_type"))
-                self.source_id.append(None if r.get("source_id") is None else str(r.get("source_id")))
-                self.document_payer.append(r.get("document_payer"))
-                self.document_state.append(r.get("document_state"))
-                self.document_program.append(r.get("document_program"))
-                self.document_authority_level.append(r.get("document_authority_level"))
-                for c in HYDRATE_COLS:
-                    self.extra[c].append(r.get(c))
+            first = self._n
+            docs = np.fromiter((self._doc(str(d)) for d in columns["document_id"]), dtype=np.uint32, count=n)
+            codes = {}
+            for col, vname, dt in _CODED:
+                voc = getattr(v, vname)
+                codes[col] = np.fromiter((voc.encode(x) for x in columns.get(col, none)), dtype=dt, count=n)
+            meta = make_meta(n, doc_idx=docs, payer=codes["document_payer"], state=codes["document_state"],
+                             program=codes["document_program"], authority=codes["document_authority_level"],
+                             source_type=codes["source_type"], valid=np.ones(n, np.uint8) if valid is None else valid)
+            # 1. host columns first ...
+            self.id.extend(str(x) for x in columns["id"])
+            self.source_id.extend(None if x is None else str(x) for x in columns.get("source_id", none))
+            if first + n > self.row_doc.shape[0]:
+                self.row_doc = np.concatenate([self.row_doc, np.zeros(max(first + n, self.row_doc.shape[0]), dtype=np.uint32)])
+            self.row_doc[first:first + n] = docs
+            for col, _, _ in _CODED:
+                getattr(self, col).extend(codes[col])
+            for c in HYDRATE_COLS:
+                self.extra[c].extend(columns.get(c, none))
+            # 2. ... then the device rows: from here on a search may return them
+            try:
+                got = self.index.append(X, meta)
+            except Exception:
+                self._truncate(first)
+                raise
+            assert got == first, "host table and device index out of step"
+            self._n = first + n
+            return first
+
+    def _truncate(self, n: int) -> None:
+        for col in (self.id, self.source_id, self.source_type, self.document_payer, self.document_state,
+                    self.document_program, self.document_authority_level, *self.extra.values()):
+            col.truncate(n)
 
     def set_document_tags(self, document_id: str, d_tags: Sequence[str] | None, p_tags: Sequence[str] | None) -> None:
         """UPSERT one document_tags row (keys of d_tags / p_tags, app/models.py:525-543)."""
@@ -137,39 +219,73 @@ class PublishedTable:
             return n
 
     # -- snapshot ------------------------------------------------------------------------------
-    _HOST_STATE = ("id", "document_id", "source_type", "source_id", "document_payer", "document_state", "document_program",
-                   "document_authority_level", "extra", "doc_idx", "_next_doc", "doc_d_tags", "doc_p_tags")
-
     def save(self, dirpath: str, corpus_version: int = 0) -> None:
-        """Snapshot = the device shard (``index.mrag``) + the host half of the table (``table.pkl``): ids, hydration
-        columns, vocabularies, document maps.  Keyed by corpus_state.corpus_version (publish.py:314)."""
-        import os
-        import pickle
+        """Snapshot = the device shard(s) (``index.mrag*``) + the host columns (``columns.npz``, plain arrays) + the small
+        dictionaries (``table.json``).  Keyed by corpus_state.corpus_version (publish.py:314).  No pickle anywhere."""
         os.makedirs(dirpath, exist_ok=True)
         with self.lock:
             self.index.save(os.path.join(dirpath, "index.mrag"), corpus_version)
-            state = {k: getattr(self, k) for k in self._HOST_STATE}
-            state["vocab"] = self.vocab
-            state["corpus_version"] = int(corpus_version)
-            with open(os.path.join(dirpath, "table.pkl"), "wb") as f:
-                pickle.dump(state, f, protocol=pickle.HIGHEST_PROTOCOL)
+            arrays = {"row_doc": self.row_doc[:self._n].copy()}
+            arrays.update(self.id.arrays("id"))
+            arrays.update(self.source_id.arrays("source_id"))
+            for col, _, _ in _CODED:
+                arrays[col + ".codes"] = getattr(self, col).view().copy()
+            for c in HYDRATE_COLS:
+                arrays.update(self.extra[c].arrays("extra." + c))
+            np.savez(os.path.join(dirpath, "columns.npz"), **arrays)
+            v = self.vocab
+            meta = {
+                "corpus_version": int(corpus_version), "n": self._n, "dim": self.index.dim,
+                "shards": len(getattr(self.index, "shards", [None])),
+                "vocab": {name: getattr(v, name).values for name in ("payer", "state", "program", "authority", "source_type")},
+                "tag_bits": [[k[0], k[1], b] for k, b in v._tag_bit.items()],
+                "doc_ids": self.doc_ids, "live_docs": sorted(self.doc_idx.values()),
+                "doc_d_tags": {k: sorted(s) for k, s in self.doc_d_tags.items()},
+                "doc_p_tags": {k: sorted(s) for k, s in self.doc_p_tags.items()},
+            }
+            with open(os.path.join(dirpath, "table.json"), "w") as f:
+                json.dump(meta, f)
 
     @classmethod
-    def load(cls, dirpath: str, device: int = 0, capacity: int = 0) -> tuple["PublishedTable", int]:
+    def load(cls, dirpath: str, device: int = 0, capacity: int = 0, devices: Sequence[int] | None = None) -> tuple["PublishedTable", int]:
         """(table, corpus_version) from a snapshot directory; the cold start is one sequential read."""
-        import os
-        import pickle
-        with open(os.path.join(dirpath, "table.pkl"), "rb") as f:
-            state = pickle.load(f)
+        with open(os.path.join(dirpath, "table.json")) as f:
+            meta = json.load(f)
         self = cls.__new__(cls)
-        self.index, ver = Index.load(os.path.join(dirpath, "index.mrag"), device, capacity)
-        if ver != state["corpus_version"] or len(self.index) != len(state["id"]):
+        path = os.path.join(dirpath, "index.mrag")
+        if meta["shards"] > 1 or (devices is not None and len(devices) > 1):
+            from .multi import MultiIndex
+            devs = list(devices) if devices is not None else [device] * meta["shards"]
+            if len(devs) != meta["shards"]:
+                raise ValueError(f"snapshot holds {meta['shards']} shards, {len(devs)} devices given")
+            self.index, ver = MultiIndex.load(path, devs, capacity)
+        else:
+            self.index, ver = Index.load(path, device if devices is None else devices[0], capacity)
+        if ver != meta["corpus_version"] or len(self.index) != meta["n"]:
             self.index.close()
-            raise ValueError("snapshot is inconsistent: index.mrag and table.pkl come from different versions")
-        self.lock = threading.RLock()
-        self.vocab = state["vocab"]
-        for k in cls._HOST_STATE:
-            setattr(self, k, state[k])
+            raise ValueError("snapshot is inconsistent: index.mrag and table.json come from different versions")
+        v = Vocab()
+        for name, values in meta["vocab"].items():
+            voc = getattr(v, name)
+            for x in values:
+                voc.encode(x)
+        for kind, key, b in meta["tag_bits"]:
+            v._tag_bit[(kind, key)] = int(b)
+        self._init_host(v)
+        z = np.load(os.path.join(dirpath, "columns.npz"), allow_pickle=False)
+        self._n = int(meta["n"])
+        self.row_doc = np.ascontiguousarray(z["row_doc"], dtype=np.uint32)
+        self.id = StrCol.from_arrays(z, "id")
+        self.source_id = StrCol.from_arrays(z, "source_id")
+        for col, _, _ in _CODED:
+            getattr(self, col).extend(z[col + ".codes"])
+        for c in HYDRATE_COLS:
+            kind = IntCol if c in _INT_COLS else JsonCol if c in _JSON_COLS else StrCol
+            self.extra[c] = kind.from_arrays(z, "extra." + c)
+        self.doc_ids = list(meta["doc_ids"])
+        self.doc_idx = {self.doc_ids[d]: d for d in meta["live_docs"]}
+        self.doc_d_tags = {k: set(s) for k, s in meta["doc_d_tags"].items()}
+        self.doc_p_tags = {k: set(s) for k, s in meta["doc_p_tags"].items()}
         return self, ver
 
     # -- WHERE builders ------------------------------------------------------------------------

@@ -60,7 +60,7 @@ class B200VectorStore(VectorStore):
 
     def __init__(self, table_name: str = "rag_published_embeddings", dim: int | None = None,
                  dtype: str | None = None, device: int | None = None, capacity: int | None = None,
-                 table: PublishedTable | None = None):
+                 table: PublishedTable | None = None, devices: list[int] | None = None):
         if table_name not in {"rag_published_embeddings", "chunk_embeddings"}:
             raise ValueError(f"B200VectorStore: unsupported table {table_name!r}")   # vector_store.py:163-164
         self._table_name = table_name
@@ -68,6 +68,10 @@ class B200VectorStore(VectorStore):
         self._dtype = (dtype or os.getenv("MRAG_DTYPE", "f32")).lower()
         self._device = int(device if device is not None else os.getenv("MRAG_DEVICE", "0"))
         self._capacity = int(capacity if capacity is not None else os.getenv("MRAG_CAPACITY", str(1 << 21)))
+        # MRAG_DEVICES="0,1,2,3,4,5,6,7": ONE store object (one FastAPI worker) row-shards the table over these GPUs;
+        # search / asearch keep the reference's signatures (vector_store.py:181-226) and hit all of them
+        env_devs = os.getenv("MRAG_DEVICES", "").strip()
+        self._devices = list(devices) if devices else ([int(x) for x in env_devs.split(",") if x.strip()] if env_devs else None)
         self._table = table
         self._init_lock = threading.Lock()
 
@@ -76,7 +80,7 @@ class B200VectorStore(VectorStore):
         if self._table is None:
             with self._init_lock:
                 if self._table is None:
-                    self._table = PublishedTable(self._dim, self._dtype, self._device, self._capacity)
+                    self._table = PublishedTable(self._dim, self._dtype, self._device, self._capacity, devices=self._devices)
         return self._table
 
     def add(self, ids: list[str], embeddings: list[list[float]], metadata: list[dict]) -> None:
@@ -143,13 +147,50 @@ class B200VectorStore(VectorStore):
         return out
 
 
+class B200ChromaVectorStore(B200VectorStore):
+    """Drop-in for ``ChromaVectorStore`` (vector_store.py:34-104): the collection ``coll.query(query_embeddings=[e],
+    n_results=k, where={"document_id": ...}, include=[metadatas, distances])`` on a ``hnsw:space = cosine`` collection.
+
+    Differences from the pgvector-shaped store, all the reference's: ``distance`` is the cosine DISTANCE (0..2, smaller is
+    closer), not the similarity; the only filter is ``document_id``; metadata values are stringified on ``add``
+    (``str(m.get(key, ""))``, :70-74 -- a None becomes the string "None").  Chroma's HNSW search is approximate; this scan
+    is exact, i.e. it returns what Chroma would with perfect recall.  A zero-norm vector has no cosine; hnswlib reports
+    distance 1.0 for it and so does this store."""
+
+    def __init__(self, collection_name: str = "chunk_embeddings", host: str | None = None, port: int | None = None,
+                 persist_directory: str | None = None, **kw):
+        super().__init__(table_name="chunk_embeddings", **kw)
+        self._collection_name = collection_name
+        self._host, self._port, self._persist_directory = host, port, persist_directory     # kept for signature parity; unused
+
+    def add(self, ids: list[str], embeddings: list[list[float]], metadata: list[dict]) -> None:
+        if not ids:
+            return
+        metas = [{"document_id": str(m.get("document_id", "")), "source_type": str(m.get("source_type", "")),
+                  "source_id": str(m.get("source_id", ""))} for m in metadata]
+        super().add(ids, embeddings, metas)
+
+    def search(self, embedding: list[float], k: int = 10, document_id: str | None = None) -> list[dict]:
+        out = self._search_blocking(embedding, k, document_id, None)
+        for r in out:
+            sim = r["distance"]
+            r["distance"] = 1.0 if sim != sim else 1.0 - sim
+        return out
+
+    async def asearch(self, embedding: list[float], k: int = 10, document_id: str | None = None, filters=None) -> list[dict]:
+        return await asyncio.to_thread(self.search, embedding, k, document_id)
+
+
 def get_vector_store() -> VectorStore:
-    """vector_store.py:306-321 with one more value: ``VECTOR_STORE=b200``."""
+    """vector_store.py:306-321 with the B200 stores in place of the engines: ``VECTOR_STORE=b200`` -> the pgvector-shaped
+    B200VectorStore; Chroma's environment (``CHROMA_HOST`` / ``CHROMA_PERSIST_DIR``) -> the Chroma-shaped store; otherwise
+    the no-op store, as in the reference.  ``VECTOR_STORE=pgvector`` is the reference's own Postgres path (INTEGRATION.md
+    shows the one-line edit that adds the ``b200`` branch next to it)."""
     explicit = (os.getenv("VECTOR_STORE") or "").strip().lower()
     if explicit == "b200":
         return B200VectorStore()
     if explicit == "pgvector":
         raise RuntimeError("VECTOR_STORE=pgvector is the reference's Postgres path; this package provides VECTOR_STORE=b200")
     if os.getenv("CHROMA_HOST") or os.getenv("CHROMA_PERSIST_DIR"):
-        raise RuntimeError("Chroma is the reference's legacy path; this package provides VECTOR_STORE=b200")
+        return B200ChromaVectorStore()
     return NoopVectorStore()

@@ -10,6 +10,6 @@ if _root not in sys.path:
     sys.path.insert(0, _root)
 _real = "mobius-rag_b200"
 _pkg = importlib.import_module(_real)
-for _sub in ("_native", "build", "index", "vocab", "table", "vector_store", "corpus_search", "hybrid", "sharded", "synth"):
+for _sub in ("_native", "build", "index", "vocab", "columns", "multi", "table", "vector_store", "corpus_search", "hybrid", "sharded", "synth"):
     sys.modules[__name__ + "." + _sub] = importlib.import_module(_real + "." + _sub)
 sys.modules[__name__] = _pkg

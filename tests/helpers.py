@@ -27,7 +27,7 @@ def tag_key(bit: int) -> tuple[str, str]:
 
 
 def build_tables(oracle, n: int, dim: int, seed: int = 7, dtype: str = "f32", null_frac: float = 2e-3,
-                 rows_per_doc: int = 16, device: int = 0, with_product: bool = True, n_tag_bits: int = 24):
+                 rows_per_doc: int = 16, device: int = 0, with_product: bool = True, n_tag_bits: int = 24, devices=None):
     """Returns (oracle.Table, PublishedTable or None, X, valid, meta, info)."""
     X, valid = synth.make_corpus(n, dim, seed=seed, null_frac=null_frac)
     meta, doc_tags, info = synth.make_metadata(n, seed=seed + 1, rows_per_doc=rows_per_doc, valid=valid)
@@ -66,7 +66,7 @@ def build_tables(oracle, n: int, dim: int, seed: int = 7, dtype: str = "f32", nu
                       doc_d_tags=d_tags, doc_p_tags=p_tags, extra=extra)
     pt = None
     if with_product:
-        pt = mrag_b200.PublishedTable(dim, dtype=dtype, device=device, capacity=n + 64)
+        pt = mrag_b200.PublishedTable(dim, dtype=dtype, device=device, capacity=n + 64, devices=devices)
         rows = []
         for i in range(n):
             r = {"id": ids[i], "document_id": document_id[i], "source_type": src[i], "source_id": f"src-{i}",
@@ -95,7 +95,7 @@ def load_golden_json(name: str):
         return json.loads(f.read().decode())
 
 
-def load_golden_table(oracle, with_product: bool = False, dtype: str = "f32", device: int = 0):
+def load_golden_table(oracle, with_product: bool = False, dtype: str = "f32", device: int = 0, devices=None):
     """The table the golden fixtures were generated on (tests/golden/make_golden.py), rebuilt from the
     committed files -- NOT from synth, so generator changes cannot silently move the fixtures."""
     import json
@@ -112,7 +112,7 @@ def load_golden_table(oracle, with_product: bool = False, dtype: str = "f32", de
     pt = None
     if with_product:
         n, dim = tj["n"], tj["dim"]
-        pt = mrag_b200.PublishedTable(dim, dtype=dtype, device=device, capacity=n + 64)
+        pt = mrag_b200.PublishedTable(dim, dtype=dtype, device=device, capacity=n + 64, devices=devices)
         rows = []
         for i in range(n):
             r = {name: col[i] for name, col in c.items()}

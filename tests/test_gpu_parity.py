@@ -473,7 +473,7 @@ def test_mma_default_dispatch_and_limits(oracle):
     idx.search(Q[:1], 10, Filter().doc_eq(3))
     assert idx.last_scan_kind() == "gemv"         # a filtered single query: the CUDA-core scan skips rows one by one
     idx.close()
-    for dtype, dim in (("f32", 768), ("bf16", 1536)):       # outside the tensor-core scan's envelope
+    for dtype, dim in (("f32", 768), ("bf16", 1600)):       # outside the tensor-core scan's envelope
         idx = Index(dim, dtype, 0, 100)
         idx.append(np.ones((3, dim), np.float32))
         idx.search(np.ones((2, dim), np.float32), 2)
@@ -481,6 +481,97 @@ def test_mma_default_dispatch_and_limits(oracle):
         with pytest.raises(N.MragError):
             idx.search(np.ones((2, dim), np.float32), 2, options=N.OPT_FORCE_MMA)
         idx.close()
+    # rows of 769 .. 1536 elements (the reference's production dimension is 1536): k-split CTA pairs
+    idx = Index(1536, "bf16", 0, 100)
+    idx.append(np.ones((3, 1536), np.float32))
+    idx.search(np.ones((2, 1536), np.float32), 2)
+    assert idx.last_scan_kind() == "mma_ks"
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# rows of 769 .. 1536 elements: the k-split pair kernel (two CTAs share every tile along K, the helper's
+# partial dots travel through distributed shared memory) must equal the oracle like the one-CTA kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (5000, 1536, 1, 10), (5000, 1536, 2, 10), (64, 832, 3, 10), (63, 1024, 1, 5), (65, 1536, 64, 10),
+    (20000, 1536, 64, 10), (20000, 1536, 65, 10), (30000, 1024, 130, 10), (20000, 832, 7, 100),
+    (9000, 1472, 4, 128), (9000, 900, 2, 129), (6000, 1500, 3, 300), (4097, 770, 5, 7), (12000, 1280, 33, 64),
+    (100000, 1536, 16, 10), (9473, 1536, 40, 10), (9472 * 2 + 1, 1152, 64, 16),
+])
+def test_ksplit_scan_bf16(oracle, n, dim, nq, k):
+    X, valid = synth.make_corpus(n, dim, seed=n + dim + 1, null_frac=3e-3)
+    Q = synth.make_queries(X, nq, seed=k + 1)
+    idx = Index(dim, "bf16", 0, n + 5)
+    idx.append(X, make_meta(n, valid=valid))
+    s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA)
+    assert idx.last_scan_kind() == "mma_ks"
+    check_all(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, s, r, c, "bf16")
+    s2, r2, c2 = idx.search(Q, k)                        # default dispatch (single queries included) -> same bytes
+    assert idx.last_scan_kind() == "mma_ks"
+    assert (s2.tobytes(), r2.tobytes(), c2.tobytes()) == (s.tobytes(), r.tobytes(), c.tobytes())
+    idx.close()
+
+
+def test_ksplit_with_filters_ties_and_nan(oracle):
+    n, dim, k = 40000, 1536, 20
+    X, valid = synth.make_corpus(n, dim, seed=231, null_frac=2e-3, zero_norm_rows=3)
+    dup = np.arange(1000, 1000 + 90)                  # a 90-row boilerplate cluster across two tiles (= both leaders)
+    X[dup] = X[dup[0]]
+    meta, doc_tags, info = synth.make_metadata(n, seed=232, rows_per_doc=64, valid=valid)
+    Q = synth.make_queries(X, 9, seed=233)
+    Q[0] = X[dup[0]] * 2.0
+    Q[1] = 0.0                                        # zero query: all NaN
+    idx = Index(dim, "bf16", 0, n)
+    idx.append(X, meta)
+    idx.set_doc_tags(0, doc_tags)
+    Xs = oracle.round_bf16(X)
+    v = valid.astype(bool)
+    doc = meta["doc_idx"]
+    pool = np.random.default_rng(5).choice(info["n_docs"], size=40, replace=False)     # most tiles are skipped entirely
+    cases = [
+        (None, v),
+        (Filter().doc_pool(pool), np.isin(doc, pool) & v),
+        (Filter().payer_in([2]), (meta["payer"] == 2) & v),
+        (Filter().doc_eq(int(doc[dup[0]])), (doc == doc[dup[0]]) & v),
+        (Filter().payer_in([0xFFFE]), np.zeros(n, bool)),
+    ]
+    for flt, want in cases:
+        s, r, c = idx.search(Q, k, flt, options=N.OPT_FORCE_MMA)
+        assert idx.last_scan_kind() == "mma_ks"
+        check_all(oracle, Xs, Q, want, k, s, r, c, "bf16")
+    idx.close()
+
+
+def test_ksplit_threshold_sampling_pass(oracle):
+    """the sampled admission bound + the shared-memory buffer select of the k-split kernel on a small shard"""
+    import subprocess, sys, textwrap, os
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        import mrag_b200
+        from mrag_b200 import synth, _native as N
+        from mrag_b200.index import Index, make_meta, Filter
+        from oracle import oracle
+        n, dim = 60000, 1536
+        X, valid = synth.make_corpus(n, dim, seed=177, null_frac=1e-3)
+        dup = np.arange(0, n, 64 * 64)[:10] + 3
+        X[dup] = X[dup[0]]; valid[dup] = 1
+        Q = synth.make_queries(X, 70, seed=178)
+        Q[0] = X[dup[0]]
+        idx = Index(dim, "bf16", 0, n)
+        idx.append(X, make_meta(n, valid=valid))
+        Xs = oracle.round_bf16(X)
+        for k in (10, 100, 200):
+            s, r, c = idx.search(Q, k, options=N.OPT_FORCE_MMA)
+            assert idx.last_scan_kind() == "mma_ks"
+            for i in range(Q.shape[0]):
+                oracle.check_topk(r[i], s[i], int(c[i]), oracle.all_similarities(Xs, Q[i]), valid.astype(bool), k, rtol=1e-2)
+        print("SAMPLING-OK")
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MRAG_SAMPLE_MIN_TILES="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "SAMPLING-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 def test_mma_with_filters_ties_and_nan(oracle):
@@ -820,5 +911,5 @@ def test_snapshot_round_trip(oracle, tmp_path):
     hit = mrag_b200.B200VectorStore(table=pt2).search(X[3].tolist(), 3)
     assert any(h["id"] == "new-1" for h in hit)
     with pytest.raises(N.MragError):
-        Index.load(str(tmp_path / "snap" / "table.pkl"))          # not a snapshot file
+        Index.load(str(tmp_path / "snap" / "table.json"))         # not a snapshot file
     pt.index.close(); pt2.index.close()
