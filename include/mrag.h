@@ -93,7 +93,9 @@ enum {
     MRAG_F_DOC_EQ      = 1u << 5,  /* document_id = :document_id           vector_store.py:247-249   */
     MRAG_F_DOC_POOL    = 1u << 6,  /* document_id = ANY(:inc_ids)          corpus_search.py:546-558  */
     MRAG_F_TAG_STRICT  = 1u << 7,  /* OR(state IN, program IN, payer IN)   corpus_search.py:1478-1496 */
-    MRAG_F_TAG_RELAXED = 1u << 8   /* doc d/p tag bitset & tag_any != 0    corpus_search.py:1497-1510 */
+    MRAG_F_TAG_RELAXED = 1u << 8,  /* doc d/p tag bitset & tag_any != 0    corpus_search.py:1497-1510 */
+    MRAG_F_DOC_POOL_HANDLE = 1u << 9 /* document_id = ANY(pool) with the pool resident on the device (mrag_pool_build):
+                                      no UUID list is marshalled per search   corpus_search_agent.py:1762-1888 */
 };
 
 typedef struct mrag_filter {
@@ -118,6 +120,8 @@ typedef struct mrag_filter {
     uint64_t tag_payer_any[MRAG_PAYER_WORDS];
     /* MRAG_F_TAG_RELAXED: document tag bits, any-of */
     uint64_t tag_any[MRAG_TAG_WORDS];
+    /* MRAG_F_DOC_POOL_HANDLE: a pool built by mrag_pool_build on the SAME index (excludes MRAG_F_DOC_POOL) */
+    const struct mrag_pool* pool;
 } mrag_filter;
 
 typedef struct mrag_index mrag_index;
@@ -228,7 +232,8 @@ typedef struct mrag_chunkfeat {
 enum {
     MRAG_CF_SHORT_TEXT    = 1u << 0,  /* body haystack has <= 20 words: _classify_jpd scores hits / sqrt(n) (:336-347) */
     MRAG_CF_CONTACT_VALUE = 1u << 1,  /* _CONTACT_VALUE_RE matches the text (:676-683, :2219-2222)                      */
-    MRAG_CF_PROMOTED      = 1u << 2   /* promoted neighbour / bm25_inherited: exempt from the coverage floor (:2205-2208) */
+    MRAG_CF_PROMOTED      = 1u << 2,  /* promoted neighbour / bm25_inherited: exempt from the coverage floor (:2205-2208) */
+    MRAG_CF_DTAG_OVERFLOW = 1u << 3   /* chunk_d_tags has more than 4 keys: the rest are in the overflow table (mrag_set_dtag_overflow) */
 };
 
 typedef struct mrag_hybrid_query {
@@ -251,6 +256,10 @@ typedef struct mrag_hybrid_query {
 
 /* per-row text features of rows [first_row, first_row + n) (HOST array) */
 int mrag_set_chunk_features(mrag_index* idx, int64_t first_row, const mrag_chunkfeat* feat, int64_t n);
+/* chunk_d_tags keys that do not fit the 4 inline slots of mrag_chunkfeat: n (row, code) pairs, HOST arrays, sorted by
+ * row (rows carry MRAG_CF_DTAG_OVERFLOW).  `chunk_d_tags ? :key` (corpus_search.py:1637-1672) matches any key of the JSONB
+ * map; this call REPLACES the whole table. */
+int mrag_set_dtag_overflow(mrag_index* idx, const uint32_t* rows, const uint16_t* codes, int64_t n);
 /* document j: tag sets as bitsets, n_docs * MRAG_JTAG_WORDS u64 (HOST), like mrag_set_doc_tags */
 int mrag_set_doc_jtags(mrag_index* idx, int64_t first_doc, const uint64_t* bits, int64_t n_docs);
 /* The fused scan: like mrag_search, ordered by rerank score DESC (ties by ascending row) over the rows that
@@ -298,6 +307,37 @@ int mrag_merge_topk(int device, int n_lists, int nq, int k,
 int mrag_exchange_merge(int device, int world, int rank, int nq, int k, void* const* peer_bufs,
                         int64_t slot_bytes, int64_t scores_off, int64_t counts_off, uint32_t epoch,
                         float* d_scores_out, int64_t* d_rows_out, int32_t* d_counts_out, void* stream);
+
+/* --- candidate pool on the device ------------------------------------------------------------------
+ * `build_candidate_pool` (corpus_search_agent.py:1762-1888) intersects per-tag document sets fetched with one SQL
+ * statement per tag (`_doc_ids_with_tag`, :1461-1482) and cascades  L1 J&D&P -> L2 J&D -> L3 AHCA&D -> L4 AHCA.  The
+ * per-document tag sets already sit in HBM as bitsets (mrag_set_doc_tags / mrag_set_doc_jtags), so all four levels are
+ * ONE kernel over the documents; the chosen level stays on the device as a document bitmap that mrag_search takes
+ * through mrag_filter.pool (MRAG_F_DOC_POOL_HANDLE) -- no list of <= 5000 UUIDs per search. */
+#define MRAG_POOL_LEVELS 4      /* 0 = L1_JDP, 1 = L2_JD, 2 = L3_AHCA_D, 3 = L4_AHCA */
+typedef struct mrag_pool_query {
+    uint64_t d_all[MRAG_TAG_WORDS];    /* bits of the d: codes of the query in the document tag sets (ALL must be present) */
+    uint64_t p_all[MRAG_TAG_WORDS];    /* bits of the p: codes */
+    uint64_t j_all[MRAG_JTAG_WORDS];   /* bits of the j: codes in the document j-tag sets */
+    uint64_t ahca[MRAG_JTAG_WORDS];    /* bit of j:regulatory_authority.ahca (:1458) */
+    int32_t has_j, has_d, has_p;       /* 1 = the query names codes of that kind AND every one of them is known to the
+                                          vocabulary (an unknown code matches no document: leave the kind 0 and the level
+                                          comes out empty, as the reference's set intersection does) */
+    int32_t has_ahca;                  /* 1 = some document carries the AHCA tag */
+} mrag_pool_query;
+typedef struct mrag_pool mrag_pool;
+/* counts[l] = documents at level l (before any cap); counts[MRAG_POOL_LEVELS] = documents carrying every d: code (the
+ * cascade tries L3 only when that set is not empty, :1851).  The document sets are those of the tag tables, as in the
+ * reference (`document_tags` rows), whether or not a document currently has chunk rows. */
+int mrag_pool_build(mrag_index* idx, const mrag_pool_query* q, mrag_pool** out, int64_t counts[MRAG_POOL_LEVELS + 1]);
+/* The level the handle stands for from now on; at most `cap` documents are kept (lowest document indices; the reference
+ * keeps list(set)[:5000], :1818); *n_kept (may be NULL) = documents kept. */
+int mrag_pool_select(mrag_pool* pool, int level, int64_t cap, int64_t* n_kept);
+/* Union extra documents into the selected level (the inherited-authority union, :1966-2002). */
+int mrag_pool_add_docs(mrag_pool* pool, const uint32_t* docs, int64_t n);
+/* Document indices of the selected level, ascending, at most `max` (HOST out); *n = how many were written. */
+int mrag_pool_docs(mrag_pool* pool, uint32_t* out, int64_t max, int64_t* n);
+int mrag_pool_destroy(mrag_pool* pool);
 
 /* K2 alone: evaluate `filter` into a row bitmap (bit r of word r/32), DEVICE pointer,
  * ceil(size/32) words; *n_pass (HOST, may be NULL) gets the popcount. */

@@ -17,10 +17,11 @@ MRAG_FUSED_K, MRAG_MAX_K = 128, 2048
 MRAG_PAYER_WORDS, MRAG_SMALL_WORDS, MRAG_TAG_WORDS = 16, 4, 8
 MRAG_CODE_NONE = 0xFFFF
 F_PAYER, F_STATE, F_PROGRAM, F_AUTHORITY, F_SOURCE_TYPE = 1, 2, 4, 8, 16
-F_DOC_EQ, F_DOC_POOL, F_TAG_STRICT, F_TAG_RELAXED = 32, 64, 128, 256
+F_DOC_EQ, F_DOC_POOL, F_TAG_STRICT, F_TAG_RELAXED, F_DOC_POOL_HANDLE = 32, 64, 128, 256, 512
+MRAG_POOL_LEVELS = 4
 OPT_DEVICE_IO, OPT_FORCE_GEMV, OPT_FORCE_MMA, OPT_NO_SYNC, OPT_FORCE_MMA128, OPT_COALESCE = 1, 2, 4, 8, 16, 32
 MRAG_PHRASE_WORDS, MRAG_JPD_CATS, MRAG_JTAG_WORDS, MRAG_HYB_MAX_PHRASES = 2, 11, 4, 16
-CF_SHORT_TEXT, CF_CONTACT_VALUE, CF_PROMOTED = 1, 2, 4
+CF_SHORT_TEXT, CF_CONTACT_VALUE, CF_PROMOTED, CF_DTAG_OVERFLOW = 1, 2, 4, 8
 
 EXPORTS = [
     "mrag_create", "mrag_destroy", "mrag_append", "mrag_append_device", "mrag_set_doc_tags",
@@ -29,7 +30,7 @@ EXPORTS = [
     "mrag_profile_begin", "mrag_profile_read", "mrag_launch_count", "mrag_last_scan_kind",
     "mrag_last_error", "mrag_version",
     "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge", "mrag_save", "mrag_load",
-    "mrag_set_row_ids",
+    "mrag_set_row_ids", "mrag_set_dtag_overflow", "mrag_pool_build", "mrag_pool_select", "mrag_pool_add_docs", "mrag_pool_docs", "mrag_pool_destroy",
 ]
 
 
@@ -55,6 +56,7 @@ class FilterStruct(C.Structure):
         ("tag_program_any", C.c_uint64 * MRAG_SMALL_WORDS),
         ("tag_payer_any", C.c_uint64 * MRAG_PAYER_WORDS),
         ("tag_any", C.c_uint64 * MRAG_TAG_WORDS),
+        ("pool", C.c_void_p),
     ]
 
 
@@ -63,6 +65,15 @@ class ChunkFeat(C.Structure):
     _fields_ = [
         ("phrase_bits", C.c_uint64 * MRAG_PHRASE_WORDS), ("jpd_hits", C.c_uint8 * MRAG_JPD_CATS), ("flags", C.c_uint8),
         ("length_score", C.c_float), ("dtags", C.c_uint16 * 4),
+    ]
+
+
+class PoolQuery(C.Structure):
+    """mrag_pool_query."""
+    _fields_ = [
+        ("d_all", C.c_uint64 * MRAG_TAG_WORDS), ("p_all", C.c_uint64 * MRAG_TAG_WORDS),
+        ("j_all", C.c_uint64 * 4), ("ahca", C.c_uint64 * 4),
+        ("has_j", C.c_int32), ("has_d", C.c_int32), ("has_p", C.c_int32), ("has_ahca", C.c_int32),
     ]
 
 
@@ -135,6 +146,18 @@ def load(build_if_missing: bool = True):
     lib.mrag_set_row_base.argtypes = [vp, i64]
     lib.mrag_set_row_ids.restype = i32
     lib.mrag_set_row_ids.argtypes = [vp, i64, vp, i64]
+    lib.mrag_set_dtag_overflow.restype = i32
+    lib.mrag_set_dtag_overflow.argtypes = [vp, vp, vp, i64]
+    lib.mrag_pool_build.restype = i32
+    lib.mrag_pool_build.argtypes = [vp, C.POINTER(PoolQuery), C.POINTER(vp), C.POINTER(i64)]
+    lib.mrag_pool_select.restype = i32
+    lib.mrag_pool_select.argtypes = [vp, i32, i64, C.POINTER(i64)]
+    lib.mrag_pool_add_docs.restype = i32
+    lib.mrag_pool_add_docs.argtypes = [vp, vp, i64]
+    lib.mrag_pool_docs.restype = i32
+    lib.mrag_pool_docs.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.mrag_pool_destroy.restype = i32
+    lib.mrag_pool_destroy.argtypes = [vp]
     lib.mrag_merge_topk.restype = i32
     lib.mrag_merge_topk.argtypes = [i32, i32, i32, i32, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]
     lib.mrag_filter_mask.restype = i32

@@ -35,12 +35,30 @@ struct HybEval {
     bool dtag_match;
 };
 
-MRAG_DEVINL bool has_dtag(const mrag_chunkfeat& f, uint32_t code) {
-    return f.dtags[0] == code || f.dtags[1] == code || f.dtags[2] == code || f.dtags[3] == code;
+// chunk_d_tags keys beyond the four inline slots of mrag_chunkfeat: (row, code) pairs sorted by row.  `chunk_d_tags ? :key`
+// (corpus_search.py:1637-1672) matches ANY key of the JSONB map, so a chunk with more than four keys keeps the rest here
+// and carries MRAG_CF_DTAG_OVERFLOW; the table is only consulted for such rows.
+struct DtagOver {
+    const uint32_t* rows;
+    const uint16_t* codes;
+    int64_t n;
+};
+
+MRAG_DEVINL bool has_dtag(const mrag_chunkfeat& f, uint32_t code, int64_t row, const DtagOver& ov) {
+    if (f.dtags[0] == code || f.dtags[1] == code || f.dtags[2] == code || f.dtags[3] == code) return true;
+    if (!(f.flags & MRAG_CF_DTAG_OVERFLOW) || ov.n == 0) return false;
+    int64_t lo = 0, hi = ov.n;                            // first pair of this row
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (int64_t(ov.rows[mid]) < row) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < ov.n && int64_t(ov.rows[lo]) == row; ++lo)
+        if (ov.codes[lo] == code) return true;
+    return false;
 }
 
 // coverage and chunk d-tag match of one (row, query) pair.  jt: the document's j-tag words or nullptr.
-MRAG_DEVINL HybEval hybrid_eval(const DevHyb& h, const mrag_chunkfeat& f, const uint64_t* jt) {
+MRAG_DEVINL HybEval hybrid_eval(const DevHyb& h, const mrag_chunkfeat& f, const uint64_t* jt, int64_t row, const DtagOver& ov) {
     HybEval e;
     e.cov = 0.0f;
     e.dtag_match = false;
@@ -55,7 +73,7 @@ MRAG_DEVINL HybEval hybrid_eval(const DevHyb& h, const mrag_chunkfeat& f, const 
         }
         if (present) acc += h.q.phrase_weight[i];          // same order as the reference's sum: complete coverage is exactly 1
         const uint32_t dc = h.q.phrase_dcode[i];
-        if (dc != 0u) e.dtag_match = e.dtag_match || has_dtag(f, dc);
+        if (dc != 0u) e.dtag_match = e.dtag_match || has_dtag(f, dc, row, ov);
     }
     if (h.q.n_phrases > 0) e.cov = acc / h.total_weight;
     return e;
@@ -96,7 +114,7 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
                                                          const uint32_t* __restrict__ base_mask, const uint32_t* __restrict__ doc_idx,
                                                          const uint8_t* __restrict__ source_type,
                                                          const uint64_t* __restrict__ doc_jtags, int64_t n_jtag_docs, int64_t n,
-                                                         uint32_t* __restrict__ hmask, int64_t nwords) {
+                                                         uint32_t* __restrict__ hmask, int64_t nwords, const DtagOver ov) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool in_range = r < n;
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
             // quick reject: a phrase that only its dictionary bit can satisfy is missing, and no exemption can apply
             const bool bits_ok = !h.impossible && (f.phrase_bits[0] & h.need[0]) == h.need[0] && (f.phrase_bits[1] & h.need[1]) == h.need[1];
             if (!bits_ok && !maybe_exempt) keep = false;
-            else keep = hybrid_keep(h, f, hybrid_eval(h, f, jt));
+            else keep = hybrid_keep(h, f, hybrid_eval(h, f, jt, r, ov));
         }
         const uint32_t word = __ballot_sync(kFull, keep);
         if (lane == 0 && (r >> 5) < nwords) hmask[size_t(q) * nwords + (r >> 5)] = word;
@@ -136,7 +154,8 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
 // holding code i.
 __global__ void __launch_bounds__(256) dtag_mask_kernel(const mrag_chunkfeat* __restrict__ feat, const uint32_t* __restrict__ base_mask,
                                                        int64_t n, const uint16_t* __restrict__ codes, int n_codes,
-                                                       uint32_t* __restrict__ mask_out, unsigned long long* __restrict__ counts) {
+                                                       uint32_t* __restrict__ mask_out, unsigned long long* __restrict__ counts,
+                                                       const DtagOver ov) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool base = false, any = false;
@@ -146,7 +165,7 @@ __global__ void __launch_bounds__(256) dtag_mask_kernel(const mrag_chunkfeat* __
         if (base) {
             const mrag_chunkfeat f = feat[r];
             for (int i = 0; i < n_codes; ++i)
-                if (has_dtag(f, codes[i])) has |= 1u << i;
+                if (has_dtag(f, codes[i], r, ov)) has |= 1u << i;
             any = has != 0u;
         }
     }

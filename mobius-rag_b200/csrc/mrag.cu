@@ -147,6 +147,9 @@ struct mrag_index {
     uint64_t* doc_tags = nullptr;       // [tag_docs_cap][MRAG_TAG_WORDS]
     int64_t n_tag_docs = 0, tag_docs_cap = 0;
     mrag_chunkfeat* feat = nullptr;     // [capacity] text features of the hybrid rerank (allocated on first use, zero = none)
+    uint32_t* over_rows = nullptr;      // chunk d-tag keys beyond the 4 inline slots: (row, code) pairs sorted by row
+    uint16_t* over_codes = nullptr;
+    int64_t n_over = 0;
     int64_t* row_ids = nullptr;         // [capacity] caller-assigned id of every row (mrag_set_row_ids), nullptr = row + row_base
     uint64_t* doc_jtags = nullptr;      // [jtag_docs_cap][MRAG_JTAG_WORDS]
     int64_t n_jtag_docs = 0, jtag_docs_cap = 0;
@@ -182,6 +185,15 @@ struct DeviceGuard {
 };
 
 static size_t elem_size(int dtype) { return dtype == MRAG_BF16 ? 2 : 4; }
+
+// a candidate pool resident on the device: the four cascade levels as document bitmaps + the level in use
+struct mrag_pool {
+    mrag_index* idx = nullptr;
+    uint32_t* bits = nullptr;           // [MRAG_POOL_LEVELS][words]
+    int64_t words = 0, n_docs = 0;
+    int level = -1;
+    int64_t counts[MRAG_POOL_LEVELS] = {0, 0, 0, 0};
+};
 
 // thread-local record of the last search (for mrag_last_kernel_ms / mrag_last_scan_kind)
 static thread_local EventSet t_last_ev;          // borrowed handles (owned by a workspace / ring)
@@ -318,6 +330,8 @@ extern "C" int mrag_destroy(mrag_index* x) {
     if (x->doc_tags) cudaFree(x->doc_tags);
     if (x->feat) cudaFree(x->feat);
     if (x->row_ids) cudaFree(x->row_ids);
+    if (x->over_rows) cudaFree(x->over_rows);
+    if (x->over_codes) cudaFree(x->over_codes);
     if (x->doc_jtags) cudaFree(x->doc_jtags);
     if (x->wstream) cudaStreamDestroy(x->wstream);
     t_last_valid = false;
@@ -581,7 +595,23 @@ static int build_mask(mrag_index* x, Workspace* w, const mrag_filter* f, int64_t
     DevFilter df;
     to_dev_filter(f, &df);
     const uint32_t* pool_bits = nullptr;
-    if (df.flags & MRAG_F_DOC_POOL) {
+    if (df.flags & MRAG_F_DOC_POOL_HANDLE) {
+        // the pool is already a document bitmap on this device (mrag_pool_build): nothing to marshal
+        const mrag_pool* p = f->pool;
+        if (df.flags & MRAG_F_DOC_POOL) return fail(MRAG_ERR_ARG, "mrag_filter: MRAG_F_DOC_POOL and MRAG_F_DOC_POOL_HANDLE exclude each other");
+        if (!p || p->idx != x || p->level < 0 || p->level >= MRAG_POOL_LEVELS || !p->bits)
+            return fail(MRAG_ERR_ARG, "mrag_filter: pool handle is null, belongs to another index, or has no level selected");
+        const uint32_t* src = p->bits + size_t(p->level) * p->words;
+        const int64_t words = ceil_div(std::max<int64_t>(x->n_docs, 1), 32);
+        if (words > p->words) {                          // documents were added since the pool was built: they are not in it
+            if (w->pool_bits.reserve(size_t(words))) return MRAG_ERR_OOM;
+            CU(cudaMemsetAsync(w->pool_bits.p, 0, size_t(words) * 4, s));
+            CU(cudaMemcpyAsync(w->pool_bits.p, src, size_t(p->words) * 4, cudaMemcpyDeviceToDevice, s));
+            src = w->pool_bits.p;
+        }
+        pool_bits = src;
+        df.flags = (df.flags & ~uint32_t(MRAG_F_DOC_POOL_HANDLE)) | MRAG_F_DOC_POOL;
+    } else if (df.flags & MRAG_F_DOC_POOL) {
         if (f->n_doc_pool < 0 || (f->n_doc_pool > 0 && !f->doc_pool))
             return fail(MRAG_ERR_ARG, "mrag_filter: doc_pool is null or n_doc_pool < 0");
         const int64_t words = ceil_div(std::max<int64_t>(x->n_docs, 1), 32);
@@ -676,7 +706,7 @@ static int launch_scan_mma(mrag_index* x, MmaArgs a, int nq, int grid, cudaStrea
         a.nq = std::min(kMmaQueries, nq - q0);
         if constexpr (KS) {
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kMmaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kMmaKsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1381,6 +1411,30 @@ extern "C" int mrag_set_chunk_features(mrag_index* x, int64_t first_row, const m
     return MRAG_OK;
 }
 
+extern "C" int mrag_set_dtag_overflow(mrag_index* x, const uint32_t* rows, const uint16_t* codes, int64_t n) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_dtag_overflow: null index");
+    if (n < 0 || (n > 0 && (!rows || !codes))) return fail(MRAG_ERR_ARG, "mrag_set_dtag_overflow: bad arrays");
+    for (int64_t i = 1; i < n; ++i)
+        if (rows[i] < rows[i - 1]) return fail(MRAG_ERR_ARG, "mrag_set_dtag_overflow: pairs must be sorted by row");
+    std::unique_lock<std::shared_mutex> wl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_set_dtag_overflow: cudaSetDevice failed");
+    uint32_t* dr = nullptr;
+    uint16_t* dc = nullptr;
+    if (n > 0) {
+        CU(cudaMalloc(&dr, size_t(n) * 4));
+        cudaError_t e = cudaMalloc(&dc, size_t(n) * 2);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dr, rows, size_t(n) * 4, cudaMemcpyHostToDevice, x->wstream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dc, codes, size_t(n) * 2, cudaMemcpyHostToDevice, x->wstream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(x->wstream);
+        if (e != cudaSuccess) { cudaFree(dr); if (dc) cudaFree(dc); return fail(MRAG_ERR_CUDA, "mrag_set_dtag_overflow: %s", cudaGetErrorString(e)); }
+    }
+    if (x->over_rows) cudaFree(x->over_rows);
+    if (x->over_codes) cudaFree(x->over_codes);
+    x->over_rows = dr; x->over_codes = dc; x->n_over = n;
+    return MRAG_OK;
+}
+
 extern "C" int mrag_set_doc_jtags(mrag_index* x, int64_t first_doc, const uint64_t* bits, int64_t n_docs) {
     if (!x) return fail(MRAG_ERR_ARG, "mrag_set_doc_jtags: null index");
     if (first_doc < 0 || n_docs < 0) return fail(MRAG_ERR_ARG, "mrag_set_doc_jtags: negative range");
@@ -1466,14 +1520,16 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             mask = w->mask.p;
         }
         if (w->hmask.reserve(size_t(nq) * nwords)) return MRAG_ERR_OOM;
+        const DtagOver ov{x->over_rows, x->over_codes, x->n_over};
         hybrid_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(w->hyb.p, nq, x->feat, mask, x->cols.doc_idx, x->cols.source_type, x->doc_jtags,
-                                                                              x->n_jtag_docs, n, w->hmask.p, nwords);
+                                                                              x->n_jtag_docs, n, w->hmask.p, nwords, ov);
         LAUNCHED();
         CU(cudaEventRecord(ev.e[1], s));
         ScanArgs a{};
         a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p; a.ub = nullptr;
         a.part = w->part.p; a.k = k; a.kp = kp; a.P = grid;
         a.hmask = w->hmask.p; a.hwords = nwords; a.feat = x->feat; a.hyb = w->hyb.p; a.doc_idx = x->cols.doc_idx;
+        a.dtag_over = ov;
         a.authority = x->cols.authority; a.doc_jtags = x->doc_jtags; a.n_jtag_docs = x->n_jtag_docs;
         int q0 = 0;
         while (q0 < nq) {
@@ -1582,7 +1638,8 @@ extern "C" int mrag_dtag_mask(mrag_index* x, const mrag_filter* filter, const ui
         unsigned long long hc[40];
         cudaMemsetAsync(w->stats.p, 0, 40 * 8, s);
         if (n_codes) cudaMemcpyAsync(w->codes.p, dcodes, size_t(n_codes) * 2, cudaMemcpyHostToDevice, s);
-        dtag_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(x->feat, w->mask.p, n, w->codes.p, n_codes, w->hmask.p, w->stats.p);
+        dtag_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(x->feat, w->mask.p, n, w->codes.p, n_codes, w->hmask.p, w->stats.p,
+                                                                             DtagOver{x->over_rows, x->over_codes, x->n_over});
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaMemcpyAsync(host_mask_out, w->hmask.p, size_t(nwords) * 4, cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(hc, w->stats.p, size_t(n_codes + 1) * 8, cudaMemcpyDeviceToHost, s);
@@ -1741,6 +1798,125 @@ extern "C" int mrag_load(mrag_index** out, const char* path, int device, int64_t
     x->size = h.size; x->n_docs = h.n_docs; x->n_tag_docs = h.n_tag_docs; x->n_jtag_docs = h.n_jtag_docs; x->row_base = h.row_base;
     if (user_version) *user_version = h.user_version;
     *out = x;
+    return MRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate pool on the device (build_candidate_pool, corpus_search_agent.py:1762-1888)
+// ------------------------------------------------------------------------------------------
+extern "C" int mrag_pool_build(mrag_index* x, const mrag_pool_query* q, mrag_pool** out, int64_t counts[MRAG_POOL_LEVELS + 1]) {
+    if (!x || !q || !out) return fail(MRAG_ERR_ARG, "mrag_pool_build: null argument");
+    *out = nullptr;
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_pool_build: cudaSetDevice failed (no CPU path)");
+    mrag_pool* p = new (std::nothrow) mrag_pool();
+    if (!p) return fail(MRAG_ERR_OOM, "mrag_pool_build: host allocation failed");
+    p->idx = x;
+    p->n_docs = std::max<int64_t>(std::max<int64_t>(x->n_docs, 1), std::max(x->n_tag_docs, x->n_jtag_docs));   // documents may have tags before rows
+    p->words = ceil_div(p->n_docs, 32);
+    Workspace* w = acquire_ws(x, nullptr);
+    if (!w) { delete p; return fail(MRAG_ERR_OOM, "mrag_pool_build: cannot create a workspace"); }
+    cudaStream_t s = w->own_stream;
+    int rc = MRAG_OK;
+    unsigned long long hc[MRAG_POOL_LEVELS + 1] = {0, 0, 0, 0, 0};
+    if (cudaMalloc(&p->bits, size_t(MRAG_POOL_LEVELS) * p->words * 4) != cudaSuccess) rc = fail(MRAG_ERR_OOM, "mrag_pool_build: bitmap allocation failed");
+    if (rc == MRAG_OK && w->stats.reserve(40)) rc = MRAG_ERR_OOM;
+    if (rc == MRAG_OK) {
+        DevPoolQuery dq;
+        memset(&dq, 0, sizeof dq);
+        memcpy(dq.d_all, q->d_all, sizeof dq.d_all); memcpy(dq.p_all, q->p_all, sizeof dq.p_all);
+        memcpy(dq.j_all, q->j_all, sizeof dq.j_all); memcpy(dq.ahca, q->ahca, sizeof dq.ahca);
+        dq.has_j = q->has_j; dq.has_d = q->has_d; dq.has_p = q->has_p; dq.has_ahca = q->has_ahca;
+        cudaMemsetAsync(w->stats.p, 0, 40 * 8, s);
+        pool_cascade_kernel<<<unsigned(ceil_div(p->words * 32, 256)), 256, 0, s>>>(dq, x->doc_tags, x->n_tag_docs, x->doc_jtags, x->n_jtag_docs,
+                                                                                  p->n_docs, p->words, p->bits, w->stats.p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaMemcpyAsync(hc, w->stats.p, sizeof hc, cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_pool_build: %s", cudaGetErrorString(e));
+    }
+    release_ws(x, w, nullptr);
+    if (rc != MRAG_OK) { if (p->bits) cudaFree(p->bits); delete p; return rc; }
+    for (int l = 0; l < MRAG_POOL_LEVELS; ++l) { p->counts[l] = int64_t(hc[l]); if (counts) counts[l] = p->counts[l]; }
+    if (counts) counts[MRAG_POOL_LEVELS] = int64_t(hc[MRAG_POOL_LEVELS]);
+    *out = p;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_pool_select(mrag_pool* p, int level, int64_t cap, int64_t* n_kept) {
+    if (!p || !p->idx) return fail(MRAG_ERR_ARG, "mrag_pool_select: null pool");
+    if (level < 0 || level >= MRAG_POOL_LEVELS) return fail(MRAG_ERR_ARG, "mrag_pool_select: level %d not in [0,%d)", level, MRAG_POOL_LEVELS);
+    DeviceGuard g(p->idx->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_pool_select: cudaSetDevice failed");
+    p->level = level;
+    int64_t kept = p->counts[level];
+    if (cap >= 0 && kept > cap) {
+        unsigned long long* d_kept = nullptr;
+        unsigned long long h = 0;
+        CU(cudaMalloc(&d_kept, 8));
+        pool_cap_kernel<<<1, 1024, 0, p->idx->wstream>>>(p->bits + size_t(level) * p->words, p->words, cap, d_kept);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaMemcpyAsync(&h, d_kept, 8, cudaMemcpyDeviceToHost, p->idx->wstream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->idx->wstream);
+        cudaFree(d_kept);
+        if (e != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_pool_select: %s", cudaGetErrorString(e));
+        kept = int64_t(h);
+        p->counts[level] = kept;
+    }
+    if (n_kept) *n_kept = kept;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_pool_add_docs(mrag_pool* p, const uint32_t* docs, int64_t n) {
+    if (!p || !p->idx || p->level < 0) return fail(MRAG_ERR_ARG, "mrag_pool_add_docs: null pool or no level selected");
+    if (n < 0 || (n > 0 && !docs)) return fail(MRAG_ERR_ARG, "mrag_pool_add_docs: bad list");
+    if (n == 0) return MRAG_OK;
+    DeviceGuard g(p->idx->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_pool_add_docs: cudaSetDevice failed");
+    uint32_t* d = nullptr;
+    CU(cudaMalloc(&d, size_t(n) * 4));
+    cudaStream_t s = p->idx->wstream;
+    cudaError_t e = cudaMemcpyAsync(d, docs, size_t(n) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        pool_bitmap_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, s>>>(d, n, p->bits + size_t(p->level) * p->words, p->n_docs);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaStreamSynchronize(s);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_pool_add_docs: %s", cudaGetErrorString(e));
+    return MRAG_OK;
+}
+
+extern "C" int mrag_pool_docs(mrag_pool* p, uint32_t* out, int64_t max, int64_t* n) {
+    if (!p || !p->idx || p->level < 0 || !n) return fail(MRAG_ERR_ARG, "mrag_pool_docs: null pool / no level selected / null count");
+    *n = 0;
+    if (max < 0 || (max > 0 && !out)) return fail(MRAG_ERR_ARG, "mrag_pool_docs: bad buffer");
+    DeviceGuard g(p->idx->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_pool_docs: cudaSetDevice failed");
+    std::vector<uint32_t> h(size_t(p->words));
+    CU(cudaMemcpy(h.data(), p->bits + size_t(p->level) * p->words, size_t(p->words) * 4, cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (int64_t w = 0; w < p->words && k < max; ++w) {
+        uint32_t x = h[size_t(w)];
+        while (x && k < max) {
+            const int b = __builtin_ctz(x);
+            x &= x - 1;
+            out[k++] = uint32_t(w * 32 + b);
+        }
+    }
+    *n = k;
+    return MRAG_OK;
+}
+
+extern "C" int mrag_pool_destroy(mrag_pool* p) {
+    if (!p) return MRAG_OK;
+    if (p->idx) {
+        DeviceGuard g(p->idx->device);
+        if (p->bits) cudaFree(p->bits);
+    }
+    delete p;
     return MRAG_OK;
 }
 

@@ -131,6 +131,92 @@ __global__ void pool_bitmap_kernel(const uint32_t* __restrict__ pool, int64_t n_
     if (int64_t(d) < n_docs) atomicOr(&bits[d >> 5], 1u << (d & 31));
 }
 
+// ---- candidate-pool cascade (build_candidate_pool, corpus_search_agent.py:1762-1888): per document, which levels of
+//      J&D&P -> J&D -> AHCA&D -> AHCA it belongs to.  Pure bitset tests over the per-document tag sets that already sit in HBM.
+struct DevPoolQuery {
+    uint64_t d_all[MRAG_TAG_WORDS], p_all[MRAG_TAG_WORDS];   // bits (document d / p tag sets) that must ALL be present
+    uint64_t j_all[MRAG_JTAG_WORDS], ahca[MRAG_JTAG_WORDS];   // same over the j tag sets; the AHCA authority bit
+    int has_j, has_d, has_p, has_ahca;                        // kind named in the query and every code known to the vocabulary
+};
+
+// out: 4 document bitmaps of `words` u32 each (L1 J&D&P, L2 J&D, L3 AHCA&D, L4 AHCA); counts[0..3] their sizes,
+// counts[4] = documents carrying every d: code (the cascade tries L3 only when that set is not empty, :1851)
+__global__ void __launch_bounds__(256) pool_cascade_kernel(const __grid_constant__ DevPoolQuery q,
+                                                          const uint64_t* __restrict__ doc_tags, int64_t n_tag_docs,
+                                                          const uint64_t* __restrict__ doc_jtags, int64_t n_jtag_docs,
+                                                          int64_t n_docs, int64_t words,
+                                                          uint32_t* __restrict__ out, unsigned long long* __restrict__ counts) {
+    const int64_t d = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool J = false, D = false, P = false, A = false;
+    if (d < n_docs) {
+        if (d < n_tag_docs) {
+            bool dd = q.has_d != 0, pp = q.has_p != 0;
+#pragma unroll
+            for (int w = 0; w < MRAG_TAG_WORDS; ++w) {
+                const uint64_t t = doc_tags[size_t(d) * MRAG_TAG_WORDS + w];
+                dd &= (t & q.d_all[w]) == q.d_all[w];
+                pp &= (t & q.p_all[w]) == q.p_all[w];
+            }
+            D = dd; P = pp;
+        }
+        if (d < n_jtag_docs) {
+            bool jj = q.has_j != 0, aa = q.has_ahca != 0;
+#pragma unroll
+            for (int w = 0; w < MRAG_JTAG_WORDS; ++w) {
+                const uint64_t t = doc_jtags[size_t(d) * MRAG_JTAG_WORDS + w];
+                jj &= (t & q.j_all[w]) == q.j_all[w];
+                aa &= (t & q.ahca[w]) == q.ahca[w];
+            }
+            J = jj; A = aa;
+        }
+    }
+    const bool lv[4] = {J && D && P, J && D, A && D, A};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const uint32_t word = __ballot_sync(kFull, lv[l]);
+        if ((threadIdx.x & 31) == 0 && (d >> 5) < words) {
+            out[size_t(l) * words + (d >> 5)] = word;
+            if (word) atomicAdd(counts + l, (unsigned long long)__popc(word));
+        }
+    }
+    const uint32_t dword = __ballot_sync(kFull, D);
+    if ((threadIdx.x & 31) == 0 && dword) atomicAdd(counts + 4, (unsigned long long)__popc(dword));
+}
+
+// keep only the first `cap` set bits (ascending document index) of a bitmap: one block; writes the kept count
+__global__ void __launch_bounds__(1024) pool_cap_kernel(uint32_t* __restrict__ bits, int64_t words, int64_t cap, unsigned long long* kept) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (words + 1023) / 1024;
+    const int64_t lo = int64_t(t) * per < words ? int64_t(t) * per : words;
+    const int64_t hi = lo + per < words ? lo + per : words;
+    long long c = 0;
+    for (int64_t w = lo; w < hi; ++w) c += __popc(bits[w]);
+    part[t] = c;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {            // inclusive scan
+        const long long v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long before = part[t] - c;
+    for (int64_t w = lo; w < hi; ++w) {
+        uint32_t x = bits[w];
+        const int n = __popc(x);
+        if (before >= cap) x = 0u;
+        else if (before + n > cap) {
+            int keep = int(cap - before);
+            uint32_t y = 0u;
+            while (keep-- > 0) { const uint32_t low = x & (0u - x); y |= low; x ^= low; }
+            x = y;
+        }
+        bits[w] = x;
+        before += n;
+    }
+    if (t == 1023) *kept = (unsigned long long)(part[1023] < (long long)cap ? part[1023] : (long long)cap);
+}
+
 __global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n, uint32_t doc, uint32_t* valid,
                                  uint32_t* live, unsigned long long* n_hit) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;

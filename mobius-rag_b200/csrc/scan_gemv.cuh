@@ -48,6 +48,7 @@ struct ScanArgs {
     const uint32_t* hmask;
     int64_t hwords;
     const mrag_chunkfeat* feat;
+    DtagOver dtag_over;
     const DevHyb* hyb;
     const uint32_t* doc_idx;
     const uint8_t* authority;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) scan_gemv_kernel(const ScanAr
                             const float cs = (nx > 0.0f) ? dotL * inv * qinvL : CUDART_NAN_F;
                             // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
                             const float c01 = (cs == cs) ? cs : 1.0f;
-                            hyb_s = hybrid_score(hq[lane], f, hybrid_eval(hq[lane], f, jt), c01, auth_code);
+                            hyb_s = hybrid_score(hq[lane], f, hybrid_eval(hq[lane], f, jt, r[j], a.dtag_over), c01, auth_code);
                         }
                     }
 #pragma unroll

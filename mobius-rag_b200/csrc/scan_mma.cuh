@@ -33,7 +33,9 @@
 // and ONE bulk copy (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the leader's mbarrier: 16 KB per
 // tile against 192 KB of corpus) moves the 64 x 64 sums into the leader's shared memory; the leader adds them to its
 // own partials and runs the select.  Each CTA thus selects every other tile of the pair and writes its own candidate
-// lists, exactly like a CTA of the one-CTA kernel.  (A first version stored the sums with st.shared::cluster and
+// lists, exactly like a CTA of the one-CTA kernel.  Sending is the job of two EXTRA warps (6, 7: tensor-memory quarters
+// 2, 3 like the hi warps), so a CTA's select of tile i and its send of tile i + 1 overlap; with the hi warps doing both
+// the two CTAs ping-ponged (A sends -> B selects -> B sends -> A selects ...) and one tile cost send + copy + select.  (A first version stored the sums with st.shared::cluster and
 // signalled with release / acquire at cluster scope: MEMBAR.ALL.GPU + CCTL.IVALL per tile, 0.47 of the HBM rate.)
 #pragma once
 #include "common.cuh"
@@ -56,6 +58,7 @@ namespace mrag {
 #define MRAG_STAMPS 0
 #endif
 constexpr int kMmaThreads = 192;
+constexpr int kMmaKsThreads = 256;        // k-split pair: two more warps (6, 7) that SEND this CTA's partials on the tiles its peer leads
 constexpr int kMmaTileRows = 64;          // UMMA N
 constexpr int kMmaKBlock = 64;            // bf16 elements per smem row = 128 B = one swizzle span
 constexpr int kMmaStageBytes = kMmaTileRows * 128;
@@ -183,7 +186,7 @@ MRAG_DEVINL void ks_bulk_copy_to_peer(uint32_t dst_cluster_addr, const void* src
                  "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
                  : "memory");
 }
-MRAG_DEVINL void ks_bar_hi() { asm volatile("bar.sync 1, 64;" ::: "memory"); }      // the 64 threads of the two hi warps
+MRAG_DEVINL void ks_bar_send() { asm volatile("bar.sync 1, 64;" ::: "memory"); }    // the 64 threads of the two send warps
 
 MRAG_DEVINL void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
     const uint64_t evict_first = 0x12F0000000000000ull;      // each corpus byte is used once
@@ -364,7 +367,7 @@ constexpr int kMmaRegK = 16;
 // SO (score only, KREG > 0): the sampling pass needs a bound, not rows: 32-bit orderable scores in the
 //           registers (half the insertion work); the lists it writes carry synthetic unique low words.
 template <int KREG, bool SO = false, bool KS = false>
-__global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
+__global__ void __launch_bounds__(KS ? kMmaKsThreads : kMmaThreads, 1) scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, const MmaArgs a) {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     // SWIZZLE_128B tiles need 1024-byte alignment; stay in the shared address space (no integer casts)
     unsigned char* smem = mma_smem + ((1024u - (smem_u32(mma_smem) & 1023u)) & 1023u);
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
     const bool hi_part = quarter >= 2;
 
     // ---- queries -> tensor memory (epilogue warps; lane of TMEM = thread)
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         const bool live = qi < nq_eff;
         const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
         const float* qrow = a.q + size_t(qsrc) * a.ld + size_t(kb0) * kMmaKBlock;
@@ -542,6 +545,48 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
         }
         __syncwarp();
         stamp(4);
+    } else if (KS && warp >= 6) {
+        // ================= KS send warps (6,7): on the tiles the PEER leads, hi + lo partials of my k-blocks ->
+        //                   staging buffer -> one bulk copy into the leader's shared memory =================
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        uint32_t it = 0;
+        uint2 m = tile_mask(t_first);
+        for (int64_t t = t_first; t < num_tiles; t += G) {
+            const uint2 mn = tile_mask(t + G);
+            if ((m.x | m.y) != 0u) {
+                if ((it & 1u) != ks_rank) {
+                    const int as = int(it & 1u), xs = as;            // slot and phase are functions of the tile count
+                    const uint32_t aph = (it >> 1) & 1u, yj = it >> 1;
+                    mbar_wait(&tfull_bar[as], aph, slp);
+                    tc_fence_after();
+                    mbar_wait(&xfull_bar[xs], aph, slp);
+                    const float* xb = xbuf + size_t(xs) * 64 * 64;
+                    float part[64];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t d[32];
+                        MRAG_TMEM_LD32(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows + h * 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) part[h * 32 + c] = __uint_as_float(d[c]) + xb[(h * 32 + c) * 64 + qi];
+                    }
+                    // the accumulator and the exchange slot go back BEFORE anything that depends on the peer
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                    mbar_arrive(&xempty_bar[xs]);
+                    if (yj > 0) mbar_wait(&yempty_bar[0], (yj - 1u) & 1u, slp);      // the leader has consumed my previous send: sbuf and its ybuf are free
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) sbuf[c * 64 + qi] = part[c];
+                    fence_proxy_async();                                     // my stores -> visible to the bulk copy engine
+                    ks_bar_send();
+                    if (warp == 6 && lane == 0)
+                        ks_bulk_copy_to_peer(ks_map_to_cta(smem_u32(ybuf), ks_rank ^ 1u), sbuf, 64 * 64 * 4,
+                                             ks_map_to_cta(smem_u32(&yfull_bar[0]), ks_rank ^ 1u));
+                }
+                ++it;
+            }
+            m = mn;
+        }
     } else if (!hi_part) {
         // ================= lo epilogue (warps 4,5): TMEM lanes 0..63 -> exchange buffer =================
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
@@ -628,34 +673,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) scan_mma_kernel(const __grid_c
                 const uint32_t yj = it >> 1;
                 if constexpr (KS) {
                     if ((it & 1u) != ks_rank) {
-                        // ---- helper of this tile: hi + lo partials of my k-blocks -> staging buffer -> the leader's shared memory
-                        mbar_wait(&tfull_bar[as], aph, slp);
-                        tc_fence_after();
-                        mbar_wait(&xfull_bar[xs], xph, slp);
-                        const float* xb = xbuf + size_t(xs) * 64 * 64;
-                        float part[64];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint32_t d[32];
-                            MRAG_TMEM_LD32(d, tmem_base + lane_addr + uint32_t(kMmaDCol0 + as * kMmaTileRows + h * 32));
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) part[h * 32 + c] = __uint_as_float(d[c]) + xb[(h * 32 + c) * 64 + qi];
-                        }
-                        // the accumulator and the exchange slot go back BEFORE anything that depends on the peer
-                        tc_fence_before();
-                        mbar_arrive(&tempty_bar[as]);
+                        // the peer leads this tile; my share of it is sent by warps 6, 7 (below)
                         if (++as == 2) { as = 0; aph ^= 1u; }
-                        mbar_arrive(&xempty_bar[xs]);
                         if (++xs == 2) { xs = 0; xph ^= 1u; }
-                        if (yj > 0) mbar_wait(&yempty_bar[0], (yj - 1u) & 1u, slp);      // the leader has consumed my previous send: sbuf and its ybuf are free
-#pragma unroll
-                        for (int c = 0; c < 64; ++c) sbuf[c * 64 + qi] = part[c];
-                        fence_proxy_async();                                     // my stores -> visible to the bulk copy engine
-                        ks_bar_hi();
-                        if (warp == 2 && lane == 0)
-                            ks_bulk_copy_to_peer(ks_map_to_cta(smem_u32(ybuf), ks_rank ^ 1u), sbuf, 64 * 64 * 4,
-                                                 ks_map_to_cta(smem_u32(&yfull_bar[0]), ks_rank ^ 1u));
                         ++it;
                         m = mn;
                         continue;

@@ -93,43 +93,62 @@ CONTACT_VALUE_RE = re.compile(
 
 
 # ---------------------------------------------------------------------------------------------
-# text rules
+# text rules: the haystacks `_rerank` substring-tests (corpus_search.py:1844-1906), produced from cached pieces
 # ---------------------------------------------------------------------------------------------
-def normalise_for_haystack(s) -> str:                        # :1844-1847
-    if not s:
-        return ""
-    return " ".join(str(s).lower().split())
+_SEP = " | "
+_PATHLIKE = str.maketrans({"_": " ", "-": " ", "/": " ", ".": " "})      # separators that pack several words into one token
+_TAGLIKE = str.maketrans({".": " ", "_": " "})
 
 
-def body_haystack(c: dict) -> str:                           # :1850-1856
-    parts = [normalise_for_haystack(c.get("text"))]
-    nbr = normalise_for_haystack(c.get("_neighbor_text"))
-    if nbr:
-        parts.append(nbr)
-    return " | ".join(p for p in parts if p)
+def _squash(value) -> str:
+    """lower case, runs of white space -> one blank; '' for None / empty (what every haystack piece goes through)"""
+    return " ".join(str(value).lower().split()) if value else ""
 
 
-def meta_haystack(c: dict) -> str:                           # :1859-1906
-    parts: list[str] = []
-    for key in ("document_name", "document_filename", "document_display_name", "payer", "state", "section_path",
-                "chapter_path", "summary"):
-        v = c.get(key)
-        if not v:
-            continue
-        parts.append(normalise_for_haystack(v))
-        if key in ("document_filename", "section_path", "chapter_path"):
-            split = normalise_for_haystack(str(v).replace("_", " ").replace("-", " ").replace("/", " ").replace(".", " "))
-            if split:
-                parts.append(split)
-    for tag_key in ("_doc_d_tags", "_doc_j_tags", "_doc_p_tags"):
-        for tag in (c.get(tag_key) or []):
-            leaf = str(tag).split(".")[-1].replace("_", " ").strip().lower()
-            if leaf:
-                parts.append(leaf)
-            full = str(tag).replace(".", " ").replace("_", " ").strip().lower()
-            if full and full != leaf:
-                parts.append(full)
-    return " | ".join(p for p in parts if p)
+def _tag_words(tags) -> list[str]:
+    """An inherited document tag contributes its leaf (``a.b.prior_authorization`` -> ``prior authorization``) and, when
+    different, its whole dotted path with the separators blanked (:1893-1905)."""
+    words: list[str] = []
+    for tag in tags or ():
+        text = str(tag)
+        leaf = text.rsplit(".", 1)[-1].replace("_", " ").strip().lower()
+        whole = text.translate(_TAGLIKE).strip().lower()
+        if leaf:
+            words.append(leaf)
+        if whole and whole != leaf:
+            words.append(whole)
+    return words
+
+
+def _field_pieces(value, pathlike: bool) -> list[str]:
+    """one metadata field -> its squashed text, plus a separator-blanked copy for filenames / paths (:1879-1890)"""
+    if not value:
+        return []
+    pieces = [_squash(value)]
+    if pathlike:
+        pieces.append(_squash(str(value).translate(_PATHLIKE)))
+    return [p for p in pieces if p]
+
+
+def body_haystack(c: dict) -> str:
+    """the chunk body and, when the enrichment step attached them, its neighbour paragraphs"""
+    return _SEP.join(p for p in (_squash(c.get("text")), _squash(c.get("_neighbor_text"))) if p)
+
+
+def meta_haystack(c: dict) -> str:
+    """document-level text that belongs to the chunk: names, payer / state, paths, summary, inherited tag words --
+    in the reference's field order, so the joined string is the same string"""
+    pieces: list[str] = []
+    for key, pathlike in (("document_name", False), ("document_filename", True), ("document_display_name", False),
+                          ("payer", False), ("state", False), ("section_path", True), ("chapter_path", True), ("summary", False)):
+        pieces += _field_pieces(c.get(key), pathlike)
+    for key in ("_doc_d_tags", "_doc_j_tags", "_doc_p_tags"):
+        pieces += _tag_words(c.get(key))
+    return _SEP.join(pieces)
+
+
+def normalise_for_haystack(s) -> str:
+    return _squash(s)
 
 
 def jpd_hits(text: str) -> tuple[list[int], bool]:
@@ -174,14 +193,16 @@ def confidence_label(score: float) -> str:                   # :2307-2314
 # the table with text features
 # ---------------------------------------------------------------------------------------------
 class HybridTable:
-    """PublishedTable + the per-row features / document j-tags the fused rerank reads.
+    """PublishedTable + the per-row features the fused rerank reads.
 
-    ``phrases`` is the phrase dictionary: the required phrases of the query bank (<= 128), fixed when
-    the features are built.  A query phrase outside the dictionary is treated as present nowhere."""
+    ``phrases`` is the phrase dictionary (<= 128 entries): the required phrases the features carry a presence bit for.
+    A query phrase outside it is ADDED on first use (one pass over the texts), never silently treated as absent.
+    Features are derived data: a change of a document's tags (d / j / p: they feed the meta haystack) or of the
+    promoted set marks the rows concerned dirty and ``build_features`` recomputes them."""
 
     def __init__(self, table: PublishedTable, phrases: Sequence[str]):
         self.table = table
-        self.phrases = []
+        self.phrases: list[str] = []
         for p in phrases:
             p = (p or "").lower()
             if p and p not in self.phrases:
@@ -190,32 +211,40 @@ class HybridTable:
             raise ValueError(f"phrase dictionary holds at most {N.MRAG_PHRASE_WORDS * 64} phrases")
         self.phrase_index = {p: i for i, p in enumerate(self.phrases)}
         self.dcodes: dict[str, int] = {}       # chunk d-tag key -> code >= 1
-        self.jbits: dict[str, int] = {}        # document j-tag key -> bit
-        self.doc_j_tags: dict[str, list[str]] = {}
         self.promoted: set[int] = set()
         self._built = 0
+        self._dirty_rows: set[int] = set()
+        self._dirty_docs: set[int] = set()
+        self._overflow: dict[int, list[int]] = {}      # row -> d-tag codes beyond the four inline slots
+        self._id_rank: np.ndarray | None = None        # row -> rank of its id in ascending id order (the d-tag arm's ORDER BY)
+        table.doc_listeners.append(self._dirty_docs.add)
 
-    # -- document j-tags (document_tags.j_tags, app/models.py:535-537) --------------------------
+    # -- document j-tags live in the table (document_tags.j_tags, app/models.py:535-537) ----------
+    @property
+    def jbits(self) -> dict[str, int]:
+        return self.table.vocab._jtag_bit
+
+    @property
+    def doc_j_tags(self) -> dict[str, list]:
+        return self.table.doc_j_tags
+
     def set_document_j_tags(self, document_id: str, j_tags: Sequence[str]) -> None:
-        t = self.table
-        with t.lock:
-            self.doc_j_tags[str(document_id)] = list(j_tags or ())
-            bits = np.zeros((1, N.MRAG_JTAG_WORDS), dtype=np.uint64)
-            for key in j_tags or ():
-                b = self.jbits.setdefault(key, len(self.jbits))
-                if b >= N.MRAG_JTAG_WORDS * 64:
-                    raise ValueError("too many distinct j-tag codes")
-                bits[0, b >> 6] |= np.uint64(1 << (b & 63))
-            t.index.set_doc_jtags(t._doc(str(document_id)), bits)
+        self.table.set_document_j_tags(document_id, j_tags)
+
+    def set_promoted(self, rows: Sequence[int]) -> None:
+        """rows promoted from a seed / inheriting a BM25 score: exempt from the coverage floor (:2205-2208)"""
+        new = set(int(r) for r in rows)
+        self._dirty_rows |= (new ^ self.promoted)
+        self.promoted = new
 
     def candidate_dict(self, r: int) -> dict:
         """The dict `_rerank` would see for row r before scoring (base dict + inherited doc tags)."""
         t = self.table
         c = _row_to_base_dict(t, r)
         did = t.document_id[r]
-        if did in t.doc_d_tags or did in self.doc_j_tags:
+        if did in t.doc_d_tags or did in t.doc_j_tags:
             c["_doc_d_tags"] = sorted(t.doc_d_tags.get(did, ()))
-            c["_doc_j_tags"] = list(self.doc_j_tags.get(did, ()))
+            c["_doc_j_tags"] = list(t.doc_j_tags.get(did, ()))
             c["_doc_p_tags"] = sorted(t.doc_p_tags.get(did, ()))
         if r in self.promoted:
             c["_promoted_from_seed"] = "seed"
@@ -230,30 +259,97 @@ class HybridTable:
             if p in body or (meta and p in meta):
                 bits[i >> 6] |= 1 << (i & 63)
         hits, short = jpd_hits(body)
+        codes = [self.dcodes.setdefault(key, len(self.dcodes) + 1) for key in (c.get("chunk_d_tags") or {})]
+        if len(self.dcodes) >= 0xFFFF:
+            raise ValueError("more than 65534 distinct chunk d-tag keys")
         flags = (N.CF_SHORT_TEXT if short else 0) | (N.CF_CONTACT_VALUE if CONTACT_VALUE_RE.search(c.get("text") or "") else 0) \
-            | (N.CF_PROMOTED if r in self.promoted else 0)
-        dt = [0, 0, 0, 0]
-        for j, key in enumerate(list(c.get("chunk_d_tags") or {})[:4]):
-            dt[j] = self.dcodes.setdefault(key, len(self.dcodes) + 1)
-        return bits, [min(255, h) for h in hits], flags, length_score(c.get("text") or ""), dt
+            | (N.CF_PROMOTED if r in self.promoted else 0) | (N.CF_DTAG_OVERFLOW if len(codes) > 4 else 0)
+        if len(codes) > 4:
+            self._overflow[r] = codes[4:]                 # `chunk_d_tags ? key` matches ANY key: nothing is dropped
+        else:
+            self._overflow.pop(r, None)
+        return bits, [min(255, h) for h in hits], flags, length_score(c.get("text") or ""), (codes + [0, 0, 0, 0])[:4]
+
+    def _features_of(self, rows: Sequence[int]) -> np.ndarray:
+        feat = np.zeros(len(rows), dtype=FEAT_DTYPE)
+        for i, r in enumerate(rows):
+            bits, hits, flags, ls, dt = self.chunk_features(int(r))
+            feat["phrase_bits"][i] = bits
+            feat["jpd_hits"][i] = hits
+            feat["flags"][i] = flags
+            feat["length_score"][i] = ls
+            feat["dtags"][i] = dt
+        return feat
 
     def build_features(self) -> None:
-        """(Re)compute the features of every row not yet covered and upload them."""
+        """Compute the features of every row not yet covered and of every row whose inputs changed; upload them."""
         t = self.table
         with t.lock:
             n = len(t)
-            if n == self._built:
-                return
-            feat = np.zeros(n - self._built, dtype=FEAT_DTYPE)
-            for i, r in enumerate(range(self._built, n)):
-                bits, hits, flags, ls, dt = self.chunk_features(r)
-                feat["phrase_bits"][i] = bits
-                feat["jpd_hits"][i] = hits
-                feat["flags"][i] = flags
-                feat["length_score"][i] = ls
-                feat["dtags"][i] = dt
-            t.index.set_chunk_features(self._built, feat)
-            self._built = n
+            over_before = dict(self._overflow)
+            stale = set(r for r in self._dirty_rows if r < self._built)
+            if self._dirty_docs:
+                docs = np.fromiter(self._dirty_docs, dtype=np.uint32)
+                stale |= set(np.flatnonzero(np.isin(t.row_doc[:self._built], docs)).tolist())
+            self._dirty_rows.clear()
+            self._dirty_docs.clear()
+            if stale:
+                rows = np.asarray(sorted(stale), dtype=np.int64)
+                cuts = np.flatnonzero(np.diff(rows) != 1) + 1          # upload run by run (a document's rows are contiguous)
+                for run in np.split(rows, cuts):
+                    t.index.set_chunk_features(int(run[0]), self._features_of(run))
+            if n > self._built:
+                t.index.set_chunk_features(self._built, self._features_of(range(self._built, n)))
+                self._built = n
+            if self._overflow != over_before:
+                self._upload_overflow()
+
+    def _upload_overflow(self) -> None:
+        pairs = sorted((r, c) for r, codes in self._overflow.items() for c in codes)
+        rows = np.asarray([p[0] for p in pairs], dtype=np.uint32)
+        codes = np.asarray([p[1] for p in pairs], dtype=np.uint16)
+        ix = self.table.index
+        if hasattr(ix, "shards"):
+            raise NotImplementedError("chunk d-tag overflow on a multi-shard table")
+        N.check(ix._lib.mrag_set_dtag_overflow(ix._h, rows.ctypes.data if rows.size else None,
+                                               codes.ctypes.data if codes.size else None, int(rows.size)))
+
+    def ensure_phrases(self, phrases: Sequence[str]) -> None:
+        """Every required phrase of a query must be in the dictionary.  New ones are added (their presence bit is computed
+        for all rows: one substring pass over the haystacks) -- `_rerank` would substring-test them, so they must not be
+        treated as absent.  A full dictionary is an error, not a silently wrong coverage."""
+        new = []
+        for p in phrases or ():
+            p = (p or "").lower()
+            if p and p not in self.phrase_index and p not in new:
+                new.append(p)
+        if not new:
+            return
+        if len(self.phrases) + len(new) > N.MRAG_PHRASE_WORDS * 64:
+            raise ValueError(f"phrase dictionary is full ({N.MRAG_PHRASE_WORDS * 64}); rebuild the HybridTable with the query bank's phrases")
+        with self.table.lock:
+            for p in new:
+                self.phrase_index[p] = len(self.phrases)
+                self.phrases.append(p)
+            self._dirty_rows |= set(range(self._built))            # recomputed by the next build_features()
+
+    def id_rank(self) -> np.ndarray:
+        """row -> position of its id in ascending id order (uuid order == order of the canonical lowercase text), cached
+        until the table grows: the d-tag arm orders by (authority tier, id) and must not sort strings per call."""
+        t = self.table
+        n = len(t)
+        if self._id_rank is None or self._id_rank.shape[0] != n:
+            col = t.id
+            lens = np.diff(col.off[:n + 1])
+            if n and (lens == lens[0]).all() and lens[0] > 0:
+                keys = col.buf[:int(col.off[n])].reshape(n, int(lens[0])).view(f"S{int(lens[0])}").ravel()
+            else:
+                keys = np.asarray([col[i] or "" for i in range(n)], dtype=object)
+            order = np.argsort(keys, kind="stable")
+            rank = np.empty(n, dtype=np.int64)
+            rank[order] = np.arange(n)
+            self._id_rank = rank
+        return self._id_rank
 
     # -- query side -----------------------------------------------------------------------------
     def hybrid_query(self, query: str, required_phrases, required_phrase_weights, required_phrase_tag_codes) -> N.HybridQuery:
@@ -309,6 +405,7 @@ def hybrid_rerank(ht: HybridTable, query_embedding: Sequence[float], k: int, que
     0.6 x best decay (:2258-2285) is exact: every category gets its own query slot in the fused scan, so
     each category's best and its top k are known; the host decays each list and merges them."""
     t = ht.table
+    ht.ensure_phrases(required_phrases)
     ht.build_features()
     q = to_float4(query_embedding)
     base = ht.hybrid_query(query, required_phrases, required_phrase_weights, required_phrase_tag_codes)
@@ -377,22 +474,41 @@ def dtag_arm(ht: "HybridTable", dtag_keys: Sequence[str], k: int, filters: Any =
     try:
         ht.build_features()
         keys = list(dtag_keys)
-        if len(keys) > 32:
-            raise ValueError("at most 32 d-tag keys")
-        codes = (C.c_uint16 * max(1, len(keys)))(*[ht.dcodes.get(key, 0xFFFF) for key in keys])   # 0xFFFF: a key no chunk has
         flt: Filter = t.filter_corpus(filters, include_document_ids)
         n = len(t)
-        mask = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
-        counts = (C.c_int64 * (len(keys) + 1))()
-        N.check(t.index._lib.mrag_dtag_mask(t.index._h, flt.ref() if flt.active else None, codes, len(keys),
-                                            mask.ctypes.data, counts))
-        rows = np.flatnonzero(np.unpackbits(mask.view(np.uint8), bitorder="little")[:n])
+        words = (n + 31) // 32
+        mask = np.zeros(words + 1, dtype=np.uint32)
+        n_total, per_key = 0, {}
+        for lo in range(0, len(keys), 32):                          # the kernel takes 32 codes per pass: any number of keys
+            part = keys[lo:lo + 32]
+            codes = (C.c_uint16 * len(part))(*[ht.dcodes.get(key, 0xFFFF) for key in part])   # 0xFFFF: a key no chunk has
+            m = np.zeros(words + 1, dtype=np.uint32)
+            counts = (C.c_int64 * (len(part) + 1))()
+            N.check(t.index._lib.mrag_dtag_mask(t.index._h, flt.ref() if flt.active else None, codes, len(part),
+                                                m.ctypes.data, counts))
+            mask |= m
+            n_total = int(counts[0])
+            for i, key in enumerate(part):
+                per_key[key] = int(counts[1 + i])
+        # matching rows from the non-zero words only (no N-sized temporary)
+        wz = np.flatnonzero(mask[:words])
+        bits = (mask[wz, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        rows = (wz[:, None] * 32 + np.arange(32)[None, :])[bits.astype(bool)]
+        rows = rows[rows < n]
         idf_weights: dict[str, float] = {}
         if idf_mode:
-            n_total = max(1, int(counts[0]) or 1)
-            for i, key in enumerate(keys):
-                idf_weights[key] = math.log(n_total / max(1, int(counts[1 + i]) or 1))
-        order = sorted(rows.tolist(), key=lambda r: (_authority_tier(t.document_authority_level[r]), t.id[r]))[:max(0, int(k))]
+            for key in keys:
+                idf_weights[key] = math.log(max(1, n_total or 1) / max(1, per_key.get(key, 0) or 1))
+        # ORDER BY CASE authority tier, id LIMIT k -- on integer keys: tier from the authority code, id through its cached rank
+        tier_of_code = np.full(256, 2, dtype=np.int64)
+        for code, level in enumerate(t.vocab.authority.values):
+            tier_of_code[code] = _authority_tier(level)
+        key64 = tier_of_code[t.document_authority_level.view()[rows]] * max(n, 1) + ht.id_rank()[rows]
+        kk = max(0, int(k))
+        if rows.size > kk > 0:
+            sel = np.argpartition(key64, kk - 1)[:kk]
+            rows, key64 = rows[sel], key64[sel]
+        order = rows[np.argsort(key64, kind="stable")][:kk].tolist()
     except Exception as exc:                       # fail-soft like the reference (:1684-1686)
         import logging
         logging.getLogger(__name__).warning("corpus_search dtag arm failed: %s", exc)
@@ -411,35 +527,51 @@ def dtag_arm(ht: "HybridTable", dtag_keys: Sequence[str], k: int, filters: Any =
 
 
 def rrf_merge(arms: dict[str, list[dict]], k: int = RRF_K, search_id: str = "") -> list[dict]:
-    """`_rrf_merge` (corpus_search.py:1708-1766): sum over arms of idf / (k + rank), first arm's dict wins,
-    blanks filled from later arms, ordered by (-rrf, best rank); `similarity` becomes the RRF score."""
-    fused: dict[str, dict] = {}
-    for arm_name, ranked in arms.items():
-        for rank0, chunk in enumerate(ranked):
-            cid = chunk.get("id") or ""
+    """Reciprocal rank fusion with the reference's outputs (`_rrf_merge`, corpus_search.py:1708-1766), done as array
+    accumulation over chunk slots.
+
+    Pass 1 gives every distinct chunk id a slot in first-seen order and records, per arm, the (slot, rank, weight,
+    similarity) of each hit; the per-slot score  sum over arms of  idf / (k + rank)  is accumulated in that same
+    order, so the float sums are the reference's.  Pass 2 builds one dict per slot: the first arm's dict wins, blanks
+    (None, '', []) are filled from later arms.  Order: score descending, best rank ascending, first-seen order last
+    (a stable sort over the slots); `similarity` becomes the fused score."""
+    BOOKKEEPING = ("retrieval_arms", "arm_ranks", "arm_scores", "rrf_score")
+    slot_of: dict[str, int] = {}
+    merged: list[dict] = []
+    score: list[float] = []
+    for arm, ranked in arms.items():
+        for rank, hit in enumerate(ranked, start=1):
+            cid = hit.get("id") or ""
             if not cid:
                 continue
-            rank1 = rank0 + 1
-            contribution = float(chunk.get("_dtag_idf") or 1.0) / (k + rank1)
-            f = fused.get(cid)
-            if f is None:
-                f = fused[cid] = dict(chunk)
-                f["retrieval_arms"] = [arm_name]
-                f["arm_ranks"] = {arm_name: rank1}
-                f["arm_scores"] = {arm_name: float(chunk.get("similarity", 0.0))}
-                f["rrf_score"] = contribution
-            else:
-                for key, val in chunk.items():
-                    if key in ("retrieval_arms", "arm_ranks", "arm_scores", "rrf_score"):
-                        continue
-                    if f.get(key) in (None, "", []) and val not in (None, "", []):
-                        f[key] = val
-                if arm_name not in f["retrieval_arms"]:
-                    f["retrieval_arms"].append(arm_name)
-                f["arm_ranks"][arm_name] = rank1
-                f["arm_scores"][arm_name] = float(chunk.get("similarity", 0.0))
-                f["rrf_score"] += contribution
-    out = sorted(fused.values(), key=lambda c: (-float(c.get("rrf_score", 0.0)), min(c.get("arm_ranks", {}).values() or [999])))
-    for c in out:
-        c["similarity"] = float(c.get("rrf_score", 0.0))
+            share = float(hit.get("_dtag_idf") or 1.0) / (k + rank)
+            sim = float(hit.get("similarity", 0.0))
+            slot = slot_of.get(cid)
+            if slot is None:
+                slot_of[cid] = len(merged)
+                first = dict(hit)
+                first.update(retrieval_arms=[arm], arm_ranks={arm: rank}, arm_scores={arm: sim})
+                merged.append(first)
+                score.append(share)
+                continue
+            entry = merged[slot]
+            for field_name, value in hit.items():
+                if field_name not in BOOKKEEPING and entry.get(field_name) in (None, "", []) and value not in (None, "", []):
+                    entry[field_name] = value
+            if arm not in entry["retrieval_arms"]:
+                entry["retrieval_arms"].append(arm)
+            entry["arm_ranks"][arm] = rank
+            entry["arm_scores"][arm] = sim
+            score[slot] += share
+    if not merged:
+        return []
+    total = np.asarray(score, dtype=np.float64)
+    best = np.fromiter((min(e["arm_ranks"].values()) for e in merged), dtype=np.int64, count=len(merged))
+    order = np.lexsort((best, -total))                   # stable: ties keep first-seen order, like sorted() over the dict
+    out = []
+    for slot in order:
+        entry = merged[int(slot)]
+        entry["rrf_score"] = float(total[slot])
+        entry["similarity"] = entry["rrf_score"]
+        out.append(entry)
     return out

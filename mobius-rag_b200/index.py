@@ -91,6 +91,12 @@ class Filter:
         self.s.n_doc_pool = int(self._pool.size)
         return self
 
+    # corpus_search_agent.py:1762-1888: the pool is a document bitmap resident on the device (mrag_pool_build)
+    def pool_handle(self, handle) -> "Filter":
+        self.s.flags |= N.F_DOC_POOL_HANDLE
+        self.s.pool = handle
+        return self
+
     # corpus_search.py:1478-1496
     def tag_strict(self, state_codes: Iterable[int] = (), program_codes: Iterable[int] = (),
                    payer_codes: Iterable[int] = ()) -> "Filter":

@@ -56,13 +56,13 @@ class _DocIdCol:
         self.t = table
 
     def __len__(self) -> int:
-        return self.t._n
+        return self.t._host_n
 
     def __getitem__(self, i: int) -> str:
         i = int(i)
         if i < 0:
-            i += self.t._n
-        if not 0 <= i < self.t._n:
+            i += self.t._host_n
+        if not 0 <= i < self.t._host_n:          # host columns are written BEFORE the device rows become searchable
             raise IndexError(i)
         return self.t.doc_ids[int(self.t.row_doc[i])]
 
@@ -83,6 +83,7 @@ class PublishedTable:
         self.vocab = vocab
         self.lock = threading.RLock()
         self._n = 0                                  # rows whose host columns AND device rows exist
+        self._host_n = 0                             # rows whose host columns exist (>= _n while an insert is in flight)
         self.id = StrCol()
         self.source_id = StrCol()
         self.row_doc = np.zeros(1024, dtype=np.uint32)
@@ -99,6 +100,8 @@ class PublishedTable:
         self.doc_ids: list[str] = []                 # doc index -> document_id (indices are never reused)
         self.doc_d_tags: dict[str, set] = {}
         self.doc_p_tags: dict[str, set] = {}
+        self.doc_j_tags: dict[str, list] = {}
+        self.doc_listeners: list = []                # callables(doc_idx): a document's tags changed (derived row features go stale)
 
     def __len__(self) -> int:
         return self._n
@@ -173,6 +176,7 @@ class PublishedTable:
             if first + n > self.row_doc.shape[0]:
                 self.row_doc = np.concatenate([self.row_doc, np.zeros(max(first + n, self.row_doc.shape[0]), dtype=np.uint32)])
             self.row_doc[first:first + n] = docs
+            self._host_n = first + n
             for col, _, _ in _CODED:
                 getattr(self, col).extend(codes[col])
             for c in HYDRATE_COLS:
@@ -188,12 +192,30 @@ class PublishedTable:
             return first
 
     def _truncate(self, n: int) -> None:
+        self._host_n = n
         for col in (self.id, self.source_id, self.source_type, self.document_payer, self.document_state,
                     self.document_program, self.document_authority_level, *self.extra.values()):
             col.truncate(n)
 
-    def set_document_tags(self, document_id: str, d_tags: Sequence[str] | None, p_tags: Sequence[str] | None) -> None:
-        """UPSERT one document_tags row (keys of d_tags / p_tags, app/models.py:525-543)."""
+    def set_document_j_tags(self, document_id: str, j_tags: Sequence[str] | None) -> None:
+        """document_tags.j_tags of one document (app/models.py:535-537): binary coverage credit of `_rerank` and the J side
+        of the candidate-pool cascade."""
+        with self.lock:
+            self.doc_j_tags[str(document_id)] = list(j_tags or ())
+            bits = np.zeros((1, N.MRAG_JTAG_WORDS), dtype=np.uint64)
+            for key in j_tags or ():
+                b = self.vocab.jtag_bit(key, allocate=True)
+                bits[0, b >> 6] |= np.uint64(1 << (b & 63))
+            d = self._doc(str(document_id))
+            self.index.set_doc_jtags(d, bits)
+            for fn in self.doc_listeners:
+                fn(d)
+
+    def set_document_tags(self, document_id: str, d_tags: Sequence[str] | None, p_tags: Sequence[str] | None,
+                          j_tags: Sequence[str] | None = None) -> None:
+        """UPSERT one document_tags row (keys of d_tags / p_tags / j_tags, app/models.py:525-543)."""
+        if j_tags is not None:
+            self.set_document_j_tags(document_id, j_tags)
         with self.lock:
             d = self._doc(str(document_id))
             self.doc_d_tags[str(document_id)] = set(d_tags or ())
@@ -204,6 +226,8 @@ class PublishedTable:
                     b = self.vocab.tag_bit(kind, key, allocate=True)
                     bits[0, b >> 6] |= np.uint64(1 << (b & 63))
             self.index.set_doc_tags(d, bits)
+            for fn in self.doc_listeners:
+                fn(d)
 
     def delete_document(self, document_id: str) -> int:
         """DELETE FROM .. WHERE document_id = :id (publish.py:310-313)."""
@@ -212,10 +236,14 @@ class PublishedTable:
             if d is None:
                 return 0
             n = self.index.tombstone_doc(d)
-            # a re-published document gets a fresh doc_idx so the tombstoned rows stay dead
+            # a re-published document gets a fresh doc_idx so the tombstoned rows stay dead; its document_tags row goes
+            # with it (host dictionaries and the device tag sets the pool cascade reads)
             del self.doc_idx[str(document_id)]
-            self.doc_d_tags.pop(str(document_id), None)
+            if self.doc_d_tags.pop(str(document_id), None) is not None or self.doc_p_tags.pop(str(document_id), None) is not None:
+                self.index.set_doc_tags(d, np.zeros((1, N.MRAG_TAG_WORDS), dtype=np.uint64))
             self.doc_p_tags.pop(str(document_id), None)
+            if self.doc_j_tags.pop(str(document_id), None) is not None:
+                self.index.set_doc_jtags(d, np.zeros((1, N.MRAG_JTAG_WORDS), dtype=np.uint64))
             return n
 
     # -- snapshot ------------------------------------------------------------------------------
@@ -238,7 +266,8 @@ class PublishedTable:
                 "corpus_version": int(corpus_version), "n": self._n, "dim": self.index.dim,
                 "shards": len(getattr(self.index, "shards", [None])),
                 "vocab": {name: getattr(v, name).values for name in ("payer", "state", "program", "authority", "source_type")},
-                "tag_bits": [[k[0], k[1], b] for k, b in v._tag_bit.items()],
+                "tag_bits": [[k[0], k[1], b] for k, b in v._tag_bit.items()], "jtag_bits": v._jtag_bit,
+                "doc_j_tags": self.doc_j_tags,
                 "doc_ids": self.doc_ids, "live_docs": sorted(self.doc_idx.values()),
                 "doc_d_tags": {k: sorted(s) for k, s in self.doc_d_tags.items()},
                 "doc_p_tags": {k: sorted(s) for k, s in self.doc_p_tags.items()},
@@ -271,9 +300,10 @@ class PublishedTable:
                 voc.encode(x)
         for kind, key, b in meta["tag_bits"]:
             v._tag_bit[(kind, key)] = int(b)
+        v._jtag_bit = {k: int(b) for k, b in meta.get("jtag_bits", {}).items()}
         self._init_host(v)
         z = np.load(os.path.join(dirpath, "columns.npz"), allow_pickle=False)
-        self._n = int(meta["n"])
+        self._n = self._host_n = int(meta["n"])
         self.row_doc = np.ascontiguousarray(z["row_doc"], dtype=np.uint32)
         self.id = StrCol.from_arrays(z, "id")
         self.source_id = StrCol.from_arrays(z, "source_id")
@@ -286,6 +316,7 @@ class PublishedTable:
         self.doc_idx = {self.doc_ids[d]: d for d in meta["live_docs"]}
         self.doc_d_tags = {k: set(s) for k, s in meta["doc_d_tags"].items()}
         self.doc_p_tags = {k: set(s) for k, s in meta["doc_p_tags"].items()}
+        self.doc_j_tags = {k: list(s) for k, s in meta.get("doc_j_tags", {}).items()}
         return self, ver
 
     # -- WHERE builders ------------------------------------------------------------------------
@@ -334,6 +365,13 @@ class PublishedTable:
                 f.program_eq(v.program.lookup(filters.program))
             if getattr(filters, "authority_level", None):
                 f.authority_eq(v.authority.lookup(filters.authority_level))
-        if include_document_ids:
+        if include_document_ids is not None and hasattr(include_document_ids, "doc_indices"):
+            # a CandidatePool built on the device (pool.build_candidate_pool): its document bitmap is used as it is
+            pool = include_document_ids
+            if pool._handle is not None and not hasattr(self.index, "shards"):
+                f.pool_handle(pool._handle)
+            else:
+                f.doc_pool(pool.doc_indices())
+        elif include_document_ids:
             f.doc_pool([d for d in (self.doc_idx.get(str(x)) for x in include_document_ids) if d is not None])
         return f

@@ -56,6 +56,17 @@ class Vocab:
         # document_tags.d_tags / p_tags keys -> bit index (d and p keys are tested against their
         # own column, corpus_search.py:1501-1508, so they get separate bits)
         self._tag_bit: dict[tuple[str, str], int] = {}
+        self._jtag_bit: dict[str, int] = {}
+
+    def jtag_bit(self, key: str, allocate: bool) -> int | None:
+        """bit of a document j-tag key (document_tags.j_tags, app/models.py:535-537) in the j-tag sets"""
+        b = self._jtag_bit.get(key)
+        if b is None and allocate:
+            if len(self._jtag_bit) >= N.MRAG_JTAG_WORDS * 64:
+                raise ValueError(f"more than {N.MRAG_JTAG_WORDS * 64} distinct document j-tag keys")
+            b = len(self._jtag_bit)
+            self._jtag_bit[key] = b
+        return b
 
     def tag_bit(self, kind: str, key: str, allocate: bool) -> int | None:
         b = self._tag_bit.get((kind, key))

@@ -297,11 +297,90 @@ def make_rerank_golden(oracle, ref_cs):
     print("rerank cases:", [(c["n_candidates"], c["n_ranked"]) for c in out_cases])
 
 
+def make_pool_golden():
+    """Runs the reference's own `build_candidate_pool` + `_augment_pool_with_inheritance`
+    (app/services/corpus_search_agent.py:1762-1888, 1966-2002) over a synthetic document_tags table; the only stand-in is
+    the session that answers `SELECT document_id FROM document_tags WHERE {column} ? :code` (:1461-1482)."""
+    import importlib
+    import re
+    os.environ.setdefault("DATABASE_URL", "postgresql+asyncpg://u:p@localhost/db")     # app/config.py refuses to import without one
+    agent = importlib.import_module("app.services.corpus_search_agent")
+    rng = np.random.default_rng(909)
+    jkeys = ["payor.sunshine_health", "payor.aetna", "payor.molina_healthcare", "state.fl", "program.medicaid", "regulatory_authority.ahca"]
+    dkeys = ["utilization_management.prior_authorization", "claims.timely_filing", "claims.appeals", "benefits.behavioral_health", "claims.general"]
+    pkeys = ["process.claims_submission", "process.appeal_filing"]
+    docs = []
+    for d in range(400):
+        docs.append({
+            "document_id": f"00000000-0000-4000-8000-{d:012d}",
+            "j_tags": [k for k, p in zip(jkeys, (0.2, 0.15, 0.1, 0.5, 0.4, 0.12)) if rng.random() < p],
+            "d_tags": [k for k, p in zip(dkeys, (0.15, 0.1, 0.1, 0.05, 0.4)) if rng.random() < p],
+            "p_tags": [k for k, p in zip(pkeys, (0.15, 0.05)) if rng.random() < p],
+            "has_tags_row": bool(rng.random() < 0.9),
+        })
+    stmt = re.compile(r"SELECT document_id FROM document_tags WHERE (j_tags|d_tags|p_tags) \? :code")
+
+    class TagSession:
+        def __init__(self):
+            self.log = []
+
+        async def execute(self, sql, params):
+            m = stmt.fullmatch(" ".join(str(sql).split()))
+            assert m, str(sql)
+            self.log.append([m.group(1), params["code"]])
+            rows = [(d["document_id"],) for d in docs if d["has_tags_row"] and params["code"] in d[m.group(1)]]
+
+            class R:
+                def all(self_inner):
+                    return rows
+            return R()
+
+    TA, TP = agent.TermAssignment, agent.TermPartition
+    import dataclasses
+    ta_fields = {f.name for f in dataclasses.fields(TA)}
+
+    def term(code):
+        kw = {"kind": "tag", "full_code": code}
+        for name in ta_fields - set(kw):
+            kw[name] = {"term": code, "selectivity": 0.9}.get(name, None)
+        return TA(**kw)
+
+    cases = [
+        dict(required=["j:payor.sunshine_health", "d:claims.timely_filing", "p:process.claims_submission"]),
+        dict(required=["j:payor.sunshine_health", "d:claims.timely_filing"], boosted=["p:process.appeal_filing"]),
+        dict(required=["j:payor.sunshine_health", "j:state.fl", "d:utilization_management.prior_authorization"]),
+        dict(required=["j:payor.molina_healthcare", "d:benefits.behavioral_health", "d:claims.appeals"]),     # J&D empty -> AHCA&D or AHCA
+        dict(required=["d:claims.general"]),
+        dict(required=["j:payor.aetna"]),
+        dict(required=["j:payor.nobody", "d:claims.general"]),                                                # unknown j code
+        dict(required=["d:no.such_domain"]),
+        dict(required=[]),
+        dict(required=["p:process.claims_submission"], boosted=["d:claims.appeals", "j:program.medicaid"]),
+        dict(required=["j:payor.aetna", "d:claims.general"], inherited=[docs[i]["document_id"] for i in (3, 5, 8, 399)] + ["ffffffff-0000-4000-8000-000000000000"]),
+    ]
+    out = []
+    for kw in cases:
+        part = TP(required=[term(c) for c in kw.get("required", [])], boosted=[term(c) for c in kw.get("boosted", [])], dropped=[])
+        db = TagSession()
+        pool = asyncio.run(agent.build_candidate_pool(db, part))
+        if kw.get("inherited"):
+            pool = agent._augment_pool_with_inheritance(pool, kw["inherited"])
+        out.append({"case": kw, "statements": db.log, "cascade_level": pool.cascade_level,
+                    "cascade_steps": [list(x) for x in pool.cascade_steps], "intersect_codes": pool.intersect_codes,
+                    "document_ids": sorted(pool.document_ids), "inherited_document_ids": list(pool.inherited_document_ids),
+                    "relaxed": pool.relaxed})
+    dump_json({"docs": docs, "cases": out}, "pool.json")
+    print("pool cases:", [(c["cascade_level"], len(c["document_ids"])) for c in out])
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("make_golden.py needs /root/reference (build container only)")
     install_stubs()
     sys.path.insert(0, REF)
+    if sys.argv[1:] == ["pool"]:                       # regenerate one fixture without touching the others
+        make_pool_golden()
+        return
     from oracle import oracle
     from helpers import build_tables
     import importlib
@@ -408,6 +487,7 @@ def main():
         store_out.append({"case": kw, "query": q, "statements": list(store_log), "result": got})
 
     make_rerank_golden(oracle, ref_cs)
+    make_pool_golden()
 
     # ---- write fixtures
     np.savez_compressed(os.path.join(HERE, "table_vectors.npz"), X=Xf, has_vec=np.asarray(ot.has_vec, dtype=np.uint8))
