@@ -269,6 +269,23 @@ int mrag_search_hybrid(mrag_index* idx, const float* q, int nq, int k, const mra
                        const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows, int32_t* counts,
                        void* stream);
 
+/* `_rerank` over a candidate LIST -- the RRF output of the bm25 / vector / d-tag arms (corpus_search.py:3519-3622), after
+ * the enrichment steps attached neighbour text and inherited document tags.  The host shim turns each candidate's
+ * haystacks into bits exactly as it does for stored rows; `sim` is `_best_arm_sim` (:1787-1814: max over the arms of the
+ * vector arm's max(0, (cos - 0.5) * 2) and the other arms' raw scores -- this is where the BM25 arm's score enters). */
+typedef struct mrag_candidate {
+    mrag_chunkfeat feat;   /* bits of the candidate's body (+ neighbour text) and meta haystacks (:1850-1906) */
+    float    sim;          /* _best_arm_sim */
+    uint32_t doc_idx;      /* its document: binary j-tag credit (:2055-2063) */
+    uint8_t  authority;    /* code of authority_level (31+ = unknown) */
+    uint8_t  dtag_match;   /* 1 = a d: phrase code is a key of the chunk's chunk_d_tags (:2124-2133) */
+    uint8_t  reserved[2];
+} mrag_candidate;          /* 52 bytes */
+/* cands: n entries (HOST); hq: ONE query.  Outputs (HOST, n each): rerank score before the per-category decay, the
+ * weighted coverage, and keep = the coverage floor and its exemptions let the candidate through (:2183-2247). */
+int mrag_rerank_candidates(mrag_index* idx, const mrag_candidate* cands, int64_t n, const mrag_hybrid_query* hq,
+                           float* scores, float* coverage, uint8_t* keep);
+
 /* The d-tag arm's WHERE (`_dtag_arm`, corpus_search.py:1605-1701): rows that pass `filter` -- evaluated over every
  * live row: that statement has no "embedding_vec IS NOT NULL" -- and whose chunk_d_tags hold any of `dcodes`
  * (n_codes <= 32).  host_mask_out: ceil(size/32) words (HOST); counts (HOST, n_codes + 1): [0] = rows passing the

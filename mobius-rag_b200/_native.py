@@ -30,7 +30,7 @@ EXPORTS = [
     "mrag_profile_begin", "mrag_profile_read", "mrag_launch_count", "mrag_last_scan_kind",
     "mrag_last_error", "mrag_version",
     "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge", "mrag_save", "mrag_load",
-    "mrag_set_row_ids", "mrag_set_dtag_overflow", "mrag_pool_build", "mrag_pool_select", "mrag_pool_add_docs", "mrag_pool_docs", "mrag_pool_destroy",
+    "mrag_set_row_ids", "mrag_set_dtag_overflow", "mrag_rerank_candidates", "mrag_pool_build", "mrag_pool_select", "mrag_pool_add_docs", "mrag_pool_docs", "mrag_pool_destroy",
 ]
 
 
@@ -75,6 +75,12 @@ class PoolQuery(C.Structure):
         ("j_all", C.c_uint64 * 4), ("ahca", C.c_uint64 * 4),
         ("has_j", C.c_int32), ("has_d", C.c_int32), ("has_p", C.c_int32), ("has_ahca", C.c_int32),
     ]
+
+
+class Candidate(C.Structure):
+    """mrag_candidate (52 bytes)."""
+    _fields_ = [("feat", ChunkFeat), ("sim", C.c_float), ("doc_idx", C.c_uint32), ("authority", C.c_uint8), ("dtag_match", C.c_uint8),
+                ("reserved", C.c_uint8 * 2)]
 
 
 class HybridQuery(C.Structure):
@@ -146,6 +152,8 @@ def load(build_if_missing: bool = True):
     lib.mrag_set_row_base.argtypes = [vp, i64]
     lib.mrag_set_row_ids.restype = i32
     lib.mrag_set_row_ids.argtypes = [vp, i64, vp, i64]
+    lib.mrag_rerank_candidates.restype = i32
+    lib.mrag_rerank_candidates.argtypes = [vp, vp, i64, C.POINTER(HybridQuery), vp, vp, vp]
     lib.mrag_set_dtag_overflow.restype = i32
     lib.mrag_set_dtag_overflow.argtypes = [vp, vp, vp, i64]
     lib.mrag_pool_build.restype = i32

@@ -87,9 +87,8 @@ MRAG_DEVINL bool hybrid_keep(const DevHyb& h, const mrag_chunkfeat& f, const Hyb
     return e.dtag_match;
 }
 
-MRAG_DEVINL float hybrid_score(const DevHyb& h, const mrag_chunkfeat& f, const HybEval& e, float cos, uint32_t auth_code) {
-    const float c01 = fminf(1.0f, fmaxf(0.0f, cos));                       // _vector_arm clamp (:1569)
-    const float sim = fmaxf(0.0f, (c01 - 0.5f) * 2.0f);                    // _best_arm_sim (:1808-1810)
+// sim = `_best_arm_sim` of the candidate (:1787-1814)
+MRAG_DEVINL float hybrid_score_sim(const DevHyb& h, const mrag_chunkfeat& f, const HybEval& e, float sim, uint32_t auth_code) {
     const float auth = h.q.auth_score[auth_code < 31u ? auth_code : 31u];
     float jpd = 0.0f;
     if (h.q.w_jpd > 0.0f) {
@@ -106,6 +105,30 @@ MRAG_DEVINL float hybrid_score(const DevHyb& h, const mrag_chunkfeat& f, const H
     float score = h.max_weight > 0.0f ? raw / h.max_weight : raw;
     if (e.dtag_match) score *= h.q.boost;
     return score;
+}
+
+MRAG_DEVINL float hybrid_score(const DevHyb& h, const mrag_chunkfeat& f, const HybEval& e, float cos, uint32_t auth_code) {
+    const float c01 = fminf(1.0f, fmaxf(0.0f, cos));                       // _vector_arm clamp (:1569)
+    return hybrid_score_sim(h, f, e, fmaxf(0.0f, (c01 - 0.5f) * 2.0f), auth_code);     // vector arm of _best_arm_sim (:1808-1810)
+}
+
+// `_rerank` over a candidate LIST (the RRF output of several arms, corpus_search.py:3519-3622): one thread per candidate.
+// Everything textual arrives as bits (mrag_candidate.feat, built by the host shim from the candidate's haystacks incl. any
+// neighbour text), sim is `_best_arm_sim` over the arms that found it.  Writes the score, the coverage and whether the
+// coverage floor keeps it; the per-(arm, source_type) decay and the sort are a host pass over <= ~600 numbers.
+__global__ void __launch_bounds__(128) rerank_candidates_kernel(const mrag_candidate* __restrict__ cands, int64_t n, const DevHyb* __restrict__ hq,
+                                                               const uint64_t* __restrict__ doc_jtags, int64_t n_jtag_docs,
+                                                               float* __restrict__ scores, float* __restrict__ cov, uint8_t* __restrict__ keep) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevHyb& h = hq[0];
+    const mrag_candidate c = cands[i];
+    const uint64_t* jt = (doc_jtags && int64_t(c.doc_idx) < n_jtag_docs) ? doc_jtags + size_t(c.doc_idx) * MRAG_JTAG_WORDS : nullptr;
+    HybEval e = hybrid_eval(h, c.feat, jt, -1, DtagOver{nullptr, nullptr, 0});
+    e.dtag_match = e.dtag_match || c.dtag_match != 0;
+    scores[i] = hybrid_score_sim(h, c.feat, e, c.sim, c.authority);
+    cov[i] = e.cov;
+    keep[i] = hybrid_keep(h, c.feat, e) ? 1 : 0;
 }
 
 // One thread per row, all queries in a loop (the row's features are read once).  Bit (q, r) = row r passes the

@@ -1611,6 +1611,43 @@ extern "C" int mrag_search_hybrid(mrag_index* x, const float* q, int nq, int k, 
 }
 
 
+extern "C" int mrag_rerank_candidates(mrag_index* x, const mrag_candidate* cands, int64_t n, const mrag_hybrid_query* hq,
+                                      float* scores, float* coverage, uint8_t* keep) {
+    if (!x || !hq || n < 0 || (n > 0 && (!cands || !scores || !coverage || !keep)))
+        return fail(MRAG_ERR_ARG, "mrag_rerank_candidates: null argument");
+    if (n == 0) return MRAG_OK;
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_rerank_candidates: cudaSetDevice failed (no CPU path)");
+    Workspace* w = acquire_ws(x, nullptr);
+    if (!w) return fail(MRAG_ERR_OOM, "mrag_rerank_candidates: cannot create a workspace");
+    cudaStream_t s = w->own_stream;
+    int rc = MRAG_OK;
+    DevHyb dh;
+    derive_hyb(*hq, &dh);
+    const size_t in_bytes = size_t(n) * sizeof(mrag_candidate);
+    // one staging buffer: candidates | scores | coverage | keep
+    const size_t off_s = (in_bytes + 15) / 16 * 16, off_c = off_s + size_t(n) * 4, off_k = off_c + size_t(n) * 4, total = off_k + size_t(n);
+    if (w->hyb.reserve(1) || w->ckeys.reserve((total + 7) / 8)) rc = MRAG_ERR_OOM;
+    if (rc == MRAG_OK) {
+        unsigned char* base = reinterpret_cast<unsigned char*>(w->ckeys.p);
+        cudaMemcpyAsync(w->hyb.p, &dh, sizeof dh, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(base, cands, in_bytes, cudaMemcpyHostToDevice, s);
+        rerank_candidates_kernel<<<unsigned(ceil_div(n, 128)), 128, 0, s>>>(reinterpret_cast<const mrag_candidate*>(base), n, w->hyb.p, x->doc_jtags,
+                                                                           x->n_jtag_docs, reinterpret_cast<float*>(base + off_s),
+                                                                           reinterpret_cast<float*>(base + off_c), base + off_k);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaMemcpyAsync(scores, base + off_s, size_t(n) * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(coverage, base + off_c, size_t(n) * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(keep, base + off_k, size_t(n), cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(MRAG_ERR_CUDA, "mrag_rerank_candidates: %s", cudaGetErrorString(e));
+    }
+    release_ws(x, w, nullptr);
+    return rc;
+}
+
 // The d-tag arm (corpus_search.py:1605-1701): WHERE over live rows + "chunk_d_tags ? key" for any key.  The row
 // bitmap comes back to the HOST (the shim orders the matches by (authority tier, id) and cuts to k, :1674-1680).
 extern "C" int mrag_dtag_mask(mrag_index* x, const mrag_filter* filter, const uint16_t* dcodes, int n_codes,

@@ -53,13 +53,14 @@ class CandidatePool:
         self.inherited_document_ids = list(inherited_document_ids or [])
         self._document_ids = document_ids
         self._doc_idx: np.ndarray | None = None
+        self._unknown_ids: list[str] = []        # inherited ids that name no document of this table (kept, like the reference)
 
     # -- the reference's fields -----------------------------------------------------------------
     @property
     def document_ids(self) -> list[str]:
         if self._document_ids is None:
             t = self._table
-            self._document_ids = [t.doc_ids[int(d)] for d in self.doc_indices()]
+            self._document_ids = [t.doc_ids[int(d)] for d in self.doc_indices()] + list(self._unknown_ids)
         return self._document_ids
 
     @property
@@ -81,7 +82,7 @@ class CandidatePool:
             if self._handle is None:
                 self._doc_idx = np.zeros(0, dtype=np.uint32)
             else:
-                out = np.zeros(max(self.size, 1), dtype=np.uint32)
+                out = np.zeros(max(self.size, 1) + 8, dtype=np.uint32)
                 n = C.c_int64(0)
                 N.check(N.load().mrag_pool_docs(self._handle, out.ctypes.data, out.shape[0], C.byref(n)))
                 self._doc_idx = out[:int(n.value)]
@@ -193,22 +194,28 @@ def augment_pool_with_inheritance(pool: CandidatePool, inherited_ids: Sequence[s
         return pool
     t = pool._table
     have = set(int(d) for d in pool.doc_indices())
+    seen_ids = set()
     added, add_idx = [], []
     for did in inherited_ids:
-        d = t.doc_idx.get(str(did))
-        if d is None or d in have:
+        did = str(did)
+        d = t.doc_idx.get(did)
+        if did in seen_ids or (d is not None and d in have):
             continue
-        have.add(d)
-        added.append(str(did))
-        add_idx.append(d)
-    room = max(0, POOL_CAP - pool.size)
-    added, add_idx = added[:room] if len(added) > room else added, add_idx[:room] if len(add_idx) > room else add_idx
+        seen_ids.add(did)
+        added.append(did)                                 # the reference does not check that the id is a known document
+        if d is not None:
+            have.add(d)
+            add_idx.append(d)
+    added = added[:max(0, POOL_CAP - pool.size)]
     if not added:
         return pool
-    arr = np.asarray(add_idx, dtype=np.uint32)
-    N.check(N.load().mrag_pool_add_docs(pool._handle, arr.ctypes.data, arr.shape[0]))
+    keep = set(added)
+    arr = np.asarray([d for d in add_idx if t.doc_ids[d] in keep], dtype=np.uint32)
+    if arr.size:
+        N.check(N.load().mrag_pool_add_docs(pool._handle, arr.ctypes.data, arr.shape[0]))
     out = CandidatePool(t, pool._handle, pool.cascade_level,
                         list(pool.cascade_steps or []) + [("inherited_authority_union", len(added))],
                         pool.intersect_codes, pool.size + len(added), inherited_document_ids=added)
+    out._unknown_ids = [x for x in added if x not in t.doc_idx]
     pool._handle = None                                   # ownership of the device bitmap moves to the new object
     return out

@@ -1,7 +1,7 @@
 """Profiling driver (GPU box): builds the 10M x 768 bf16 bench corpus and runs a few searches.
 
     ncu --set full --clock-control none --import-source on -k regex:scan_mma128 -s 5 -c 1 -o out \\
-        python tools/one_search.py <batch> <k> <reps> [rows] [dtype]
+        python tools/one_search.py <batch> <k> <reps> [rows] [dtype] [dim]
 """
 import os
 import sys
@@ -17,7 +17,7 @@ from mrag_b200 import synth
 B, k, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 10_000_000
 dtype = sys.argv[5] if len(sys.argv) > 5 else "bf16"
-dim = 768
+dim = int(sys.argv[6]) if len(sys.argv) > 6 else 768
 dev = torch.device("cuda:0")
 idx = mi.Index(dim, dtype, 0, n)
 plant = None
