@@ -1211,7 +1211,9 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
                 LAUNCHED();
             }
-            int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!sampled, s);
+            // unsampled shards: register top-k by default; MRAG_UNSAMPLED_BUFFER=1 pins the shared-memory buffer kernel (tuning)
+            static const bool unsampled_buffer = [] { const char* e = getenv("MRAG_UNSAMPLED_BUFFER"); return e && e[0] == '1'; }();
+            int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!sampled && !unsampled_buffer, s);
             if (rc != MRAG_OK) return rc;
             t_last_kind = ksplit ? "mma_ks" : "mma";
         } else if (n > 0) {

@@ -96,6 +96,29 @@ class MultiIndex:
         self._n = need
         return first
 
+    def append_device_shard(self, s: int, X, meta: np.ndarray) -> int:
+        """Bulk load: rows already resident on shard s's GPU (torch float32 CUDA [m, dim]) go to that shard as a block;
+        their ids are the next m host positions.  The caller keeps a document's rows together (a loader that streams whole
+        documents per shard, publish.py:310-313)."""
+        ix = self.shards[s]
+        m = int(X.shape[0])
+        first, base = self._n, len(ix)
+        ids = np.arange(first, first + m, dtype=np.int64)
+        N.check(ix._lib.mrag_set_row_ids(ix._h, base, ids.ctypes.data, m))
+        got = ix.append_device(X, meta)
+        assert got == base
+        need = first + m
+        if need > self.pos_shard.shape[0]:
+            cap = max(need, 2 * self.pos_shard.shape[0])
+            self.pos_shard = np.concatenate([self.pos_shard, np.zeros(cap - self.pos_shard.shape[0], dtype=np.uint8)])
+            self.pos_local = np.concatenate([self.pos_local, np.zeros(cap - self.pos_local.shape[0], dtype=np.int64)])
+        self.pos_shard[first:need] = s
+        self.pos_local[first:need] = base + np.arange(m)
+        for d in np.unique(meta["doc_idx"]):
+            self.doc_home.setdefault(int(d), s)
+        self._n = need
+        return first
+
     def set_doc_tags(self, first_doc: int, bits: np.ndarray) -> None:
         for ix in self.shards:                                         # the per-document tables are small: every shard holds all of them
             ix.set_doc_tags(first_doc, bits)

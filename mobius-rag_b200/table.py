@@ -101,6 +101,8 @@ class PublishedTable:
         self.doc_d_tags: dict[str, set] = {}
         self.doc_p_tags: dict[str, set] = {}
         self.doc_j_tags: dict[str, list] = {}
+        self.dead_docs: set[int] = set()             # doc indices whose rows were deleted (a re-published document gets a new index)
+        self.doc_rows = np.zeros(1024, dtype=np.int64)   # rows per doc index (count(*) .. WHERE document_id = ANY(..), corpus_search.py:3461-3470)
         self.doc_listeners: list = []                # callables(doc_idx): a document's tags changed (derived row features go stale)
 
     def __len__(self) -> int:
@@ -177,6 +179,9 @@ class PublishedTable:
                 self.row_doc = np.concatenate([self.row_doc, np.zeros(max(first + n, self.row_doc.shape[0]), dtype=np.uint32)])
             self.row_doc[first:first + n] = docs
             self._host_n = first + n
+            if len(self.doc_ids) > self.doc_rows.shape[0]:
+                self.doc_rows = np.concatenate([self.doc_rows, np.zeros(max(len(self.doc_ids), self.doc_rows.shape[0]), dtype=np.int64)])
+            np.add.at(self.doc_rows, docs, 1)
             for col, _, _ in _CODED:
                 getattr(self, col).extend(codes[col])
             for c in HYDRATE_COLS:
@@ -239,6 +244,7 @@ class PublishedTable:
             # a re-published document gets a fresh doc_idx so the tombstoned rows stay dead; its document_tags row goes
             # with it (host dictionaries and the device tag sets the pool cascade reads)
             del self.doc_idx[str(document_id)]
+            self.dead_docs.add(d)
             if self.doc_d_tags.pop(str(document_id), None) is not None or self.doc_p_tags.pop(str(document_id), None) is not None:
                 self.index.set_doc_tags(d, np.zeros((1, N.MRAG_TAG_WORDS), dtype=np.uint64))
             self.doc_p_tags.pop(str(document_id), None)
@@ -268,7 +274,7 @@ class PublishedTable:
                 "vocab": {name: getattr(v, name).values for name in ("payer", "state", "program", "authority", "source_type")},
                 "tag_bits": [[k[0], k[1], b] for k, b in v._tag_bit.items()], "jtag_bits": v._jtag_bit,
                 "doc_j_tags": self.doc_j_tags,
-                "doc_ids": self.doc_ids, "live_docs": sorted(self.doc_idx.values()),
+                "doc_ids": self.doc_ids, "live_docs": sorted(self.doc_idx.values()), "dead_docs": sorted(self.dead_docs),
                 "doc_d_tags": {k: sorted(s) for k, s in self.doc_d_tags.items()},
                 "doc_p_tags": {k: sorted(s) for k, s in self.doc_p_tags.items()},
             }
@@ -314,6 +320,8 @@ class PublishedTable:
             self.extra[c] = kind.from_arrays(z, "extra." + c)
         self.doc_ids = list(meta["doc_ids"])
         self.doc_idx = {self.doc_ids[d]: d for d in meta["live_docs"]}
+        self.dead_docs = set(int(d) for d in meta.get("dead_docs", []))
+        self.doc_rows = np.bincount(self.row_doc[:self._n], minlength=max(len(self.doc_ids), 1024)).astype(np.int64)
         self.doc_d_tags = {k: set(s) for k, s in meta["doc_d_tags"].items()}
         self.doc_p_tags = {k: set(s) for k, s in meta["doc_p_tags"].items()}
         self.doc_j_tags = {k: list(s) for k, s in meta.get("doc_j_tags", {}).items()}

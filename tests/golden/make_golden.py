@@ -373,6 +373,162 @@ def make_pool_golden():
     print("pool cases:", [(c["cascade_level"], len(c["document_ids"])) for c in out])
 
 
+def make_corpus_search_golden(oracle):
+    """Runs the reference's own `corpus_search` (app/services/corpus_search.py:3280-3826) end to end over the hybrid table.
+    Stand-ins: the Postgres session (statement shapes answered below; the vector / d-tag statements go through mini_pg as in
+    the other fixtures), `_bm25_arm` (returns a recorded list: Postgres full-text search is outside the path),
+    `_embed_with_cache` (returns the case's embedding), `expand_query_via_lexicon`, and the fire-and-forget
+    `_persist_search_event`.  Everything between them -- arm orchestration per mode, RRF, content de-duplication,
+    neighbour enrichment, inherited tags, topic-block merge, `_rerank`, `_assemble`, neighbour expansion, chunk shaping --
+    is the reference's code."""
+    import importlib
+    import re
+    import mini_pg
+    cfg = types.ModuleType("app.config")
+    cfg.CHUNK_TAG_BOOST = 1.5
+    sys.modules["app.config"] = cfg
+    ref_cs = importlib.import_module("app.services.corpus_search")
+    ref_lex = importlib.import_module("app.services.corpus_search_lexicon")
+    docs, rows, X, promoted = hybrid_table()
+    # four consecutive chunks share a page here (the shared fixture puts every chunk on its own page, which would leave the
+    # same-page topic-block merge without work); tests/test_gpu_corpus_search.py applies the same renumbering
+    rows = [dict(r, page_number=(i // 4) % 30 + 1) for i, r in enumerate(rows)]
+    doc_by_id = {d["document_id"]: d for d in docs}
+    table_rows = []
+    for r in rows:
+        tr = dict(r)
+        tr["embedding_vec"] = True if r["has_vec"] else None
+        d = doc_by_id[r["document_id"]]
+        tr["_doc_d_tags"] = set(d["d_tags"]) if d["has_tags_row"] else None
+        tr["_doc_p_tags"] = set(d["p_tags"]) if d["has_tags_row"] else None
+        table_rows.append(tr)
+
+    def cd(Xs, q):
+        with np.errstate(all="ignore"):
+            return oracle.cosine_distance_c(np.ascontiguousarray(Xs), q)
+
+    class Result:
+        def __init__(self, rows, scalar=None):
+            self._rows, self._scalar = rows, scalar
+
+        def mappings(self):
+            return self
+
+        def all(self):
+            return self._rows
+
+        def scalar(self):
+            return self._scalar
+
+    class Session:
+        def __init__(self):
+            self.log = []
+
+        async def execute(self, stmt, params=None):
+            sql = " ".join(str(stmt).split())
+            params = dict(params or {})
+            self.log.append(sql[:60])
+            if "<=>" in sql or "0.5 AS similarity" in sql or "COUNT(*) AS n_total" in sql:
+                return Result(mini_pg.execute_any(table_rows, X, str(stmt), params, cd))
+            if sql.startswith("SELECT count(*) FROM rag_published_embeddings WHERE document_id = ANY"):
+                ids = set(params["_vc_ids"])
+                return Result([], scalar=sum(1 for r in rows if r["document_id"] in ids))
+            if sql.startswith("SELECT DISTINCT ON (m.id)"):
+                hit = {}
+                for doc, lo, hi, plo, phi, ex in zip(params["doc_ids"], params["para_lo"], params["para_hi"], params["page_lo"],
+                                                     params["page_hi"], params["excludes"]):
+                    for r in rows:
+                        if (r["document_id"] == doc and r["paragraph_index"] is not None and lo <= r["paragraph_index"] <= hi
+                                and r["page_number"] is not None and plo <= r["page_number"] <= phi and r["id"] != ex):
+                            hit[r["id"]] = r
+                return Result([dict(hit[i]) for i in sorted(hit)][:500])
+            if "FROM document_tags" in sql:
+                ids = set(params["ids"])
+                return Result([{"doc_id": d["document_id"], "d_tags": list(d["d_tags"]), "j_tags": list(d["j_tags"]), "p_tags": list(d["p_tags"])}
+                               for d in docs if d["has_tags_row"] and d["document_id"] in ids])
+            if "FROM payor_inherited_authority" in sql:
+                return Result([])
+            raise ValueError("corpus_search golden: statement not recognised: " + sql[:200])
+
+    async def no_persist(*a, **k):
+        return None
+    ref_cs._persist_search_event = no_persist
+    rng = np.random.default_rng(4242)
+    dim = X.shape[1]
+
+    def bm25_list(seed_rows, n_extra):
+        idx = list(seed_rows) + [int(x) for x in rng.permutation(len(rows))[:n_extra]]
+        out, seen = [], set()
+        for j, i in enumerate(idx):
+            if i in seen:
+                continue
+            seen.add(i)
+            c = ref_cs._row_to_base_dict(rows[i])
+            c["similarity"] = round(0.95 - 0.02 * j, 4) if j < 40 else 0.1
+            c["match_score"] = c["similarity"]
+            c["_arm"] = "bm25"
+            out.append(c)
+        return out
+
+    cases = [
+        dict(req=dict(query="what is the appeal process for a denial", k=8, mode="recall")),
+        dict(req=dict(query="timely filing deadline", k=5, mode="recall", min_similarity=0.2, neighbor_paragraph_window=0)),
+        dict(req=dict(query="prior authorization requirements", k=10, mode="recall", filters=dict(payer="AHCA")),
+             lexicon=dict(domain_tags=["d:claims.timely_filing"], jurisdiction_tags=["j:state.fl"])),
+        dict(req=dict(query="sunshine health prior authorization requirements", k=10, mode="corpus",
+                      required_phrases=["Sunshine Health", "prior authorization"], required_phrase_weights=[0.93, 0.79],
+                      required_phrase_tag_codes=["j:payor.sunshine_health", "d:utilization_management.prior_authorization"]),
+             bm25=dict(n_extra=30), expansion=dict(domain_tags=["d:utilization_management.prior_authorization"])),
+        dict(req=dict(query="timely filing deadline for corrected claim", k=6, mode="corpus", required_phrases=["timely filing"],
+                      required_phrase_weights=[0.8], required_phrase_tag_codes=["d:claims.timely_filing"], assembly_strategy="balanced",
+                      canonical_floor=0.5), bm25=dict(n_extra=25)),
+        dict(req=dict(query="provider services phone number", k=10, mode="corpus", assembly_strategy="canonical_first",
+                      neighbor_paragraph_window=1, neighbor_page_window=0), bm25=dict(n_extra=20)),
+        dict(req=dict(query="medical records documentation required", k=10, mode="precision", required_phrases=["medical records"],
+                      required_phrase_weights=[0.7], required_phrase_tag_codes=[None]), bm25=dict(n_extra=40)),
+        dict(req=dict(query="appeals", k=10, mode="precision", required_phrase_tag_codes=["d:claims.appeals"]), bm25=dict(n_extra=15)),
+        dict(req=dict(query="behavioral health credentialing", k=200, mode="corpus", include_document_ids=[d["document_id"] for d in docs[:25]]),
+             bm25=dict(n_extra=10)),
+        dict(req=dict(query="anything", k=10, mode="recall", include_document_ids=[d["document_id"] for d in docs])),      # > 2000 chunks? no: 900
+        dict(req=dict(query="   ", k=10)),
+    ]
+    out = []
+    for ci, case in enumerate(cases):
+        q = (X[int(rng.integers(0, len(rows)))].astype(np.float64) + 0.1 * rng.standard_normal(dim)).tolist() if ci % 2 == 0 \
+            else rng.standard_normal(dim).tolist()
+        qv = np.asarray([np.float32(x) for x in q], dtype=np.float32)
+        order = [i for i in np.argsort(cd(X, qv), kind="stable") if rows[i]["has_vec"]][:6]
+        bm = bm25_list(order[1:4], case["bm25"]["n_extra"]) if case.get("bm25") else []
+        expansion = dict(matched_codes=[], expansion_phrases=[], expansion_phrases_count=0, final_tsquery="", log=[], domain_tags=[],
+                         jurisdiction_tags=[], process_tags=[])
+        expansion.update(case.get("expansion") or {})
+
+        async def fake_bm25(db, query, k, filters, include_document_ids, search_id="", tag_mode="auto", _bm=bm, _e=expansion):
+            return [dict(c) for c in _bm], None, dict(_e)
+
+        async def fake_embed(query, search_id="", _q=q):
+            return list(_q), 0.0, False
+
+        async def fake_expand(db, query, _c=case):
+            return ref_lex.LexiconExpansion(**_c["lexicon"]) if _c.get("lexicon") else None
+        ref_cs._bm25_arm, ref_cs._embed_with_cache = fake_bm25, fake_embed
+        ref_lex.expand_query_via_lexicon = fake_expand
+        req = ref_cs.CorpusSearchRequest(**case["req"])
+
+        async def run(req=req):
+            db = Session()
+            resp = await ref_cs.corpus_search(db, req)
+            await asyncio.sleep(0)                      # let the fire-and-forget task run
+            return resp, db.log
+        resp, log = asyncio.run(run())
+        tel = resp.telemetry
+        out.append({"request": case["req"], "query_embedding": q, "bm25": bm, "bm25_expansion": expansion, "lexicon": case.get("lexicon"),
+                    "statements": log, "chunks": [c.model_dump() for c in resp.chunks],
+                    "telemetry": {k: tel.get(k) for k in ("mode", "k", "arm_hits", "candidates", "returned", "min_label_applied", "assembly", "error")}})
+    dump_json(out, "corpus_search.json")
+    print("corpus_search cases:", [(c["request"].get("mode", "corpus"), len(c["chunks"]), c["telemetry"].get("candidates")) for c in out])
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("make_golden.py needs /root/reference (build container only)")
@@ -382,6 +538,9 @@ def main():
         make_pool_golden()
         return
     from oracle import oracle
+    if sys.argv[1:] == ["corpus_search"]:
+        make_corpus_search_golden(oracle)
+        return
     from helpers import build_tables
     import importlib
     ref_cs = importlib.import_module("app.services.corpus_search")
@@ -488,6 +647,7 @@ def main():
 
     make_rerank_golden(oracle, ref_cs)
     make_pool_golden()
+    make_corpus_search_golden(oracle)
 
     # ---- write fixtures
     np.savez_compressed(os.path.join(HERE, "table_vectors.npz"), X=Xf, has_vec=np.asarray(ot.has_vec, dtype=np.uint8))

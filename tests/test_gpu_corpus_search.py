@@ -1,0 +1,115 @@
+"""a11: the retrieval driver (`mrag_b200.search.corpus_search`) against the outputs of the reference's own `corpus_search`
+(app/services/corpus_search.py:3280-3826) recorded in tests/golden/corpus_search.json.gz -- every mode, RRF over three arms
+with a recorded BM25 list, content de-duplication, neighbour enrichment / inherited tags / topic-block merge, the rerank
+(scored on the GPU), the three assembly strategies, neighbour expansion, chunk shaping and the telemetry counters.
+f4: the sibling index behind it against a brute-force evaluation of the reference's UNNEST statement."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR, load_golden_json
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_golden_json("corpus_search.json")
+
+
+@pytest.fixture(scope="module")
+def ht():
+    import mrag_b200
+    tj = load_golden_json("hybrid_table.json")
+    X = np.load(os.path.join(GOLDEN_DIR, "hybrid_vectors.npz"))["X"]
+    rows = tj["rows"] = [dict(r, page_number=(i // 4) % 30 + 1) for i, r in enumerate(tj["rows"])]   # as make_corpus_search_golden
+    pt = mrag_b200.PublishedTable(X.shape[1], dtype="f32", device=0, capacity=len(rows) + 8)
+    pt.insert(rows, [X[i].tolist() if r["has_vec"] else None for i, r in enumerate(rows)])
+    for d in tj["docs"]:
+        if d["has_tags_row"]:
+            pt.set_document_tags(d["document_id"], d["d_tags"], d["p_tags"], d["j_tags"])
+    h = mrag_b200.HybridTable(pt, tj["phrase_pool"])
+    h.build_features()
+    yield h, tj
+    pt.index.close()
+
+
+def test_inventory():
+    modes = [c["request"].get("mode", "corpus") for c in CASES]
+    assert {"corpus", "precision", "recall"} <= set(modes) and len(CASES) >= 10
+    assert any(ch["is_neighbor"] for c in CASES for ch in c["chunks"]) and any("\n\n" in ch["text"] for c in CASES for ch in c["chunks"])
+    assert any(len(ch["retrieval_arms"]) > 1 for c in CASES for ch in c["chunks"])
+    assert {c["request"].get("assembly_strategy", "score") for c in CASES} == {"score", "balanced", "canonical_first"}
+
+
+@pytest.mark.parametrize("i", range(len(CASES)))
+def test_corpus_search_matches_reference(ht, i):
+    from mrag_b200 import search as S
+    from mrag_b200.corpus_search import LexiconExpansion
+    h, _ = ht
+    case = CASES[i]
+
+    def bm25_arm(query, k, filters, include_document_ids, search_id="", tag_mode="auto"):
+        return [dict(c) for c in case["bm25"]], None, dict(case["bm25_expansion"])
+
+    def expand(query):
+        return LexiconExpansion(**case["lexicon"]) if case.get("lexicon") else None
+
+    resp = S.corpus_search(h, S.CorpusSearchRequest(**case["request"]), embed=lambda q: case["query_embedding"], bm25_arm=bm25_arm, expand=expand)
+    want, got = case["chunks"], [c.model_dump() for c in resp.chunks]
+    tel = resp.telemetry
+    for key, val in case["telemetry"].items():
+        if val is not None or key == "error":
+            assert tel.get(key) == val, (key, tel.get(key), val)
+    assert len(got) == len(want)
+    # same chunks in the same order; where two neighbours' rerank scores are equal to 4 decimals the order may swap
+    if [g["id"] for g in got] != [w["id"] for w in want]:
+        assert sorted(g["id"] for g in got) == sorted(w["id"] for w in want)
+        by_id = {w["id"]: w for w in want}
+        for pos, g in enumerate(got):
+            assert abs(by_id[g["id"]]["rerank_score"] - want[pos]["rerank_score"]) <= 2e-4, f"pos {pos}: {g['id']} out of order"
+        want = [by_id[g["id"]] for g in got]
+    for g, w in zip(got, want):
+        for key in w:
+            if key in ("rerank_score", "similarity"):
+                assert g[key] == pytest.approx(w[key], abs=2e-4), (g["id"], key)
+            elif key == "jpd_tags":
+                assert sorted(g[key]) == sorted(w[key])
+            else:
+                assert g[key] == w[key], (g["id"], key)
+
+
+def test_sibling_index_matches_the_unnest_statement(ht):
+    """f4: `_fetch_sibling_chunks_batch` (corpus_search.py:2560-2687) -- the index lookup against a brute-force evaluation
+    of the statement (JOIN on document, BETWEEN windows, `m.id <> exclude_id` per seed, DISTINCT ON (id) ORDER BY id)."""
+    from mrag_b200.neighbors import NeighborIndex
+    h, tj = ht
+    rows = tj["rows"]
+    nb = NeighborIndex(h.table)
+    rng = np.random.default_rng(3)
+    for pw, gw in ((2, 1), (1, 1), (3, 0), (1, 0)):
+        seeds = [dict(rows[int(j)]) for j in rng.choice(len(rows), 25, replace=False)]
+        seeds[3]["page_number"] = None                      # no page: unconstrained page window
+        seeds[4]["paragraph_index"] = None                  # no paragraph index: window around 0
+        seeds.append({"id": "x", "document_id": None})
+        got = nb.fetch_siblings(seeds, paragraph_window=pw, page_window=gw)
+        hit = {}
+        for s in seeds:
+            if not s.get("document_id"):
+                continue
+            pi = int(s["paragraph_index"]) if s.get("paragraph_index") is not None else 0
+            plo, phi = (max(0, s["page_number"] - gw), s["page_number"] + gw) if isinstance(s.get("page_number"), int) else (0, 10_000_000)
+            for r in rows:
+                if (r["document_id"] == s["document_id"] and r["paragraph_index"] is not None and max(0, pi - pw) <= r["paragraph_index"] <= pi + pw
+                        and r["page_number"] is not None and plo <= r["page_number"] <= phi and r["id"] != s["id"]):
+                    hit[r["id"]] = r
+        assert [g["id"] for g in got] == sorted(hit)[:500]
+        for g in got[:20]:
+            r = hit[g["id"]]
+            assert g["text"] == (r["text"] or "") and g["page_number"] == r["page_number"] and g["is_neighbor"] is True
+            assert g["document_name"] == (r["document_display_name"] or r["document_filename"] or "document")
+            assert g["retrieval_arms"] == ["neighbor"] and g["source_type"] == "hierarchical"
+    # deleted documents leave the index
+    doc = rows[100]["document_id"]
+    h.table.delete_document(doc)
+    got = nb.fetch_siblings([dict(rows[100])], paragraph_window=3, page_window=1)
+    assert got == []
