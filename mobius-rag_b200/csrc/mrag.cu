@@ -957,13 +957,12 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     }
     const int64_t tiles = ceil_div(n, kMmaTileRows);
     if (tiles >= sample_min_tiles(x->num_sms)) {
-        // admission bound from a strided sample (4 tiles per CTA), same arithmetic, register top-16 per CTA: the
-        // K'-th best of the union of the per-CTA lists is reached by K' known rows, so the full pass may skip
-        // anything below it (a CTA holds 1/#CTAs of the sample: its top 16 almost never truncate the sample's top K')
+        // admission bound from a strided sample, same arithmetic, the best kMmaSampleK scores per (query, CTA) in registers:
+        // the K'-th best of the union of the per-CTA lists is reached by K' known rows, so the full pass may skip anything
+        // below it (a CTA holds 1/#CTAs of the sample; a list that truncates only loosens the bound)
         MmaArgs sa = a;
         sa.stats = nullptr;
-        // up to 32 tiles per CTA, at most ~3 % of the shard (16 and ~1.5 % for large k, where the register top-16 of the sampling
-        // kernel starts to truncate): the k'-th best of the sample is the admission bound of the full pass, and every row
+        // up to 32 tiles per CTA, at most ~3 % of the shard (16 and ~1.5 % for large k): the k'-th best of the sample is the admission bound of the full pass, and every row
         // above it costs a buffer append and, every `slack` appends, a compaction.  Measured r1q (10M x 768, k = 10): 4 -> 32
         // tiles per CTA = 3.18 -> 2.49 ms at 128 queries, 5.0 -> 3.36 ms at 256 (pair scan); 64 tiles cost more than they save
         const char* pc_env = getenv("MRAG_SAMPLE128_PER_CTA");
@@ -972,9 +971,12 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * x->num_sms)));
         const int sgrid = int(std::min<int64_t>(x->num_sms, ceil_div(tiles, sa.tile_mul)));
         sa.P = sgrid;
-        sa.k = std::min(kc, kMmaRegK);
-        sa.kp = kMmaRegK;
-        rc = launch_scan_mma128<kMmaRegK>(x, sa, nq, sgrid, s);
+        // per-CTA list length of the sample: 4 scores for k' <= 64 (the union's k'-th best is spread ~k'/148 per CTA), the
+        // full 16 beyond (measured r2i, 10M x 768: k = 10, B = 256: 3.66 -> 3.38 ms with 4; k = 100: 7.33 -> 8.48 ms with 4)
+        const bool short_lists = kc <= 64;
+        sa.k = std::min(kc, short_lists ? kMmaSampleK : kMmaRegK);
+        sa.kp = short_lists ? kMmaSampleK : kMmaRegK;
+        rc = short_lists ? launch_scan_mma128<kMmaSampleK>(x, sa, nq, sgrid, s) : launch_scan_mma128<kMmaRegK>(x, sa, nq, sgrid, s);
         if (rc != MRAG_OK) return rc;
         MergeArgs sm{};
         sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kc; sm.lk = sa.k; sm.k_total = kc;
@@ -1184,9 +1186,9 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             const int64_t tiles = ceil_div(n, kMmaTileRows);
             const bool sampled = tiles >= sample_min_tiles(mma_units);
             if (sampled) {
-                // always the register top-k kernel: each CTA keeps the 16 best of a few tiles per query and
-                // the merge takes the k-th best of the union (k known rows reach it, so it is a valid bound;
-                // a CTA holds 1/#CTAs of the sample, so its top 16 almost never truncate the sample's top k)
+                // always the register top-k kernel: each CTA keeps the kMmaSampleK best scores of a few tiles per query and
+                // the merge takes the k-th best of the union (k known rows reach it, so it is a valid bound; a CTA holds
+                // 1/#CTAs of the sample, and a list that truncates only loosens the bound)
                 MmaArgs sa = a;
                 sa.stats = nullptr;
                 sa.tstamps = ts_sample;
@@ -1200,10 +1202,13 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 sa.tile_mul = int(std::max<int64_t>(1, tiles / (int64_t(per_cta) * mma_units)));
                 const int sgrid = int(std::min<int64_t>(mma_units, ceil_div(tiles, sa.tile_mul))) * (ksplit ? 2 : 1);
                 sa.P = sgrid;
-                sa.k = std::min(kr, kMmaRegK);
-                sa.kp = kMmaRegK;
-                int rc = ksplit ? launch_scan_mma<kMmaRegK, true, true>(x, sa, nq, sgrid, s)
-                                : launch_scan_mma<kMmaRegK, true>(x, sa, nq, sgrid, s);     // scores only
+                const bool short_lists = kr <= 64;              // see search_approx_rescore
+                sa.k = std::min(kr, short_lists ? kMmaSampleK : kMmaRegK);
+                sa.kp = short_lists ? kMmaSampleK : kMmaRegK;
+                int rc = ksplit ? (short_lists ? launch_scan_mma<kMmaSampleK, true, true>(x, sa, nq, sgrid, s)
+                                               : launch_scan_mma<kMmaRegK, true, true>(x, sa, nq, sgrid, s))
+                                : (short_lists ? launch_scan_mma<kMmaSampleK, true>(x, sa, nq, sgrid, s)
+                                               : launch_scan_mma<kMmaRegK, true>(x, sa, nq, sgrid, s));     // scores only
                 if (rc != MRAG_OK) return rc;
                 MergeArgs sm{};
                 sm.part = w->part.p; sm.P = sgrid; sm.kp = sa.kp; sm.nq = nq; sm.k = kr; sm.lk = sa.k; sm.k_total = k; sm.k_off = k_off;

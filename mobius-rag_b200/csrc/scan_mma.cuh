@@ -363,6 +363,14 @@ MRAG_DEVINL void walk_group64(const float (&sc)[64], float& thr, SelState& st, u
 //           (branch-free insertion), so its threshold is always the exact k-th best so far:
 //           ~k ln(n/k) insertions per query and CTA, no buffers, no compaction, no sampling pass.
 constexpr int kMmaRegK = 16;
+#ifndef MRAG_SAMPLE_K
+#define MRAG_SAMPLE_K 4
+#endif
+// The threshold-sampling passes keep only the best kMmaSampleK scores per (query, CTA): the bound is the k'-th best of
+// the UNION over ~148 CTAs, of which a CTA holds k'/148 on average, so 4 per CTA lose (almost) nothing -- and a list
+// that does truncate only makes the bound slightly looser, never wrong.  The sorted insertion is the sampling kernels'
+// whole epilogue (fully unrolled: 64 rows x K compare-exchange steps, instruction-fetch bound at K = 16, r1q ncu).
+constexpr int kMmaSampleK = MRAG_SAMPLE_K;
 
 // SO (score only, KREG > 0): the sampling pass needs a bound, not rows: 32-bit orderable scores in the
 //           registers (half the insertion work); the lists it writes carry synthetic unique low words.
