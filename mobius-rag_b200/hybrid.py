@@ -306,13 +306,7 @@ class HybridTable:
 
     def _upload_overflow(self) -> None:
         pairs = sorted((r, c) for r, codes in self._overflow.items() for c in codes)
-        rows = np.asarray([p[0] for p in pairs], dtype=np.uint32)
-        codes = np.asarray([p[1] for p in pairs], dtype=np.uint16)
-        ix = self.table.index
-        if hasattr(ix, "shards"):
-            raise NotImplementedError("chunk d-tag overflow on a multi-shard table")
-        N.check(ix._lib.mrag_set_dtag_overflow(ix._h, rows.ctypes.data if rows.size else None,
-                                               codes.ctypes.data if codes.size else None, int(rows.size)))
+        self.table.index.set_dtag_overflow(np.asarray([p[0] for p in pairs], dtype=np.int64), np.asarray([p[1] for p in pairs], dtype=np.uint16))
 
     def ensure_phrases(self, phrases: Sequence[str]) -> None:
         """Every required phrase of a query must be in the dictionary.  New ones are added (their presence bit is computed
@@ -476,25 +470,8 @@ def dtag_arm(ht: "HybridTable", dtag_keys: Sequence[str], k: int, filters: Any =
         keys = list(dtag_keys)
         flt: Filter = t.filter_corpus(filters, include_document_ids)
         n = len(t)
-        words = (n + 31) // 32
-        mask = np.zeros(words + 1, dtype=np.uint32)
-        n_total, per_key = 0, {}
-        for lo in range(0, len(keys), 32):                          # the kernel takes 32 codes per pass: any number of keys
-            part = keys[lo:lo + 32]
-            codes = (C.c_uint16 * len(part))(*[ht.dcodes.get(key, 0xFFFF) for key in part])   # 0xFFFF: a key no chunk has
-            m = np.zeros(words + 1, dtype=np.uint32)
-            counts = (C.c_int64 * (len(part) + 1))()
-            N.check(t.index._lib.mrag_dtag_mask(t.index._h, flt.ref() if flt.active else None, codes, len(part),
-                                                m.ctypes.data, counts))
-            mask |= m
-            n_total = int(counts[0])
-            for i, key in enumerate(part):
-                per_key[key] = int(counts[1 + i])
-        # matching rows from the non-zero words only (no N-sized temporary)
-        wz = np.flatnonzero(mask[:words])
-        bits = (mask[wz, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
-        rows = (wz[:, None] * 32 + np.arange(32)[None, :])[bits.astype(bool)]
-        rows = rows[rows < n]
+        rows, n_total, counts = t.index.dtag_rows(flt, [ht.dcodes.get(key, 0xFFFF) for key in keys])   # 0xFFFF: a key no chunk has
+        per_key = dict(zip(keys, counts))
         idf_weights: dict[str, float] = {}
         if idf_mode:
             for key in keys:

@@ -229,6 +229,42 @@ class Index:
             raise ValueError("feat must be a 1-D FEAT_DTYPE array")
         N.check(self._lib.mrag_set_chunk_features(self._h, int(first_row), feat.ctypes.data, feat.shape[0]))
 
+    def set_dtag_overflow(self, rows: np.ndarray, codes: np.ndarray) -> None:
+        """chunk d-tag keys beyond the four inline slots: (row, code) pairs sorted by row; replaces the whole table"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint16)
+        N.check(self._lib.mrag_set_dtag_overflow(self._h, rows.ctypes.data if rows.size else None,
+                                                 codes.ctypes.data if codes.size else None, int(rows.size)))
+
+    def dtag_rows(self, flt: "Filter | None", codes: Sequence[int]):
+        """The d-tag arm's WHERE on the GPU (mrag_dtag_mask): (rows whose chunk_d_tags hold any of `codes` among the LIVE rows
+        that pass flt, ascending; n_total = live rows passing flt; per-code counts).  Any number of codes (32 per pass)."""
+        n = len(self)
+        words = (n + 31) // 32
+        mask = np.zeros(words + 1, dtype=np.uint32)
+        n_total, per_code = 0, []
+        codes = [int(c) for c in codes]
+        for lo in range(0, max(len(codes), 1), 32):
+            part = codes[lo:lo + 32]
+            arr = (C.c_uint16 * max(1, len(part)))(*part)
+            m = np.zeros(words + 1, dtype=np.uint32)
+            counts = (C.c_int64 * (len(part) + 1))()
+            N.check(self._lib.mrag_dtag_mask(self._h, flt.ref() if (flt is not None and flt.active) else None, arr, len(part),
+                                             m.ctypes.data, counts))
+            mask |= m
+            n_total = int(counts[0])
+            per_code += [int(counts[1 + i]) for i in range(len(part))]
+        wz = np.flatnonzero(mask[:words])                      # expand the non-zero words only (no N-sized temporary)
+        bits = (mask[wz, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        rows = (wz[:, None] * 32 + np.arange(32)[None, :])[bits.astype(bool)]
+        return rows[rows < n], n_total, per_code
+
+    def rerank_candidates(self, cands, n: int, hq):
+        """mrag_rerank_candidates: (scores f32 [n], coverage f32 [n], keep u8 [n]) for a ctypes array of N.Candidate"""
+        scores, cov, keep = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        N.check(self._lib.mrag_rerank_candidates(self._h, cands, int(n), C.byref(hq), scores.ctypes.data, cov.ctypes.data, keep.ctypes.data))
+        return scores, cov, keep
+
     def set_doc_jtags(self, first_doc: int, bits: np.ndarray) -> None:
         bits = np.ascontiguousarray(bits, dtype=np.uint64)
         if bits.ndim != 2 or bits.shape[1] != N.MRAG_JTAG_WORDS:

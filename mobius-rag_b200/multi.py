@@ -40,6 +40,7 @@ class MultiIndex:
         self.pos_shard = np.zeros(1024, dtype=np.uint8)                 # host position -> shard
         self.pos_local = np.zeros(1024, dtype=np.int64)                 # host position -> row inside that shard
         self.doc_home: dict[int, int] = {}                              # doc_idx -> shard
+        self.shard_ids: list[list[np.ndarray]] = [[] for _ in self.devices]   # per shard: host positions of its rows, in row order
         self._last_kind = "none"
 
     # -- lifecycle ---------------------------------------------------------------------------
@@ -93,6 +94,7 @@ class MultiIndex:
             assert got == base
             self.pos_shard[first + sel] = s
             self.pos_local[first + sel] = base + np.arange(sel.size)
+            self.shard_ids[s].append(ids)
         self._n = need
         return first
 
@@ -114,6 +116,7 @@ class MultiIndex:
             self.pos_local = np.concatenate([self.pos_local, np.zeros(cap - self.pos_local.shape[0], dtype=np.int64)])
         self.pos_shard[first:need] = s
         self.pos_local[first:need] = base + np.arange(m)
+        self.shard_ids[s].append(ids)
         for d in np.unique(meta["doc_idx"]):
             self.doc_home.setdefault(int(d), s)
         self._n = need
@@ -138,6 +141,50 @@ class MultiIndex:
             # rows of one shard inside a host range are consecutive there as well (both orders are append order)
             assert (np.diff(loc) == 1).all()
             ix.set_chunk_features(int(loc[0]), np.ascontiguousarray(feat[sel]))
+
+    def _ids_of(self, s: int) -> np.ndarray:
+        if len(self.shard_ids[s]) > 1:
+            self.shard_ids[s] = [np.concatenate(self.shard_ids[s])]
+        return self.shard_ids[s][0] if self.shard_ids[s] else np.zeros(0, dtype=np.int64)
+
+    def set_dtag_overflow(self, rows: np.ndarray, codes: np.ndarray) -> None:
+        rows = np.asarray(rows, dtype=np.int64)
+        codes = np.asarray(codes, dtype=np.uint16)
+        sh, lo = self.pos_shard[rows], self.pos_local[rows]
+        for s, ix in enumerate(self.shards):
+            sel = np.flatnonzero(sh == s)
+            order = sel[np.argsort(lo[sel], kind="stable")]
+            ix.set_dtag_overflow(lo[order].astype(np.uint32), codes[order])
+
+    def dtag_rows(self, flt, codes):
+        """as Index.dtag_rows over every shard; rows come back as host positions"""
+        rows, n_total, per_code = [], 0, None
+        for s, ix in enumerate(self.shards):
+            r, nt, pc = ix.dtag_rows(flt, codes)
+            rows.append(self._ids_of(s)[r])
+            n_total += nt
+            per_code = pc if per_code is None else [a + b for a, b in zip(per_code, pc)]
+        return np.sort(np.concatenate(rows)) if rows else np.zeros(0, dtype=np.int64), n_total, per_code or []
+
+    def rerank_candidates(self, cands, n: int, hq):
+        return self.shards[0].rerank_candidates(cands, n, hq)       # every shard holds all per-document tag sets
+
+    def search_hybrid(self, Q: np.ndarray, k: int, hq, flt: Filter | None = None):
+        """the fused hybrid rerank on every shard, then a k-way merge of the <= 8 short lists (score DESC, id ASC)"""
+        parts = [ix.search_hybrid(Q, k, hq, flt) for ix in self.shards]
+        nq = parts[0][0].shape[0]
+        scores = np.full((nq, k), np.nan, dtype=np.float32)
+        cos = np.full((nq, k), np.nan, dtype=np.float32)
+        rows = np.full((nq, k), -1, dtype=np.int64)
+        counts = np.zeros(nq, dtype=np.int32)
+        for q in range(nq):
+            s_all = np.concatenate([p[0][q, :int(p[3][q])] for p in parts])
+            c_all = np.concatenate([p[1][q, :int(p[3][q])] for p in parts])
+            r_all = np.concatenate([p[2][q, :int(p[3][q])] for p in parts])
+            order = np.lexsort((r_all, -s_all))[:k]
+            m = order.shape[0]
+            scores[q, :m], cos[q, :m], rows[q, :m], counts[q] = s_all[order], c_all[order], r_all[order], m
+        return scores, cos, rows, counts
 
     def tombstone_doc(self, doc_idx: int) -> int:
         s = self.doc_home.get(int(doc_idx))
@@ -211,6 +258,7 @@ class MultiIndex:
         for s, ix in enumerate(self.shards):
             ix.save(f"{path}.{s}", version)
         np.savez(path + ".routing.npz", pos_shard=self.pos_shard[:self._n], pos_local=self.pos_local[:self._n],
+                 **{f"ids{s}": self._ids_of(s) for s in range(len(self.shards))},
                  doc_home=np.asarray(sorted(self.doc_home.items()), dtype=np.int64).reshape(-1, 2), n=np.int64(self._n))
 
     @classmethod
@@ -221,6 +269,7 @@ class MultiIndex:
         self._n = int(z["n"])
         self.pos_shard, self.pos_local = z["pos_shard"].copy(), z["pos_local"].copy()
         self.doc_home = {int(a): int(b) for a, b in z["doc_home"]}
+        self.shard_ids = [[z[f"ids{s}"].copy()] for s in range(len(self.devices))]
         s = len(self.devices)
         per = 0 if capacity <= 0 else (int(capacity) * 11 // 10 + s - 1) // s + 1024
         self.shards, ver = [], 0

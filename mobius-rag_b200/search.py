@@ -177,10 +177,7 @@ def rerank_candidates(ht: "H.HybridTable", chunks: list[dict], search_id: str = 
         cats = H.classify_jpd(body) if hq.w_jpd > 0 else {}
         jpd_tags.append(sorted({JPD_FAMILY.get(k, "O") for k in sorted(cats, key=lambda k: -cats[k])[:2]}))
     hq.auth_score[31] = H.AUTHORITY_DEFAULT
-    n = len(chunks)
-    scores, cov, keep = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
-    index = getattr(t.index, "shards", [t.index])[0]
-    N.check(index._lib.mrag_rerank_candidates(index._h, cands, n, C.byref(hq), scores.ctypes.data, cov.ctypes.data, keep.ctypes.data))
+    scores, cov, keep = t.index.rerank_candidates(cands, len(chunks), hq)
     survivors = []
     for i, c in enumerate(chunks):
         c["rerank_score"] = float(scores[i])

@@ -16,14 +16,16 @@ pytestmark = pytest.mark.gpu
 CASES = load_golden_json("corpus_search.json")
 
 
-@pytest.fixture(scope="module")
-def ht():
+@pytest.fixture(scope="module", params=["one shard", "three shards in one process"])
+def ht(request):
     import mrag_b200
+    devices = None if request.param == "one shard" else [0, 0, 0]
     tj = load_golden_json("hybrid_table.json")
     X = np.load(os.path.join(GOLDEN_DIR, "hybrid_vectors.npz"))["X"]
     rows = tj["rows"] = [dict(r, page_number=(i // 4) % 30 + 1) for i, r in enumerate(tj["rows"])]   # as make_corpus_search_golden
-    pt = mrag_b200.PublishedTable(X.shape[1], dtype="f32", device=0, capacity=len(rows) + 8)
-    pt.insert(rows, [X[i].tolist() if r["has_vec"] else None for i, r in enumerate(rows)])
+    pt = mrag_b200.PublishedTable(X.shape[1], dtype="f32", device=0, capacity=len(rows) + 8, devices=devices)
+    for lo in range(0, len(rows), 50):                       # the embedding worker's batch size (embedding_worker.py:256)
+        pt.insert(rows[lo:lo + 50], [X[i].tolist() if rows[i]["has_vec"] else None for i in range(lo, min(lo + 50, len(rows)))])
     for d in tj["docs"]:
         if d["has_tags_row"]:
             pt.set_document_tags(d["document_id"], d["d_tags"], d["p_tags"], d["j_tags"])
