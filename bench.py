@@ -413,18 +413,22 @@ def run_c5(args, idx, plant, dev, n_local, world, rank, hbm_peak, peak_src, t_bu
     idx.set_doc_jtags(0, jt)
     t_feat = time.perf_counter() - t0
     # ---- the query bank: 22 queries shaped like eval/queries.yaml entries, 1-4 required phrases each
+    # (its own generator: the bank does not depend on the corpus layout.  Shape of eval/queries.yaml entries: a payer / state
+    #  phrase that carries a j: code -- binary credit for every chunk of a tagged document -- only next to topical phrases,
+    #  which are substring-tested; some topical phrases carry a d: code)
+    qrng = np.random.default_rng(56)
     hq = (N.HybridQuery * nq)()
     for i in range(nq):
         h = hq[i]
-        npz = int(rng.integers(1, 5))
+        npz = int(qrng.integers(1, 5))
         h.n_phrases = npz
         for j in range(npz):
-            h.phrase_weight[j] = float(rng.uniform(0.65, 1.0))
-            h.phrase_bit[j] = int(rng.integers(0, 64))
-            h.phrase_jbit[j] = int(rng.integers(0, 8)) if rng.random() < 0.3 else -1
-            h.phrase_dcode[j] = int(rng.integers(1, 33)) if rng.random() < 0.2 else 0
+            h.phrase_weight[j] = float(qrng.uniform(0.65, 1.0))
+            h.phrase_bit[j] = int(qrng.integers(0, 64))
+            h.phrase_jbit[j] = int(qrng.integers(0, 8)) if (j == 0 and npz >= 2 and qrng.random() < 0.5) else -1
+            h.phrase_dcode[j] = int(qrng.integers(1, 33)) if (h.phrase_jbit[j] < 0 and qrng.random() < 0.2) else 0
         for c in range(N.MRAG_JPD_CATS):
-            h.qcat[c] = float(rng.random() < 0.2) * 0.4
+            h.qcat[c] = float(qrng.random() < 0.2) * 0.4
         for a in range(32):
             h.auth_score[a] = 0.1
         h.w_sim, h.w_auth, h.w_len, h.w_cov, h.boost, h.floor = 0.25, 0.10, 0.05, 0.55, 1.5, 1.0

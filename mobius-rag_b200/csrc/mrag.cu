@@ -111,7 +111,7 @@ struct Workspace {
     EventSet ev;
     DevBuf<float> qraw, qpad, qinv, scores;
     DevBuf<__nv_bfloat16> qbf;
-    DevBuf<uint32_t> mask, pool, pool_bits, gthr;
+    DevBuf<uint32_t> mask, pool, pool_bits, gthr, qhl;
     DevBuf<uint64_t> part, part2, part3, ub, gcand;
     DevBuf<int64_t> rows, crows;
     DevBuf<int32_t> counts, ccounts;
@@ -124,7 +124,7 @@ struct Workspace {
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
-        qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release();
+        qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release(); qhl.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
         rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
@@ -1036,7 +1036,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     int gskip = 0;
     if (exact_mma) {
         MmaArgs e{};
-        e.n = n; e.ld = ld; e.mask = mask; e.inv_norm = x->inv_norm; e.q = w->qpad.p; e.qinv = w->qinv.p;
+        e.n = n; e.ld = ld; e.mask = mask; e.inv_norm = x->inv_norm; e.q = w->qpad.p; e.qinv = w->qinv.p; e.qhl = (getenv("MRAG_QHL") && getenv("MRAG_QHL")[0] == '0') ? nullptr : w->qhl.p;
         e.part = w->part.p; e.k = k; e.kp = kp; e.P = grid; e.cap = k + kMmaSlack; e.gthr = w->gthr.p; e.tile_mul = 1;
         e.sleep_ns = mma_sleep_ns(); e.qlist = w->fb.p + 1; e.qcount = w->fb.p;
         rc = launch_scan_mma<0>(x, e, /*nq=*/1, grid, s);        // one launch; the kernel reads the list length itself
@@ -1093,8 +1093,15 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     if (w->qpad.reserve(size_t(nq) * ld) || w->qinv.reserve(size_t(nq)) || w->flags.reserve(4) ||
         w->counts.reserve(size_t(nq)) || w->scores.reserve(nk) || w->rows.reserve(nk))
         return MRAG_ERR_OOM;
+    // bf16 shards: also the packed hi / lo planes the exact tensor-core scan loads into tensor memory
+    uint32_t* qhl = nullptr;
+    static const bool qhl_ok = [] { const char* e = getenv("MRAG_QHL"); return !(e && e[0] == '0'); }();    // MRAG_QHL=0: split in the scan (A/B)
+    if (qhl_ok && x->has_tmap && x->dtype == MRAG_BF16) {
+        if (w->qhl.reserve(size_t(nq) * ld)) return MRAG_ERR_OOM;
+        qhl = w->qhl.p;
+    }
     query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(d_q, nq, x->dim, ld, w->qpad.p,
-                                                                               w->qinv.p, nullptr, nq);
+                                                                               w->qinv.p, nullptr, nq, qhl);
     LAUNCHED();
     CU(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), s));
 
@@ -1164,6 +1171,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (n > 0 && use_mma) {
             MmaArgs a{};
             a.n = n; a.ld = ld; a.mask = mask; a.inv_norm = x->inv_norm; a.q = w->qpad.p; a.qinv = w->qinv.p;
+            a.qhl = qhl;
             a.ub = (r > 0) ? w->ub.p : nullptr;
             a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid; a.cap = kr + kMmaSlack;
             if (w->gthr.reserve(size_t(nq))) return MRAG_ERR_OOM;
@@ -1507,7 +1515,7 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         w->cscores.reserve(nk) || w->hyb.reserve(size_t(nq)))
         return MRAG_ERR_OOM;
     CU(cudaMemcpyAsync(w->qraw.p, q, size_t(nq) * x->dim * 4, cudaMemcpyHostToDevice, s));
-    query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(w->qraw.p, nq, x->dim, ld, w->qpad.p, w->qinv.p, nullptr, nq);
+    query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(w->qraw.p, nq, x->dim, ld, w->qpad.p, w->qinv.p, nullptr, nq, nullptr);
     LAUNCHED();
     std::vector<DevHyb> dh;
     dh.resize(size_t(nq));

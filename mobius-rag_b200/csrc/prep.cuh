@@ -228,10 +228,13 @@ __global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n
     }
 }
 
-// one warp per query: zero-pad to ld, 1/|q| (float4 query, vector_store.py:272), bf16 copy
+// one warp per query: zero-pad to ld, 1/|q| (float4 query, vector_store.py:272), bf16 copy; qhl (optional): the tensor-memory
+// image of the exact scan's A operand -- per query a plane of bf16 `hi` pairs and a plane of bf16 `lo` pairs (q = hi + lo to
+// 16 mantissa bits, element 2c in the low half of word c), so that every scan CTA loads packed words instead of splitting
+// 64 x ld floats itself
 __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ q, int nq, int dim, int ld,
                                                         float* __restrict__ qpad, float* __restrict__ qinv,
-                                                        __nv_bfloat16* __restrict__ qbf, int nq_pad) {
+                                                        __nv_bfloat16* __restrict__ qbf, int nq_pad, uint32_t* __restrict__ qhl) {
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq_pad) return;
@@ -240,6 +243,13 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict
         float v = (i < nq && e < dim) ? q[size_t(i) * dim + e] : 0.0f;
         if (i < nq) qpad[size_t(i) * ld + e] = v;
         if (qbf) qbf[size_t(i) * ld + e] = __float2bfloat16_rn(v);
+        if (qhl && i < nq) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));      // q - hi is exact in fp32
+            __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(qhl) + size_t(i) * 2 * ld;
+            planes[e] = hi;
+            planes[ld + e] = lo;
+        }
         ss = fmaf(v, v, ss);
     }
     ss = warp_sum(ss);

@@ -75,6 +75,7 @@ struct MmaArgs {
     const uint32_t* mask;    // row bitmap (valid AND filter), ceil(n/32) words
     const float* inv_norm;   // [n] 1/|x| of the stored row (+inf for a zero row)
     const float* q;          // [*][ld] fp32 queries, zero padded
+    const uint32_t* qhl;     // [*][2][ld/2] the same queries as packed bf16 hi / lo planes (query_prep_kernel); nullptr: split here
     const float* qinv;       // [*] 1/|q| (+inf for a zero query)
     const uint64_t* ub;      // [*] exclusive upper-bound key per query, or nullptr
     uint64_t* part;          // [*][P][kp] per-CTA sorted candidate lists
@@ -460,8 +461,30 @@ __global__ void __launch_bounds__(KS ? kMmaKsThreads : kMmaThreads, 1) scan_mma_
     if (warp >= 2 && warp < 6) {
         const bool live = qi < nq_eff;
         const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
+        const int ncols = kblocks * (kMmaKBlock / 2);
+        if (a.qhl) {
+            // packed planes: two 32-column chunks in flight per round (16 x 128-bit loads), no conversion
+            const uint4* src = reinterpret_cast<const uint4*>(a.qhl + (size_t(qsrc) * 2 + (hi_part ? 0 : 1)) * (a.ld / 2) + size_t(kb0) * (kMmaKBlock / 2));
+            for (int c0 = 0; c0 < ncols; c0 += 64) {
+                uint32_t r0[32], r1[32];
+                const bool two = c0 + 32 < ncols;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 u = live ? __ldg(src + c0 / 4 + v) : make_uint4(0u, 0u, 0u, 0u);
+                    r0[4 * v] = u.x; r0[4 * v + 1] = u.y; r0[4 * v + 2] = u.z; r0[4 * v + 3] = u.w;
+                }
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 u = (live && two) ? __ldg(src + c0 / 4 + 8 + v) : make_uint4(0u, 0u, 0u, 0u);
+                    r1[4 * v] = u.x; r1[4 * v + 1] = u.y; r1[4 * v + 2] = u.z; r1[4 * v + 3] = u.w;
+                }
+                const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0);
+                MRAG_TMEM_ST32(taddr, r0);
+                if (two) MRAG_TMEM_ST32(taddr + 32u, r1);
+            }
+        } else {
         const float* qrow = a.q + size_t(qsrc) * a.ld + size_t(kb0) * kMmaKBlock;
-        for (int c0 = 0; c0 < kblocks * (kMmaKBlock / 2); c0 += 32) {     // 32 columns = 64 elements per store
+        for (int c0 = 0; c0 < ncols; c0 += 32) {     // 32 columns = 64 elements per store
             uint32_t r[32];
 #pragma unroll
             for (int v = 0; v < 16; ++v) {
@@ -477,6 +500,7 @@ __global__ void __launch_bounds__(KS ? kMmaKsThreads : kMmaThreads, 1) scan_mma_
             }
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0);
             MRAG_TMEM_ST32(taddr, r);
+        }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 #if MRAG_QREADY_BAR
