@@ -775,7 +775,7 @@ static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
     return MRAG_OK;
 }
 
-// largest k of the candidate-generating path: K' = 1.5 k nominees + 32 slack keys must fit a warp's rank sort (192 keys)
+// largest k of the candidate-generating path: K' = 2 k nominees + 32 slack keys must fit a warp's rank sort (256 keys)
 static const int kMma128MaxK = 106;
 
 // fp32 shards: nominate from the bf16 shadow on the CUDA cores when the shard is big enough for the halved traffic to
@@ -906,7 +906,9 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     const int64_t n = x->size;
     const int ld = x->ld;
     // nominees per query: k + 32, or 1.5 k for large k (the number of rows within eps of the k-th best grows with k)
-    const int kc = std::max(k + 32, k + k / 2), kpc = host_next_pow2(kc);
+    // (k > 64: 2k -- the number of rows within eps of the k-th best grows with k; MRAG_KC_2K=0 restores 1.5k for A/B)
+    static const bool kc_2k = [] { const char* e = getenv("MRAG_KC_2K"); return !(e && e[0] == '0'); }();
+    const int kc = (k > 64 && kc_2k) ? 2 * k : std::max(k + 32, k + k / 2), kpc = host_next_pow2(kc);
     const int cap = kc + kMma128Slack;
     const bool global_cand = mma128_smem_bytes(12, cap) > size_t(kMaxSmem);      // keep >= 12 stages (96 KB) in flight
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(n, kMmaTileRows))));

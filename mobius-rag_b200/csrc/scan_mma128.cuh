@@ -38,13 +38,16 @@ MRAG_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64
                  : "memory");
 }
 
-// rank sort like warp_rank_select, with the per-lane work bounded by the lanes actually in use
+// rank sort like warp_rank_select, with the per-lane work bounded by the lanes actually in use; up to 256 keys
+// (K' = 2k nominees + 32 slack keys for k up to 106: with K' = 1.5k a few certificates per 256 queries failed at k = 100
+//  and each failure cost one exact pass over the shard)
+constexpr int kRank128PerLane = 8;
 MRAG_DEVINL void warp_rank_select_n(uint64_t* buf, int n, int keep, int lane) {
-    uint64_t key[kRankPerLane];
-    int rank[kRankPerLane];
+    uint64_t key[kRank128PerLane];
+    int rank[kRank128PerLane];
     const int ne = (n + 31) >> 5;             // warp uniform
 #pragma unroll
-    for (int e = 0; e < kRankPerLane; ++e) {
+    for (int e = 0; e < kRank128PerLane; ++e) {
         const int i = lane + 32 * e;
         key[e] = (i < n) ? buf[i] : 0ull;
         rank[e] = 0;
@@ -52,12 +55,12 @@ MRAG_DEVINL void warp_rank_select_n(uint64_t* buf, int n, int keep, int lane) {
     for (int j = 0; j < n; ++j) {
         const uint64_t kj = buf[j];           // broadcast read
 #pragma unroll
-        for (int e = 0; e < kRankPerLane; ++e)
+        for (int e = 0; e < kRank128PerLane; ++e)
             if (e < ne) rank[e] += (kj > key[e]) ? 1 : 0;
     }
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < kRankPerLane; ++e) {
+    for (int e = 0; e < kRank128PerLane; ++e) {
         const int i = lane + 32 * e;
         if (i < n && rank[e] < keep) buf[rank[e]] = key[e];
     }

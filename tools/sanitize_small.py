@@ -42,4 +42,33 @@ for dtype in ("f32", "bf16"):
     print("hybrid", int(out[3][0]))
     idx.tombstone_doc(3)
     idx.close()
+# round 2: the k-split pair kernel (rows of 1536 elements), the pool cascade, the candidate rerank, explicit row ids
+Xw, vw = synth.make_corpus(700, 1536, seed=9)
+idx = Index(1536, "bf16", 0, 800)
+ids = np.arange(1000, 1700, dtype=np.int64)
+N.check(idx._lib.mrag_set_row_ids(idx._h, 0, ids.ctypes.data, 700))
+idx.append(Xw, None)
+for nq, k in ((1, 10), (40, 10), (70, 100)):
+    s, r, c = idx.search(synth.make_queries(Xw, nq, seed=nq), k)
+    print("ks", nq, k, idx.last_scan_kind(), int(c[0]), int(r[0, 0]))
+idx.set_doc_tags(0, np.ones((700, N.MRAG_TAG_WORDS), dtype=np.uint64))
+idx.set_doc_jtags(0, np.ones((700, N.MRAG_JTAG_WORDS), dtype=np.uint64))
+import ctypes as C
+q = N.PoolQuery()
+q.d_all[0] = 1; q.j_all[0] = 1; q.ahca[0] = 1; q.has_d = q.has_j = q.has_ahca = 1
+h = C.c_void_p(); counts = (C.c_int64 * 5)()
+N.check(idx._lib.mrag_pool_build(idx._h, C.byref(q), C.byref(h), counts))
+kept = C.c_int64()
+N.check(idx._lib.mrag_pool_select(h, 1, 100, C.byref(kept)))
+print("pool", list(counts), kept.value)
+s, r, c = idx.search(synth.make_queries(Xw, 3, seed=1), 5, Filter().pool_handle(h))
+print("pool search", int(c[0]))
+N.check(idx._lib.mrag_pool_destroy(h))
+cands = (N.Candidate * 50)()
+hq1 = N.HybridQuery()
+hq1.w_sim, hq1.w_auth, hq1.w_len = 0.25, 0.1, 0.05
+for i in range(50):
+    cands[i].sim = i / 50.0
+print("rerank", float(idx.rerank_candidates(cands, 50, hq1)[0][49]))
+idx.close()
 print("sanitize driver done")
