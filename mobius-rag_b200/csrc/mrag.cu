@@ -111,7 +111,7 @@ struct Workspace {
     EventSet ev;
     DevBuf<float> qraw, qpad, qinv, scores;
     DevBuf<__nv_bfloat16> qbf;
-    DevBuf<uint32_t> mask, pool, pool_bits, gthr, qhl;
+    DevBuf<uint32_t> mask, pool, pool_bits, gthr, qhl, gmax;
     DevBuf<uint64_t> part, part2, part3, ub, gcand;
     DevBuf<int64_t> rows, crows;
     DevBuf<int32_t> counts, ccounts;
@@ -125,7 +125,7 @@ struct Workspace {
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release(); qhl.release();
-        mask.release(); pool.release(); pool_bits.release(); gthr.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
+        mask.release(); pool.release(); pool_bits.release(); gthr.release(); gmax.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
         rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -958,6 +958,10 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         t_stats_ptr = w->stats.p;
     }
     const int64_t tiles = ceil_div(n, kMmaTileRows);
+    // (the group-maxima bound of the exact scan was tried here too, with K' <= 64 groups: r2n, 10M x 768, k = 10: 1-3 % slower
+    //  than the sampling launches at 128 / 256 / 1024 queries and 0.52 against 0.35 ms on config 2, whose tag filter leaves a
+    //  CTA ~10 tiles -- with K' = 42 groups of 3.5 producers the bound is 4x looser in rank than the union's and the first
+    //  tile of every producer is admitted whole)
     if (tiles >= sample_min_tiles(x->num_sms)) {
         // admission bound from a strided sample, same arithmetic, the best kMmaSampleK scores per (query, CTA) in registers:
         // the K'-th best of the union of the per-CTA lists is reached by K' known rows, so the full pass may skip anything
@@ -1102,10 +1106,17 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (w->qhl.reserve(size_t(nq) * ld)) return MRAG_ERR_OOM;
         qhl = w->qhl.p;
     }
+    // cross-CTA admission bound of the exact tensor-core scan (k <= 16): group maxima (scan_mma.cuh, GroupBound) instead of a
+    // threshold-sampling launch.  MRAG_GMAX: 0 = sampling launches as before, 1 = group maxima + register top-k,
+    // 2 (default) = group maxima + shared-memory candidate buffers on shards of >= sample_min_tiles tiles
+    // (measured r2m, 1.25M x 768, 64 queries, k = 10: 0.378 / 0.480 / 0.349 ms per step)
+    static const int gmax_mode = [] { const char* e = getenv("MRAG_GMAX"); return (e && *e) ? atoi(e) : 2; }();
+    const bool use_gmax = gmax_mode > 0 && x->has_tmap && x->dtype == MRAG_BF16 && k <= kMmaRegK;
+    if (w->gthr.reserve(size_t(nq)) || (use_gmax && w->gmax.reserve(size_t(nq) * 16))) return MRAG_ERR_OOM;
     query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(d_q, nq, x->dim, ld, w->qpad.p,
-                                                                               w->qinv.p, nullptr, nq, qhl);
+                                                                               w->qinv.p, nullptr, nq, qhl, w->gthr.p,
+                                                                               use_gmax ? w->gmax.p : nullptr, k, 16, w->flags.p);
     LAUNCHED();
-    CU(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), s));
 
     float* d_scores = dev_io ? scores : w->scores.p;
     int64_t* d_rows = dev_io ? rows : w->rows.p;
@@ -1176,9 +1187,10 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             a.qhl = qhl;
             a.ub = (r > 0) ? w->ub.p : nullptr;
             a.part = w->part.p; a.k = kr; a.kp = kp; a.P = grid; a.cap = kr + kMmaSlack;
-            if (w->gthr.reserve(size_t(nq))) return MRAG_ERR_OOM;
-            CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
+            if (r > 0) CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));      // (round 0: cleared by query_prep_kernel)
             a.gthr = w->gthr.p;
+            const bool gmax_on = use_gmax && rounds == 1;
+            if (gmax_on) { a.gmax = w->gmax.p; a.ngroups = kr; a.gslots = 16; }
             a.tile_mul = 1;
             a.stats = nullptr;
             a.tstamps = nullptr;
@@ -1194,7 +1206,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                 t_stats_ptr = w->stats.p;
             }
             const int64_t tiles = ceil_div(n, kMmaTileRows);
-            const bool sampled = tiles >= sample_min_tiles(mma_units);
+            const bool sampled = !gmax_on && tiles >= sample_min_tiles(mma_units);
             if (sampled) {
                 // always the register top-k kernel: each CTA keeps the kMmaSampleK best scores of a few tiles per query and
                 // the merge takes the k-th best of the union (k known rows reach it, so it is a valid bound; a CTA holds
@@ -1228,7 +1240,8 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             }
             // unsampled shards: register top-k by default; MRAG_UNSAMPLED_BUFFER=1 pins the shared-memory buffer kernel (tuning)
             static const bool unsampled_buffer = [] { const char* e = getenv("MRAG_UNSAMPLED_BUFFER"); return e && e[0] == '1'; }();
-            int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!sampled && !unsampled_buffer, s);
+            const bool buffers = gmax_on ? (gmax_mode == 2 && tiles >= sample_min_tiles(mma_units)) : (sampled || unsampled_buffer);
+            int rc = run_scan_mma(x, a, nq, grid, /*reg_topk=*/!buffers, s);
             if (rc != MRAG_OK) return rc;
             t_last_kind = ksplit ? "mma_ks" : "mma";
         } else if (n > 0) {

@@ -234,10 +234,20 @@ __global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n
 // 64 x ld floats itself
 __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ q, int nq, int dim, int ld,
                                                         float* __restrict__ qpad, float* __restrict__ qinv,
-                                                        __nv_bfloat16* __restrict__ qbf, int nq_pad, uint32_t* __restrict__ qhl) {
+                                                        __nv_bfloat16* __restrict__ qbf, int nq_pad, uint32_t* __restrict__ qhl,
+                                                        uint32_t* __restrict__ gthr = nullptr, uint32_t* __restrict__ gmax = nullptr,
+                                                        int gk = 0, int gslots = 16, int* __restrict__ flags4 = nullptr) {
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq_pad) return;
+    // per-search scratch the scan expects cleared (saves the memset launches): the cross-CTA bound of query i, its group
+    // maxima (slots [gk, 16) can never be the minimum), the four step flags
+    if (i < nq) {
+        if (gthr && lane == 0) gthr[i] = 0u;
+        if (gmax)
+            for (int j = lane; j < gslots; j += 32) gmax[size_t(i) * gslots + j] = j < gk ? 0u : 0xFFFFFFFFu;
+    }
+    if (flags4 && i == 0 && lane < 4) flags4[lane] = 0;
     float ss = 0.0f;
     for (int e = lane; e < ld; e += 32) {
         float v = (i < nq && e < dim) ? q[size_t(i) * dim + e] : 0.0f;
