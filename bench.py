@@ -644,6 +644,9 @@ def main():
         idx.close()
         return
 
+    # N > 1: overlap every step's exchange with the next step's scan (MRAG_PIPELINE=0: one search at a time)
+    pipelined = world > 1 and os.environ.get("MRAG_PIPELINE", "1") != "0"
+
     class Arm:
         """One resident shard + (N > 1) its cross-rank searcher; everything measured below goes through it."""
         def __init__(self, ix, dtype):
@@ -654,6 +657,23 @@ def main():
             if self.ss is not None:
                 return self.ss.search(qd, k, flt)
             return self.idx.search_device(qd, k, flt, out=out, sync=False)
+
+        def run(self, qd, k, steps, out=None):
+            """`steps` searches back to back; returns the last result.  N > 1: two searches in flight (search_async) -- the
+            exchange + k-way merge of step i runs on a side stream under the scan of step i + 1; every step's result is
+            taken (the caller's stream is ordered after its exchange) before step i + 2 is issued."""
+            res = None
+            if self.ss is not None and pipelined:
+                pend = None
+                for _ in range(steps):
+                    p = self.ss.search_async(qd, k, flt)
+                    if pend is not None:
+                        res = pend.result()
+                    pend = p
+                return pend.result() if pend is not None else res
+            for _ in range(steps):
+                res = self.step(qd, k, out)
+            return res
 
     def barrier():
         if world > 1:
@@ -674,8 +694,7 @@ def main():
             out = (torch.empty((batch, args.k), dtype=torch.float32, device=dev),
                    torch.empty((batch, args.k), dtype=torch.int64, device=dev),
                    torch.empty((batch,), dtype=torch.int32, device=dev))
-        for _ in range(max(warmup, 3)):
-            res = arm.step(Q, args.k, out)
+        res = arm.run(Q, args.k, max(warmup, 3), out)
         barrier()
         clocks = ClockSampler(local_rank) if sample_clocks else None
         if clocks:
@@ -685,8 +704,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(steps):
-            res = arm.step(Q, args.k, out)
+        res = arm.run(Q, args.k, steps, out)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
@@ -768,12 +786,33 @@ def main():
             s, r, c = ss.search(qd, args.k, flt)
             hs.copy_(s, non_blocking=True); hr.copy_(r, non_blocking=True); hc.copy_(c, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-    for _ in range(3):
-        e2e_step()
+
+    def e2e_run(steps):
+        if ss is None or not pipelined:
+            for _ in range(steps):
+                e2e_step()
+            return
+        # two requests in flight: H2D + scan of step i on the main stream, exchange + D2H of step i on the side stream;
+        # the host takes step i - 1's results (event) before it issues step i + 1
+        prev = None
+        for i in range(steps):
+            qd2[i & 1].copy_(Qh, non_blocking=True)
+            ev = ss.search_async(qd2[i & 1], args.k, flt).copy_to_host(hs2[i & 1], hr2[i & 1], hc2[i & 1])
+            if prev is not None:
+                prev.synchronize()
+            prev = ev
+        prev.synchronize()
+        j = (steps - 1) & 1
+        hs.copy_(hs2[j]); hr.copy_(hr2[j]); hc.copy_(hc2[j])
+    if ss is not None and pipelined:
+        qd2 = [torch.empty_like(m["Q"]) for _ in range(2)]
+        hs2 = [torch.empty_like(hs).pin_memory() for _ in range(2)]
+        hr2 = [torch.empty_like(hr).pin_memory() for _ in range(2)]
+        hc2 = [torch.empty_like(hc).pin_memory() for _ in range(2)]
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_qps = args.batch * args.steps / e2e_s
@@ -899,6 +938,8 @@ def main():
             line["shard_phases_ms"] = shard_phases
         if world > 1:
             line["config"]["exchange"] = exchange_name
+            line["config"]["pipeline"] = ("two searches in flight: exchange + k-way merge of step i on a side stream under the scan of step i + 1 "
+                                          "(shard_phases_ms is the one-search-at-a-time latency view)") if pipelined else "one search at a time"
         if concurrent:
             line["concurrent_single_query"] = concurrent
         print(json.dumps(line), flush=True)

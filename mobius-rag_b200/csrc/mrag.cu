@@ -233,6 +233,8 @@ static int make_corpus_tmap(mrag_index* x, CUtensorMap* out, void* base, int64_t
 // ------------------------------------------------------------------------------------------
 // lifecycle
 // ------------------------------------------------------------------------------------------
+static int set_search_chain_carveout(int device);
+
 extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int64_t capacity) {
     if (!out) return fail(MRAG_ERR_ARG, "mrag_create: out is null");
     *out = nullptr;
@@ -251,6 +253,7 @@ extern "C" int mrag_create(mrag_index** out, int dim, int dtype, int device, int
     if (prop.major < 10)
         return fail(MRAG_ERR_CUDA, "mrag_create: device %d is sm_%d%d; this library is built for sm_100a only",
                     device, prop.major, prop.minor);
+    if (int rc = set_search_chain_carveout(device)) return rc;
     mrag_index* x = new (std::nothrow) mrag_index();
     if (!x) return fail(MRAG_ERR_OOM, "mrag_create: host allocation failed");
     x->dim = dim;
@@ -541,6 +544,30 @@ extern "C" int mrag_tombstone_doc(mrag_index* x, uint32_t doc_idx, int64_t* n_ro
 // ------------------------------------------------------------------------------------------
 // workspaces
 // ------------------------------------------------------------------------------------------
+// The kernels of a search alternate with the tensor-core scans, which need the SM's largest shared-memory carve-out; an SM
+// only changes its carve-out while it is empty, so every small kernel of the chain asks for the same (maximal) carve-out
+// instead of its own default (MRAG_CARVEOUT=0: leave the defaults, for A/B).
+static int set_search_chain_carveout(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return MRAG_OK;
+    const char* e = getenv("MRAG_CARVEOUT");
+    if (!(e && e[0] == '0')) {
+        const int c = cudaSharedmemCarveoutMaxShared;
+        CU(cudaFuncSetAttribute(query_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(filter_mask_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(pool_bitmap_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(nan_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(remap_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(xmerge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(rescore_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(rescore_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+        CU(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+    }
+    done[device] = true;
+    return MRAG_OK;
+}
+
 static Workspace* acquire_ws(mrag_index* x, cudaStream_t want_stream) {
     std::lock_guard<std::mutex> l(x->ws_lock);
     Workspace* pick = nullptr;
@@ -684,7 +711,10 @@ static int run_scan_gemv(mrag_index* x, ScanArgs a, int nq, int grid, cudaStream
 static int mma_stages_for(int cap, bool ksplit = false) {
     const size_t fixed = mma_smem_bytes(0, cap, ksplit);
     if (fixed + 4 * size_t(kMmaStageBytes) > size_t(kMaxSmem)) return 0;
-    return int(std::min<size_t>(24, (size_t(kMaxSmem) - fixed) / kMmaStageBytes));
+    // leave 6 KB of the SM's shared memory free when the ring is deep anyway: the cross-rank exchange kernel of the previous
+    // search (1.5 KB + the per-block reserve) can then be resident beside a scan CTA
+    const size_t budget = (fixed + 16 * size_t(kMmaStageBytes) + 6144 <= size_t(kMaxSmem)) ? size_t(kMaxSmem) - 6144 : size_t(kMaxSmem);
+    return int(std::min<size_t>(24, (budget - fixed) / kMmaStageBytes));
 }
 
 // KS: the k-split pair kernel (rows of 769 .. 1536 elements): `grid` counts CTAs and is even, clusters of 2
@@ -896,6 +926,14 @@ static int launch_scan_mma256w(mrag_index* x, const MmaArgs& a, int nq, int npai
                             : launch_scan_mma256w_t<1>(x, a, nq, npairs, s);
 }
 
+// MRAG_EVENTS: which of a search's phase events are recorded in its stream.  2 (default): start / prepared / scanned / end;
+// 1: prepared / scanned / end (the scan phase only, what the roofline needs); 0: end only (workspace reuse needs it).
+// Measured r2q (1.25M x 768, 64 queries): see profiles/README.md.
+static int events_level() {
+    static const int v = [] { const char* e = getenv("MRAG_EVENTS"); return (e && *e) ? atoi(e) : 2; }();
+    return v;
+}
+
 // Large batches: candidate generation on the tensor cores (128 queries per pass over the bf16 rows or
 // the bf16 shadow), exact rescoring of the K' = k + 32 nominees from the primary rows, certificate,
 // exact CUDA-core rescan of the queries that fail it.  Results are EXACT (same arithmetic as scan_gemv).
@@ -1015,7 +1053,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     }
     if (rc != MRAG_OK) return rc;
     }
-    CU(cudaEventRecord(ev.e[2], s));
+    if (events_level() >= 1) CU(cudaEventRecord(ev.e[2], s));
     // nominees per query, by approximate score
     MergeArgs m{};
     m.part = w->part.p; m.P = gen_gemv ? ggrid : (use_pairs ? nparts : grid); m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
@@ -1088,7 +1126,8 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     const int ld = x->ld;
     const size_t nk = size_t(nq) * k;
 
-    CU(cudaEventRecord(ev.e[0], s));
+    const int evl = events_level();
+    if (evl >= 2) CU(cudaEventRecord(ev.e[0], s));
     // ---- queries
     const float* d_q = q;
     if (!dev_io) {
@@ -1130,7 +1169,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         if (rc != MRAG_OK) return rc;
         mask = w->mask.p;
     }
-    CU(cudaEventRecord(ev.e[1], s));
+    if (evl >= 1) CU(cudaEventRecord(ev.e[1], s));
 
     // ---- scan + select, MRAG_FUSED_K results per round
     const int rounds = int(ceil_div(k, MRAG_FUSED_K));
@@ -1256,12 +1295,14 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         } else {
             CU(cudaMemsetAsync(w->part.p, 0, size_t(nq) * grid * kp * 8, s));
         }
-        if (r == rounds - 1) CU(cudaEventRecord(ev.e[2], s));
+        if (r == rounds - 1 && evl >= 1) CU(cudaEventRecord(ev.e[2], s));
         MergeArgs m{};
         m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = kr; m.k_total = k; m.k_off = k_off;
         m.scores = d_scores; m.rows = d_rows; m.counts = d_counts; m.row_base = x->row_base;
         m.ub_out = (rounds > 1) ? w->ub.p : nullptr;
         m.need_tail = w->flags.p;
+        // the exact tensor-core scan leaves a bound that k rows of the query reach (group maxima / compactions) in gthr
+        if (n > 0 && use_mma && rounds == 1 && int64_t(grid) * kp <= kMergeSlots) m.thr_in = w->gthr.p;
         int rcm = launch_merge(w, m, nq, s);
         if (rcm != MRAG_OK) return rcm;
     }
@@ -2062,6 +2103,9 @@ extern "C" int mrag_exchange_merge(int device, int world, int rank, int nq, int 
     static bool attr_set[64] = {};
     if (device < 64 && !attr_set[device]) {
         CU(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXMergeMaxSlots * 12));
+        // same shared-memory carve-out as the scan kernels, so that an exchange block and a scan CTA can share an SM
+        // (an SM only changes its carve-out when it is empty)
+        CU(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[device] = true;
     }
     XchgArgs a{};
@@ -2077,7 +2121,9 @@ extern "C" int mrag_exchange_merge(int device, int world, int rank, int nq, int 
     a.scores_out = d_scores_out; a.rows_out = d_rows_out; a.counts_out = d_counts_out;
     const int total = world * k;
     const size_t smem = size_t(host_next_pow2(total < 2 ? 2 : total)) * 12;
-    xchg_merge_kernel<<<nq, kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    // small merges run with 128 threads (40 registers each): such a block fits on an SM beside a resident scan CTA, so an
+    // exchange issued on a side stream overlaps the NEXT search's scan (sharded.py, search_async)
+    xchg_merge_kernel<<<nq, total <= 256 ? 128 : kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     LAUNCHED();
     return MRAG_OK;
 }
@@ -2097,6 +2143,7 @@ static float phase_ms(const EventSet& ev, int what) {
         case 3: e = cudaEventElapsedTime(&ms, ev.e[0], ev.e[3]); break;
         default: return -1.0f;
     }
+    if (e != cudaSuccess) cudaGetLastError();       // (an event MRAG_EVENTS left out)
     return e == cudaSuccess ? ms : -1.0f;
 }
 

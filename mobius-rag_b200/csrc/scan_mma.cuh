@@ -511,24 +511,24 @@ __global__ void __launch_bounds__(KS ? kMmaKsThreads : kMmaThreads, 1) scan_mma_
         const int qsrc = live ? (a.qlist ? a.qlist[qi] : a.q0 + qi) : a.q0;
         const int ncols = kblocks * (kMmaKBlock / 2);
         if (a.qhl) {
-            // packed planes: two 32-column chunks in flight per round (16 x 128-bit loads), no conversion
+            // packed planes: four 32-column chunks (32 x 128-bit loads) in flight per round, no conversion -- the loads hit
+            // L2 (every CTA reads the same planes) and a round costs about one L2 round trip whatever its size
             const uint4* src = reinterpret_cast<const uint4*>(a.qhl + (size_t(qsrc) * 2 + (hi_part ? 0 : 1)) * (a.ld / 2) + size_t(kb0) * (kMmaKBlock / 2));
-            for (int c0 = 0; c0 < ncols; c0 += 64) {
-                uint32_t r0[32], r1[32];
-                const bool two = c0 + 32 < ncols;
+            for (int c0 = 0; c0 < ncols; c0 += 128) {
+                uint32_t r[4][32];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const uint4 u = live ? __ldg(src + c0 / 4 + v) : make_uint4(0u, 0u, 0u, 0u);
-                    r0[4 * v] = u.x; r0[4 * v + 1] = u.y; r0[4 * v + 2] = u.z; r0[4 * v + 3] = u.w;
-                }
+                for (int ch = 0; ch < 4; ++ch) {
+                    const bool on = live && c0 + 32 * ch < ncols;
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const uint4 u = (live && two) ? __ldg(src + c0 / 4 + 8 + v) : make_uint4(0u, 0u, 0u, 0u);
-                    r1[4 * v] = u.x; r1[4 * v + 1] = u.y; r1[4 * v + 2] = u.z; r1[4 * v + 3] = u.w;
+                    for (int v = 0; v < 8; ++v) {
+                        const uint4 u = on ? __ldg(src + c0 / 4 + 8 * ch + v) : make_uint4(0u, 0u, 0u, 0u);
+                        r[ch][4 * v] = u.x; r[ch][4 * v + 1] = u.y; r[ch][4 * v + 2] = u.z; r[ch][4 * v + 3] = u.w;
+                    }
                 }
                 const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0);
-                MRAG_TMEM_ST32(taddr, r0);
-                if (two) MRAG_TMEM_ST32(taddr + 32u, r1);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (c0 + 32 * ch < ncols) MRAG_TMEM_ST32(taddr + 32u * ch, r[ch]);
             }
         } else {
         const float* qrow = a.q + size_t(qsrc) * a.ld + size_t(kb0) * kMmaKBlock;

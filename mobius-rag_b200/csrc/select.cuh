@@ -38,6 +38,8 @@ struct MergeArgs {
     const int* qcount;
     int q_lo, q_hi;         // q_hi == 0 means no upper limit
     int no_clamp;           // hybrid rerank scores are not cosines: do not clamp them to [-1, 1]
+    const uint32_t* thr_in; // [nq] orderable(score) that k rows of the query are known to reach (the scan's cross-CTA bound), 0 =
+                            // unknown; or nullptr.  Replaces the pass over the lists' k-th entries: one dependent round trip less.
 };
 
 // Block-cooperative top-k of n UNIQUE non-zero keys in s[0..n): afterwards s[0..min(n,k)) holds the k largest,
@@ -122,7 +124,9 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     if (tid == 0) { s_T = 0ull; s_cnt = 0; }
     __syncthreads();
     uint64_t t = 0;
-    if (a.lk == 0 || a.lk >= a.k) {
+    if (a.thr_in) {
+        if (tid == 0) t = uint64_t(a.thr_in[q]) << 32;          // every key of a row scoring >= the bound compares >= t
+    } else if (a.lk == 0 || a.lk >= a.k) {
         for (int p = tid; p < P; p += kMergeThreads) {
             uint64_t v = base[size_t(p) * a.kp + (a.k - 1)];
             t = v > t ? v : t;
@@ -150,7 +154,27 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
         done += take;
         __syncthreads();
     }
-    const int got = block_topk(s, s_cnt, a.k, s_hist, s_small, s_misc);
+    int got;
+    if (s_cnt <= 32) {
+        // the usual case with a tight bound: a handful of survivors -- one warp ranks them with shuffles
+        got = s_cnt < a.k ? s_cnt : a.k;
+        __syncthreads();
+        if (tid < 32) {
+            const int n = s_cnt;
+            const uint64_t mine = tid < n ? s[tid] : 0ull;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint64_t other = __shfl_sync(kFull, mine, j);
+                rank += other > mine ? 1 : 0;                   // keys are unique
+            }
+            __syncwarp();
+            if (tid < n) s[rank] = mine;
+        }
+        __syncthreads();
+    } else {
+        got = block_topk(s, s_cnt, a.k, s_hist, s_small, s_misc);
+    }
     if (a.part_out) {
         uint64_t* out = a.part_out + (size_t(q) * gridDim.y + blockIdx.y) * a.kp;
         for (int i = tid; i < a.kp; i += kMergeThreads) out[i] = (i < got) ? s[i] : 0ull;
@@ -329,7 +353,7 @@ struct XchgArgs {
 
 __global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const XchgArgs a) {
     extern __shared__ __align__(16) unsigned char xm_smem[];
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;      // 128 threads for small merges: the block then fits beside a resident scan CTA
     const int64_t area = int64_t(a.epoch & 1u) * a.area_bytes;
     unsigned char* own_slot = a.bufs[a.rank] + area + int64_t(a.rank) * a.slot_bytes;
     // 1. my results for query q -> every peer's gather area (slot = my rank)
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const Xchg
     for (int p = 0; p < a.world; ++p) {
         if (p == a.rank) continue;
         unsigned char* dst = a.bufs[p] + area + int64_t(a.rank) * a.slot_bytes;
-        for (int i = tid; i < a.k; i += kMergeThreads) {
+        for (int i = tid; i < a.k; i += nt) {
             reinterpret_cast<int64_t*>(dst)[size_t(q) * a.k + i] = my_rows[i];
             reinterpret_cast<float*>(dst + a.scores_off)[size_t(q) * a.k + i] = my_scores[i];
         }
@@ -371,7 +395,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const Xchg
     int got = 0;
     for (int l = 0; l < a.world; ++l) got += reinterpret_cast<const int32_t*>(g + int64_t(l) * a.slot_bytes + a.counts_off)[q];
     got = got < a.k ? got : a.k;
-    for (int i = tid; i < n2; i += kMergeThreads) {
+    for (int i = tid; i < n2; i += nt) {
         uint32_t c = 0; int64_t r = INT64_MAX;
         if (i < total) {
             const int l = i / a.k, j = i - l * a.k;
@@ -388,7 +412,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const Xchg
     __syncthreads();
     for (int kk = 2; kk <= n2; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n2; i += kMergeThreads) {
+            for (int i = tid; i < n2; i += nt) {
                 const int p = i ^ j;
                 if (p > i) {
                     const uint32_t ci = sc[i], cp = sc[p]; const int64_t ri = sr[i], rp = sr[p];
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) xchg_merge_kernel(const Xchg
             __syncthreads();
         }
     }
-    for (int i = tid; i < a.k; i += kMergeThreads) {
+    for (int i = tid; i < a.k; i += nt) {
         const size_t o = size_t(q) * a.k + i;
         if (i < got) {
             const uint32_t c = sc[i];

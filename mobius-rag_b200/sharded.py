@@ -106,6 +106,8 @@ class ShardedSearcher:
         key = (nq, k)
         if self._p2p is not None and self._p2p["key"] == key:
             return self._p2p
+        if self._p2p is not None and "xstream" in self._p2p:
+            self._p2p["xstream"].synchronize()          # exchanges of the old shape still in flight on the side stream
         try:
             import ctypes as C
             import torch
@@ -136,6 +138,10 @@ class ShardedSearcher:
         from . import _native as N
         nq = int(q.shape[0])
         lay, buf = st["lay"], st["buf"]
+        # exchanges issued by search_async run on a side stream: this rank's exchange kernels must stay in epoch order
+        for ev in st.get("done", ()):
+            if ev is not None:
+                torch.cuda.current_stream(buf.device).wait_event(ev)
         self._epoch += 1
         area = (self._epoch & 1) * self.world * lay["size"]
         slot = buf[area + self.rank * lay["size"]: area + (self.rank + 1) * lay["size"]]
@@ -154,6 +160,54 @@ class ShardedSearcher:
         if events:
             events[2].record()
         return out
+
+    # -- pipelined search --------------------------------------------------------------------------
+    def search_async(self, q, k: int, flt=None) -> "PendingSearch":
+        """Like `search`, but the cross-rank exchange + k-way merge runs on a side stream, so it overlaps the local scan
+        of the NEXT search issued on the caller's stream (the exchange block is small enough to be resident beside a scan
+        CTA).  Returns a handle; `.result()` orders the caller's stream after the exchange and hands out the tensors.
+        At most two searches are in flight: issuing search j first waits (on the device) for the exchange of search
+        j - 2, whose gather area and output buffers it reuses.  The tensors of a result stay valid until three more
+        searches have been issued.  Without peer-mapped memory this degrades to `search` (already complete)."""
+        import torch
+        nq = int(q.shape[0])
+        st = None
+        if self._local == self._cuda_local and self._merge == self._cuda_merge:
+            st = self._p2p_state(nq, k)
+        if st is None:
+            return PendingSearch(self.search(q, k, flt), None, None)
+        from . import _native as N
+        dev = st["buf"].device
+        if "xstream" not in st:
+            st["xstream"] = torch.cuda.Stream(device=dev)
+            st["ring"] = [(torch.empty((nq, k), dtype=torch.float32, device=dev),
+                           torch.empty((nq, k), dtype=torch.int64, device=dev),
+                           torch.empty((nq,), dtype=torch.int32, device=dev)) for _ in range(3)]
+            st["done"] = [None, None, None]
+            st["issued"] = 0
+        j = st["issued"]
+        st["issued"] = j + 1
+        cur = torch.cuda.current_stream(dev)
+        prev2 = st["done"][(j - 2) % 3] if j >= 2 else None
+        if prev2 is not None:
+            cur.wait_event(prev2)                      # gather area (epoch parity) and slot of search j - 2 are free again
+        lay, buf = st["lay"], st["buf"]
+        self._epoch += 1
+        area = (self._epoch & 1) * self.world * lay["size"]
+        slot = buf[area + self.rank * lay["size"]: area + (self.rank + 1) * lay["size"]]
+        self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        local_done = torch.cuda.Event()
+        local_done.record(cur)
+        out = st["ring"][j % 3]
+        xs = st["xstream"]
+        xs.wait_event(local_done)
+        N.check(N.load().mrag_exchange_merge(self.index.device, self.world, self.rank, nq, int(k), st["ptrs"],
+                                             lay["size"], lay["scores_off"], lay["counts_off"], self._epoch,
+                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), xs.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(xs)
+        st["done"][j % 3] = done
+        return PendingSearch(out, done, xs)
 
     def phase_names(self) -> tuple:
         """Names of the intervals between the events `search(..., events=)` records, for the exchange in use."""
@@ -185,3 +239,36 @@ class ShardedSearcher:
         if events:
             events[3].record()
         return out
+
+
+class PendingSearch:
+    """Handle of `ShardedSearcher.search_async`."""
+
+    def __init__(self, out, done_event, stream):
+        self._out = out
+        self._done = done_event
+        self._stream = stream
+
+    def copy_to_host(self, scores, rows, counts):
+        """Device -> (pinned) host copies of the result, enqueued behind the exchange on ITS stream, so the caller's
+        stream -- and the next search's scan on it -- does not wait for them.  Returns the event to synchronize on."""
+        import torch
+        dev = self._out[0].device
+        stream = self._stream if self._stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(stream):
+            scores.copy_(self._out[0], non_blocking=True)
+            rows.copy_(self._out[1], non_blocking=True)
+            counts.copy_(self._out[2], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return ev
+
+    def result(self, host_sync: bool = False):
+        """(scores, rows, counts); the caller's current stream is ordered after the exchange (host_sync: the host too)."""
+        if self._done is not None:
+            import torch
+            if host_sync:
+                self._done.synchronize()
+            else:
+                torch.cuda.current_stream(self._out[0].device).wait_event(self._done)
+        return self._out

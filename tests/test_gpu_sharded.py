@@ -61,7 +61,7 @@ def _free_port() -> int:
     return p
 
 
-def _nccl_worker(rank, world, port, n, dim, nq, k, outdir, exchange="nccl"):
+def _nccl_worker(rank, world, port, n, dim, nq, k, outdir, exchange="nccl", pipelined=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -78,6 +78,21 @@ def _nccl_worker(rank, world, port, n, dim, nq, k, outdir, exchange="nccl"):
         idx.set_row_base(lo)
         ss = sharded.ShardedSearcher(index=idx, exchange=exchange)
         qd = torch.from_numpy(Q).cuda()
+        if pipelined:
+            # a different batch every step, two searches in flight, then a plain search on the same searcher
+            pend, outs = [], []
+            for i in range(pipelined):
+                pend.append(ss.search_async(torch.from_numpy(synth.make_queries(X, nq, seed=193 + i)).cuda(), k))
+                if i >= 1:
+                    outs.append(tuple(t.clone() for t in pend[i - 1].result()))
+            outs.append(tuple(t.clone() for t in pend[-1].result(host_sync=True)))
+            s, r, c = ss.search(qd, k)
+            torch.cuda.synchronize()
+            assert torch.equal(r, outs[0][1]) and torch.equal(c, outs[0][2])
+            np.savez(os.path.join(outdir, f"out{rank}.npz"), s=np.stack([o[0].cpu().numpy() for o in outs]),
+                     r=np.stack([o[1].cpu().numpy() for o in outs]), c=np.stack([o[2].cpu().numpy() for o in outs]))
+            idx.close()
+            return
         for _ in range(5):                             # several epochs: both gather areas and the flags are reused
             s, r, c = ss.search(qd, k)
         assert ss.exchange == exchange
@@ -115,3 +130,20 @@ def test_sharded_p2p_exchange_two_ranks(oracle, tmp_path):
     outs = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
     assert (outs[0]["r"] == outs[1]["r"]).all() and (outs[0]["c"] == outs[1]["c"]).all()
     _check(oracle, oracle.round_bf16(X), Q, valid.astype(bool), k, outs[0]["s"], outs[0]["r"], outs[0]["c"], 1e-2)
+
+
+def test_sharded_pipelined_exchange_two_ranks(oracle, tmp_path):
+    """search_async: the exchange of search i runs on a side stream while search i + 1 scans; every step returns its own
+    batch's answer on both ranks."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, dim, nq, k, steps = 80000, 768, 7, 10, 7
+    mp.spawn(_nccl_worker, args=(2, _free_port(), n, dim, nq, k, str(tmp_path), "p2p", steps), nprocs=2, join=True)
+    X, valid = synth.make_corpus(n, dim, seed=191, null_frac=1e-3)
+    outs = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
+    assert (outs[0]["r"] == outs[1]["r"]).all() and (outs[0]["c"] == outs[1]["c"]).all()
+    Xb = oracle.round_bf16(X)
+    for i in range(steps):
+        _check(oracle, Xb, synth.make_queries(X, nq, seed=193 + i), valid.astype(bool), k, outs[0]["s"][i], outs[0]["r"][i], outs[0]["c"][i], 1e-2)

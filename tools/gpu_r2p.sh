@@ -1,0 +1,19 @@
+set -x
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2p_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2p_pytest.log
+tail -3 gpurun_out/r2p_pytest.log
+B="python bench.py --rows 1250000 --no-cpu-baseline --sweep '' --threads 0 --also-f32 0 --steps 300 --no-parity"
+for rep in 1 2 3; do
+eval timeout 300 $B > gpurun_out/r2p_shard_$rep.json 2>/dev/null
+done
+timeout 300 python bench.py --no-cpu-baseline --sweep '' --threads 0 --also-f32 0 --steps 30 > gpurun_out/r2p_10m.json 2>/dev/null
+timeout 300 python bench.py --rows 6250000 --dim 1536 --no-cpu-baseline --sweep '' --threads 0 --also-f32 0 --steps 30 > gpurun_out/r2p_1536.json 2>/dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2p_launches_shard.csv python bench.py --rows 1250000 --no-cpu-baseline --sweep '' --threads 0 --also-f32 0 --steps 3 --warmup 3 --no-parity > gpurun_out/r2p_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2p_launches_c2.csv python bench.py --workload c2 --no-cpu-baseline --sweep '' --threads 0 --steps 3 --warmup 3 --no-parity > gpurun_out/r2p_ncu_c2.log 2>&1
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2p_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d['value'],1), round(d['ms_per_step'],4), {k:round(v,4) for k,v in d['phases_ms'].items()}, d['gpu_launches'], (d.get('parity') or {}).get('status'), round(d['roofline']['frac'],3))
+    except Exception as e: print(f,'ERR',e)
+PY
