@@ -1213,6 +1213,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         ? int(std::max<int64_t>(1, std::min<int64_t>(mma_units, ceil_div(n, kMmaTileRows)))) * (ksplit ? 2 : 1)
         : int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
     if (rounds > 1 && w->ub.reserve(size_t(nq))) return MRAG_ERR_OOM;
+    bool tail_folded = false;
     // event 2 marks the end of the LAST scan; for multi-round searches the merge time of the
     // earlier rounds is attributed to the scan phase
     for (int r = 0; r < rounds && !use_mma128 && !use_shadow_gemv; ++r) {
@@ -1303,11 +1304,16 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         m.need_tail = w->flags.p;
         // the exact tensor-core scan leaves a bound that k rows of the query reach (group maxima / compactions) in gthr
         if (n > 0 && use_mma && rounds == 1 && int64_t(grid) * kp <= kMergeSlots) m.thr_in = w->gthr.p;
+        // the last merge of the search also appends the NaN tail of the queries that end short (no nan_tail_kernel launch)
+        if (n > 0 && r == rounds - 1) {
+            m.tail_mask = mask; m.tail_inv_norm = x->inv_norm; m.tail_qinv = w->qinv.p; m.tail_n = n;
+            tail_folded = true;
+        }
         int rcm = launch_merge(w, m, nq, s);
         if (rcm != MRAG_OK) return rcm;
     }
     // ---- NaN tail (Postgres: NaN distances sort last)
-    if (n > 0) {
+    if (n > 0 && !tail_folded) {
         TailArgs t{};
         t.inv_norm = x->inv_norm; t.mask = mask; t.n = n; t.qinv = w->qinv.p; t.nq = nq; t.k_total = k;
         t.scores = d_scores; t.rows = d_rows; t.counts = d_counts; t.row_base = x->row_base;

@@ -249,6 +249,43 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict
     }
     if (flags4 && i == 0 && lane < 4) flags4[lane] = 0;
     float ss = 0.0f;
+    if ((dim & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && i < nq && !qbf) {
+        // vector path: all of a lane's 128-bit loads are independent (one round trip instead of ld / 32 dependent ones)
+        const float4* src = reinterpret_cast<const float4*>(q + size_t(i) * dim);
+        float4* dst = reinterpret_cast<float4*>(qpad + size_t(i) * ld);
+        uint2* hi2 = qhl ? reinterpret_cast<uint2*>(qhl + size_t(i) * ld) : nullptr;          // plane of ld / 2 words
+        uint2* lo2 = qhl ? hi2 + ld / 4 : nullptr;
+        const int nv = ld >> 2, dv = dim >> 2;
+        for (int v0 = 0; v0 < nv; v0 += 32 * 8) {
+            float4 f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int v = v0 + 32 * j + lane;
+                f[j] = v < dv ? __ldg(src + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int v = v0 + 32 * j + lane;
+                if (v < nv) {
+                    dst[v] = f[j];
+                    const float e4[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
+                    if (qhl) {
+                        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            h[c] = __float2bfloat16_rn(e4[c]);
+                            l[c] = __float2bfloat16_rn(e4[c] - __bfloat162float(h[c]));      // q - hi is exact in fp32
+                        }
+                        __nv_bfloat162 h01(h[0], h[1]), h23(h[2], h[3]), l01(l[0], l[1]), l23(l[2], l[3]);
+                        hi2[v] = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+                        lo2[v] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ss = fmaf(e4[c], e4[c], ss);
+                }
+            }
+        }
+    } else
     for (int e = lane; e < ld; e += 32) {
         float v = (i < nq && e < dim) ? q[size_t(i) * dim + e] : 0.0f;
         if (i < nq) qpad[size_t(i) * ld + e] = v;

@@ -38,6 +38,9 @@ struct MergeArgs {
     const int* qcount;
     int q_lo, q_hi;         // q_hi == 0 means no upper limit
     int no_clamp;           // hybrid rerank scores are not cosines: do not clamp them to [-1, 1]
+    // NaN tail folded into the last merge of a search (tail_mask != nullptr): a query that ends short of k_total walks the
+    // mask for NaN rows in this block instead of in a nan_tail_kernel launch; need_tail is then left alone
+    const uint32_t* tail_mask; const float* tail_inv_norm; const float* tail_qinv; int64_t tail_n;
     const uint32_t* thr_in; // [nq] orderable(score) that k rows of the query are known to reach (the scan's cross-CTA bound), 0 =
                             // unknown; or nullptr.  Replaces the pass over the lists' k-th entries: one dependent round trip less.
 };
@@ -101,6 +104,68 @@ MRAG_DEVINL int block_topk(uint64_t* s, int n, int k, unsigned* hist, uint64_t* 
     __syncthreads();
     block_sort_desc(s, n2);
     return n;
+}
+
+// NaN tail.  Postgres sorts a NaN distance after every number, so rows whose similarity is NaN
+// (zero-norm row, or every row when the query itself has zero norm) are returned only when
+// fewer than k finite rows pass the filter.  One block per query walks the mask in row order.
+// inv_norm[r] == +inf marks a stored zero-norm row.
+struct TailArgs {
+    const float* inv_norm; const uint32_t* mask; int64_t n;
+    const float* qinv; int nq; int k_total;
+    float* scores; int64_t* rows; int32_t* counts; int64_t row_base;
+    const int* need_tail;
+};
+
+// the walk for query q, by a whole block of <= 512 threads (all must call); `have` = results the query holds so far
+MRAG_DEVINL void nan_tail_block(const TailArgs& a, int q, int have, int* s_scan /*[blockDim]*/, int* s_count /*[1]*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) *s_count = have;
+    __syncthreads();
+    if (*s_count >= a.k_total) return;
+    const bool all_nan = isinf(a.qinv[q]);
+    // a zero query makes EVERY similarity NaN; the scan kernels then selected nothing for it
+    const int64_t nwords = (a.n + 31) >> 5;
+    for (int64_t w0 = 0; w0 < nwords; w0 += nt) {
+        int64_t w = w0 + tid;
+        uint32_t m = (w < nwords) ? a.mask[w] : 0u;
+        if (m && !all_nan) {
+            uint32_t keep = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                int b = __ffs(mm) - 1;
+                if (isinf(a.inv_norm[w * 32 + b])) keep |= 1u << b;
+            }
+            m = keep;
+        }
+        int c = __popc(m);
+        s_scan[tid] = c;
+        __syncthreads();
+        for (int o = 1; o < nt; o <<= 1) {          // inclusive scan
+            int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        int pos = *s_count + s_scan[tid] - c;
+        for (; m && pos < a.k_total; m &= m - 1, ++pos) {
+            int b = __ffs(m) - 1;
+            size_t o = size_t(q) * a.k_total + pos;
+            a.scores[o] = CUDART_NAN_F;
+            a.rows[o] = w * 32 + b + a.row_base;
+        }
+        __syncthreads();
+        if (tid == nt - 1) *s_count = min(a.k_total, *s_count + s_scan[nt - 1]);
+        __syncthreads();
+        if (*s_count >= a.k_total) break;
+    }
+    if (tid == 0) a.counts[q] = *s_count;
+}
+
+__global__ void __launch_bounds__(256, 1) nan_tail_kernel(const TailArgs a) {
+    if (*a.need_tail == 0) return;
+    __shared__ int s_scan[256];
+    __shared__ int s_count;
+    nan_tail_block(a, blockIdx.x, a.counts[blockIdx.x], s_scan, &s_count);
 }
 
 // One block per query.  Keys below T = max_p(list_p[k-1]) cannot be in the global top-k (list p
@@ -204,65 +269,15 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     if (tid == 0) {
         a.counts[q] = prev + got;
         if (a.ub_out) a.ub_out[q] = (got == a.k) ? s[a.k - 1] : 0ull;
-        if (prev + got < a.k_total && a.need_tail) *a.need_tail = 1;
+        if (prev + got < a.k_total && a.need_tail && !a.tail_mask) *a.need_tail = 1;
     }
-}
-
-// NaN tail.  Postgres sorts a NaN distance after every number, so rows whose similarity is NaN
-// (zero-norm row, or every row when the query itself has zero norm) are returned only when
-// fewer than k finite rows pass the filter.  One block per query walks the mask in row order.
-// inv_norm[r] == +inf marks a stored zero-norm row.
-struct TailArgs {
-    const float* inv_norm; const uint32_t* mask; int64_t n;
-    const float* qinv; int nq; int k_total;
-    float* scores; int64_t* rows; int32_t* counts; int64_t row_base;
-    const int* need_tail;
-};
-
-__global__ void __launch_bounds__(256, 1) nan_tail_kernel(const TailArgs a) {
-    if (*a.need_tail == 0) return;
-    __shared__ int s_scan[256];
-    __shared__ int s_count;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) s_count = a.counts[q];
-    __syncthreads();
-    if (s_count >= a.k_total) return;
-    const bool all_nan = isinf(a.qinv[q]);
-    // a zero query makes EVERY similarity NaN; the scan kernels then selected nothing for it
-    const int64_t nwords = (a.n + 31) >> 5;
-    for (int64_t w0 = 0; w0 < nwords; w0 += 256) {
-        int64_t w = w0 + tid;
-        uint32_t m = (w < nwords) ? a.mask[w] : 0u;
-        if (m && !all_nan) {
-            uint32_t keep = 0;
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-                int b = __ffs(mm) - 1;
-                if (isinf(a.inv_norm[w * 32 + b])) keep |= 1u << b;
-            }
-            m = keep;
-        }
-        int c = __popc(m);
-        s_scan[tid] = c;
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {          // inclusive scan
-            int v = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        int pos = s_count + s_scan[tid] - c;
-        for (; m && pos < a.k_total; m &= m - 1, ++pos) {
-            int b = __ffs(m) - 1;
-            size_t o = size_t(q) * a.k_total + pos;
-            a.scores[o] = CUDART_NAN_F;
-            a.rows[o] = w * 32 + b + a.row_base;
-        }
-        __syncthreads();
-        if (tid == 255) s_count = min(a.k_total, s_count + s_scan[255]);
-        __syncthreads();
-        if (s_count >= a.k_total) break;
+    if (a.tail_mask && prev + got < a.k_total) {          // block-uniform
+        __syncthreads();                                    // s[] is free from here on
+        TailArgs t;
+        t.inv_norm = a.tail_inv_norm; t.mask = a.tail_mask; t.n = a.tail_n; t.qinv = a.tail_qinv; t.nq = a.nq; t.k_total = a.k_total;
+        t.scores = a.scores; t.rows = a.rows; t.counts = a.counts; t.row_base = a.row_base; t.need_tail = nullptr;
+        nan_tail_block(t, q, prev + got, reinterpret_cast<int*>(s), &s_cnt);
     }
-    if (tid == 0) a.counts[q] = s_count;
 }
 
 // K4: k-way merge of per-shard results after the allgather.  Entries are (score, global row);
