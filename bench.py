@@ -694,6 +694,8 @@ def main():
             out = (torch.empty((batch, args.k), dtype=torch.float32, device=dev),
                    torch.empty((batch, args.k), dtype=torch.int64, device=dev),
                    torch.empty((batch,), dtype=torch.int32, device=dev))
+        if arm.ss is not None:
+            arm.ss.defer_exchange = os.environ.get("MRAG_DEFER_EXCHANGE", "1") != "0"
         res = arm.run(Q, args.k, max(warmup, 3), out)
         barrier()
         clocks = ClockSampler(local_rank) if sample_clocks else None
@@ -797,12 +799,12 @@ def main():
         prev = None
         for i in range(steps):
             qd2[i & 1].copy_(Qh, non_blocking=True)
-            ev = ss.search_async(qd2[i & 1], args.k, flt).copy_to_host(hs2[i & 1], hr2[i & 1], hc2[i & 1])
-            if prev is not None:
-                prev.synchronize()
-            prev = ev
-        prev.synchronize()
+            p = ss.search_async(qd2[i & 1], args.k, flt)
+            if prev is not None:                      # step i - 1: its exchange was released by issuing step i
+                prev.copy_to_host(hs2[(i - 1) & 1], hr2[(i - 1) & 1], hc2[(i - 1) & 1]).synchronize()
+            prev = p
         j = (steps - 1) & 1
+        prev.copy_to_host(hs2[j], hr2[j], hc2[j]).synchronize()
         hs.copy_(hs2[j]); hr.copy_(hr2[j]); hc.copy_(hc2[j])
     if ss is not None and pipelined:
         qd2 = [torch.empty_like(m["Q"]) for _ in range(2)]

@@ -294,6 +294,13 @@ int mrag_rerank_candidates(mrag_index* idx, const mrag_candidate* cands, int64_t
 int mrag_dtag_mask(mrag_index* idx, const mrag_filter* filter, const uint16_t* dcodes, int n_codes,
                    uint32_t* host_mask_out, int64_t* counts);
 
+/* Optional hook for callers that pipeline work across streams: `cuda_event` (a cudaEvent_t, or NULL to clear) is
+ * recorded in the search's stream right after the PREPARE phase of every following mrag_search on this index (queries
+ * padded, filter mask built -- i.e. just before the scan kernels are launched).  The row-sharded searcher
+ * (mobius-rag_b200/sharded.py, search_async) uses it to release the PREVIOUS search's cross-rank exchange kernel on a side
+ * stream once the next scan is already queued, so the two launches do not compete at the moment the previous search ends. */
+int mrag_set_prepared_event(mrag_index* idx, void* cuda_event);
+
 /* Global row id offset added to every returned row (shard base for row-sharded corpora). */
 int mrag_set_row_base(mrag_index* idx, int64_t row_base);
 /* Explicit ids for rows [first_row, first_row + n) (HOST array; may be set before those rows are appended, up to the

@@ -157,6 +157,7 @@ struct mrag_index {
     CUtensorMap tmap32;                 // the same tensor with 64x32 boxes (half tiles of the CTA-pair scan)
     bool has_tmap = false;
     cudaStream_t wstream = nullptr;     // write-side stream
+    std::atomic<cudaEvent_t> prepared_event{nullptr};   // mrag_set_prepared_event
     std::shared_mutex lock;             // searches share, writers exclude
     std::mutex ws_lock;
     std::vector<Workspace*> pool;
@@ -347,6 +348,12 @@ extern "C" int64_t mrag_capacity(const mrag_index* x) { return x ? x->capacity :
 extern "C" int mrag_dim(const mrag_index* x) { return x ? x->dim : -1; }
 extern "C" int mrag_index_dtype(const mrag_index* x) { return x ? x->dtype : -1; }
 extern "C" int mrag_device(const mrag_index* x) { return x ? x->device : -1; }
+
+extern "C" int mrag_set_prepared_event(mrag_index* x, void* cuda_event) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_set_prepared_event: null index");
+    x->prepared_event.store(static_cast<cudaEvent_t>(cuda_event), std::memory_order_release);
+    return MRAG_OK;
+}
 
 extern "C" int mrag_set_row_base(mrag_index* x, int64_t row_base) {
     if (!x) return fail(MRAG_ERR_ARG, "mrag_set_row_base: null index");
@@ -1170,6 +1177,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         mask = w->mask.p;
     }
     if (evl >= 1) CU(cudaEventRecord(ev.e[1], s));
+    if (cudaEvent_t pe = x->prepared_event.load(std::memory_order_acquire)) CU(cudaEventRecord(pe, s));
 
     // ---- scan + select, MRAG_FUSED_K results per round
     const int rounds = int(ceil_div(k, MRAG_FUSED_K));

@@ -66,6 +66,8 @@ class ShardedSearcher:
         self.exchange = exchange
         self._p2p = None
         self._epoch = 0
+        # search_async: hold a search's exchange back until the next search's prepare phase has run (see there)
+        self.defer_exchange = True
 
     # -- buffers -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -107,6 +109,7 @@ class ShardedSearcher:
         if self._p2p is not None and self._p2p["key"] == key:
             return self._p2p
         if self._p2p is not None and "xstream" in self._p2p:
+            self._flush_deferred(self._p2p)
             self._p2p["xstream"].synchronize()          # exchanges of the old shape still in flight on the side stream
         try:
             import ctypes as C
@@ -139,6 +142,7 @@ class ShardedSearcher:
         nq = int(q.shape[0])
         lay, buf = st["lay"], st["buf"]
         # exchanges issued by search_async run on a side stream: this rank's exchange kernels must stay in epoch order
+        self._flush_deferred(st)
         for ev in st.get("done", ()):
             if ev is not None:
                 torch.cuda.current_stream(buf.device).wait_event(ev)
@@ -162,22 +166,50 @@ class ShardedSearcher:
         return out
 
     # -- pipelined search --------------------------------------------------------------------------
+    def _enqueue_exchange(self, st, rec, after_event) -> None:
+        """Launch the exchange + k-way merge of the search `rec` on the side stream, behind `after_event`."""
+        import torch
+        from . import _native as N
+        lay, xs = st["lay"], st["xstream"]
+        xs.wait_event(rec["local_done"])              # (already implied by after_event unless another thread moved the hook's event)
+        xs.wait_event(after_event)
+        out = rec["out"]
+        N.check(N.load().mrag_exchange_merge(self.index.device, self.world, self.rank, rec["nq"], rec["k"], st["ptrs"],
+                                             lay["size"], lay["scores_off"], lay["counts_off"], rec["epoch"],
+                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), xs.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(xs)
+        rec["done"] = done
+        st["done"][rec["j"] % 3] = done
+
+    def _flush_deferred(self, st) -> None:
+        """Enqueue the exchange of the last search_async if it is still waiting for a successor."""
+        rec = st.get("deferred") if st is not None else None
+        if rec is not None:
+            st["deferred"] = None
+            self._enqueue_exchange(st, rec, rec["local_done"])
+
     def search_async(self, q, k: int, flt=None) -> "PendingSearch":
         """Like `search`, but the cross-rank exchange + k-way merge runs on a side stream, so it overlaps the local scan
         of the NEXT search issued on the caller's stream (the exchange block is small enough to be resident beside a scan
         CTA).  Returns a handle; `.result()` orders the caller's stream after the exchange and hands out the tensors.
-        At most two searches are in flight: issuing search j first waits (on the device) for the exchange of search
-        j - 2, whose gather area and output buffers it reuses.  The tensors of a result stay valid until three more
-        searches have been issued.  Without peer-mapped memory this degrades to `search` (already complete)."""
+
+        The exchange of search j is enqueued when search j + 1 is issued, behind the event the library records after
+        j + 1's prepare phase (mrag_set_prepared_event): by then scan j + 1 is already queued behind its prepare kernel, so
+        the exchange launch does not compete with it at the moment search j ends.  (`.result()` enqueues it at once if no
+        successor came.)  At most two searches are in flight: issuing search j first waits (on the device) for the
+        exchange of search j - 2, whose gather area and output buffers it reuses; the tensors of a result stay valid
+        until three more searches have been issued.  Without peer-mapped memory this degrades to `search`."""
         import torch
         nq = int(q.shape[0])
         st = None
         if self._local == self._cuda_local and self._merge == self._cuda_merge:
             st = self._p2p_state(nq, k)
         if st is None:
-            return PendingSearch(self.search(q, k, flt), None, None)
+            return PendingSearch(self.search(q, k, flt), None, None, None)
         from . import _native as N
         dev = st["buf"].device
+        cur = torch.cuda.current_stream(dev)
         if "xstream" not in st:
             st["xstream"] = torch.cuda.Stream(device=dev)
             st["ring"] = [(torch.empty((nq, k), dtype=torch.float32, device=dev),
@@ -185,9 +217,14 @@ class ShardedSearcher:
                            torch.empty((nq,), dtype=torch.int32, device=dev)) for _ in range(3)]
             st["done"] = [None, None, None]
             st["issued"] = 0
+            st["deferred"] = None
+            st["prepared"] = []
+            for _ in range(3):                          # persistent events (torch creates the CUDA event at its first record)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                st["prepared"].append(ev)
         j = st["issued"]
         st["issued"] = j + 1
-        cur = torch.cuda.current_stream(dev)
         prev2 = st["done"][(j - 2) % 3] if j >= 2 else None
         if prev2 is not None:
             cur.wait_event(prev2)                      # gather area (epoch parity) and slot of search j - 2 are free again
@@ -195,19 +232,28 @@ class ShardedSearcher:
         self._epoch += 1
         area = (self._epoch & 1) * self.world * lay["size"]
         slot = buf[area + self.rank * lay["size"]: area + (self.rank + 1) * lay["size"]]
-        self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        prev = st["deferred"]
+        prepared = st["prepared"][j % 3]
+        lib = N.load()
+        if prev is not None and self.defer_exchange:
+            N.check(lib.mrag_set_prepared_event(self.index._h, prepared.cuda_event))
+        try:
+            self._local(q, k, flt, self.slot_views(slot, nq, k, lay))
+        finally:
+            if prev is not None and self.defer_exchange:
+                lib.mrag_set_prepared_event(self.index._h, None)
         local_done = torch.cuda.Event()
         local_done.record(cur)
-        out = st["ring"][j % 3]
-        xs = st["xstream"]
-        xs.wait_event(local_done)
-        N.check(N.load().mrag_exchange_merge(self.index.device, self.world, self.rank, nq, int(k), st["ptrs"],
-                                             lay["size"], lay["scores_off"], lay["counts_off"], self._epoch,
-                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), xs.cuda_stream))
-        done = torch.cuda.Event()
-        done.record(xs)
-        st["done"][j % 3] = done
-        return PendingSearch(out, done, xs)
+        rec = {"j": j, "nq": nq, "k": int(k), "epoch": self._epoch, "out": st["ring"][j % 3], "local_done": local_done, "done": None}
+        if prev is not None:
+            # the previous search's exchange: behind this search's prepare phase (or, without the hook, its own end)
+            st["deferred"] = None
+            self._enqueue_exchange(st, prev, prepared if self.defer_exchange else prev["local_done"])
+        if self.defer_exchange:
+            st["deferred"] = rec
+        else:
+            self._enqueue_exchange(st, rec, local_done)
+        return PendingSearch(rec["out"], rec, st, self)
 
     def phase_names(self) -> tuple:
         """Names of the intervals between the events `search(..., events=)` records, for the exchange in use."""
@@ -244,17 +290,26 @@ class ShardedSearcher:
 class PendingSearch:
     """Handle of `ShardedSearcher.search_async`."""
 
-    def __init__(self, out, done_event, stream):
+    def __init__(self, out, rec, st, searcher):
         self._out = out
-        self._done = done_event
-        self._stream = stream
+        self._rec = rec
+        self._st = st
+        self._searcher = searcher
+
+    def _done_event(self):
+        if self._rec is None:
+            return None
+        if self._rec["done"] is None:                 # no successor was issued: enqueue the exchange now
+            self._searcher._flush_deferred(self._st)
+        return self._rec["done"]
 
     def copy_to_host(self, scores, rows, counts):
         """Device -> (pinned) host copies of the result, enqueued behind the exchange on ITS stream, so the caller's
         stream -- and the next search's scan on it -- does not wait for them.  Returns the event to synchronize on."""
         import torch
         dev = self._out[0].device
-        stream = self._stream if self._stream is not None else torch.cuda.current_stream(dev)
+        done = self._done_event()
+        stream = self._st["xstream"] if done is not None else torch.cuda.current_stream(dev)
         with torch.cuda.stream(stream):
             scores.copy_(self._out[0], non_blocking=True)
             rows.copy_(self._out[1], non_blocking=True)
@@ -265,10 +320,11 @@ class PendingSearch:
 
     def result(self, host_sync: bool = False):
         """(scores, rows, counts); the caller's current stream is ordered after the exchange (host_sync: the host too)."""
-        if self._done is not None:
+        done = self._done_event()
+        if done is not None:
             import torch
             if host_sync:
-                self._done.synchronize()
+                done.synchronize()
             else:
-                torch.cuda.current_stream(self._out[0].device).wait_event(self._done)
+                torch.cuda.current_stream(self._out[0].device).wait_event(done)
         return self._out

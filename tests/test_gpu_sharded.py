@@ -80,15 +80,26 @@ def _nccl_worker(rank, world, port, n, dim, nq, k, outdir, exchange="nccl", pipe
         qd = torch.from_numpy(Q).cuda()
         if pipelined:
             # a different batch every step, two searches in flight, then a plain search on the same searcher
-            pend, outs = [], []
-            for i in range(pipelined):
-                pend.append(ss.search_async(torch.from_numpy(synth.make_queries(X, nq, seed=193 + i)).cuda(), k))
-                if i >= 1:
-                    outs.append(tuple(t.clone() for t in pend[i - 1].result()))
-            outs.append(tuple(t.clone() for t in pend[-1].result(host_sync=True)))
+            def lagged():
+                pend, outs = [], []
+                for i in range(pipelined):
+                    pend.append(ss.search_async(torch.from_numpy(synth.make_queries(X, nq, seed=193 + i)).cuda(), k))
+                    if i >= 1:
+                        outs.append(tuple(t.clone() for t in pend[i - 1].result()))
+                outs.append(tuple(t.clone() for t in pend[-1].result(host_sync=True)))
+                return outs
+            outs = lagged()                              # exchange of step i released by step i + 1's prepare phase
             s, r, c = ss.search(qd, k)
             torch.cuda.synchronize()
             assert torch.equal(r, outs[0][1]) and torch.equal(c, outs[0][2])
+            # the result taken at once (no successor: the handle enqueues the exchange itself)
+            for i in range(3):
+                o = ss.search_async(torch.from_numpy(synth.make_queries(X, nq, seed=193 + i)).cuda(), k).result(host_sync=True)
+                assert torch.equal(o[1], outs[i][1]) and torch.equal(o[0], outs[i][0])
+            ss.defer_exchange = False                    # exchange enqueued right behind its own search
+            outs2 = lagged()
+            for a, b in zip(outs, outs2):
+                assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
             np.savez(os.path.join(outdir, f"out{rank}.npz"), s=np.stack([o[0].cpu().numpy() for o in outs]),
                      r=np.stack([o[1].cpu().numpy() for o in outs]), c=np.stack([o[2].cpu().numpy() for o in outs]))
             idx.close()
