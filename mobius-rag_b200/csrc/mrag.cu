@@ -797,7 +797,8 @@ static int64_t sample_min_tiles(int num_sms) {
 // set is wide (many blocks in flight sorting <= 2048 keys each, then one block per query)
 // (nblocks = queries served by this launch; the group lists are indexed by query id, so they are sized by m.nq)
 static int launch_merge(Workspace* w, MergeArgs m, int nq, cudaStream_t s) {
-    if (int64_t(m.P) * m.kp > kMergeSlots && !m.gthr_out) {      // everything fits one block's shared memory otherwise
+    // (with a bound from the scan the survivors are few: one block per query streams all the lists through its prefilter)
+    if (int64_t(m.P) * m.kp > kMergeSlots && !m.gthr_out && !m.thr_in) {      // everything fits one block's shared memory otherwise
         MergeArgs m1 = m;
         m1.Pg = std::max(2, (kMergeSlots / 2) / m.kp);
         const int groups = int(ceil_div(m.P, m1.Pg));
@@ -972,7 +973,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));
     CU(cudaMemsetAsync(w->fb.p, 0, sizeof(int), s));
     int rc;
-    bool use_pairs = false;
+    bool use_pairs = false, sampled_bound = false;
     int npairs = 0, nparts = 0;
     if (gen_gemv) {
         ScanArgs ga{};
@@ -1034,6 +1035,7 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
         sm.gthr_out = w->gthr.p;     // (overwrites the looser per-CTA bounds the sampling launches left there)
         merge_kernel<<<nq, kMergeThreads, 0, s>>>(sm);
         LAUNCHED();
+        sampled_bound = true;
     }
     // more than 128 queries: CTA pairs share every corpus tile (256 queries per pass)
     static const bool pairs_ok = [] { const char* e = getenv("MRAG_MMA256"); return !(e && e[0] == '0'); }();
@@ -1065,6 +1067,9 @@ static int search_approx_rescore(mrag_index* x, Workspace* w, EventSet& ev, int 
     MergeArgs m{};
     m.part = w->part.p; m.P = gen_gemv ? ggrid : (use_pairs ? nparts : grid); m.kp = kpc; m.nq = nq; m.k = kc; m.k_total = kc; m.k_off = 0;
     m.scores = w->cscores.p; m.rows = w->crows.p; m.counts = w->ccounts.p; m.row_base = 0;
+    // sampled scans leave in gthr a score that K' rows of the query reach (the sample's K'-th best, raised by compactions):
+    // the nominee merge prefilters with it and needs no first level
+    if (sampled_bound) m.thr_in = w->gthr.p;
     rc = launch_merge(w, m, nq, s);
     if (rc != MRAG_OK) return rc;
     RescoreArgs ra{};

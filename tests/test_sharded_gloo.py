@@ -61,6 +61,10 @@ def _worker(rank, world, port, n, dim, k, nq, result_dir):
 
         ss = sharded.ShardedSearcher(index=None, local_search=local_search, merge=_np_merge, device="cpu")
         scores, rows, counts = ss.search(torch.from_numpy(Q), k)
+        # without peer-mapped device memory search_async is a completed search behind the same handle
+        p = ss.search_async(torch.from_numpy(Q), k)
+        s2, r2, c2 = p.result(host_sync=True)
+        assert torch.equal(r2, rows) and torch.equal(c2, counts)
         if rank == 0:
             np.savez(os.path.join(result_dir, "out.npz"), scores=scores.numpy(), rows=rows.numpy(), counts=counts.numpy())
     finally:
