@@ -461,13 +461,22 @@ def run_c5(args, idx, plant, dev, n_local, world, rank, hbm_peak, peak_src, t_bu
             if hq[i].phrase_jbit[j] < 0:
                 need[i] |= np.uint64(1 << hq[i].phrase_bit[j])
     group = 4                                                # queries per scan pass (scan_gemv, hybrid mode)
+    kind = idx.last_scan_kind()                              # "pairs_hybrid": one warp per surviving (query, row) pair
     pass_rows = 0
-    for g0 in range(0, nq, group):
-        u = np.zeros(n, dtype=bool)
-        for i in range(g0, min(g0 + group, nq)):
-            u |= (feat["phrase_bits"][:, 0] & need[i]) == need[i]
-        pass_rows += int(u.sum())
-    scan_bytes = pass_rows * args.dim * (2 if args.dtype == "bf16" else 4) + 2 * (n // 8) * nq
+    elem = 2 if args.dtype == "bf16" else 4
+    if kind == "pairs_hybrid":
+        for i in range(nq):
+            pass_rows += int(((feat["phrase_bits"][:, 0] & need[i]) == need[i]).sum())
+        # per pair: the vector, the feature record + doc_idx + authority, the row id written and read, the key written and read;
+        # the bitmaps are read twice more (count, fill)
+        scan_bytes = pass_rows * (args.dim * elem + 40 + 4 + 1 + 8 + 16) + 2 * (n // 8) * nq
+    else:
+        for g0 in range(0, nq, group):
+            u = np.zeros(n, dtype=bool)
+            for i in range(g0, min(g0 + group, nq)):
+                u |= (feat["phrase_bits"][:, 0] & need[i]) == need[i]
+            pass_rows += int(u.sum())
+        scan_bytes = pass_rows * args.dim * elem + 2 * (n // 8) * nq
     scan_ms_mean = float(np.mean(scan_ms))
     dominant = "scan" if scan_ms_mean >= mask_ms else "mask"
     dom_bytes, dom_ms = (scan_bytes, scan_ms_mean) if dominant == "scan" else (mask_bytes, mask_ms)
@@ -485,7 +494,9 @@ def run_c5(args, idx, plant, dev, n_local, world, rank, hbm_peak, peak_src, t_bu
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                     "kernel": "scan_gemv<hybrid> x %d passes" % ((nq + group - 1) // group) if dominant == "scan" else "hybrid_mask_kernel (+ query prep)",
+                     "kernel": (("hybrid_count + hybrid_fill + hybrid_pair_score (one warp per surviving pair)" if kind == "pairs_hybrid"
+                                 else "scan_gemv<hybrid> x %d passes" % ((nq + group - 1) // group)) if dominant == "scan"
+                                else "hybrid_mask_kernel (+ query prep)"),
                      "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
                      "note": "dominant phase of the step; both phases in `phases`",
                      "phases": {"mask": {"ms": mask_ms, "bytes": mask_bytes, "frac": mask_bytes / (mask_ms * 1e-3) / 1e9 / hbm_peak},

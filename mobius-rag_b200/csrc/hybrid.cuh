@@ -156,18 +156,154 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
     }
     const bool maybe_exempt = base && ((f.flags & (MRAG_CF_PROMOTED | MRAG_CF_CONTACT_VALUE)) ||
                                        (f.dtags[0] | f.dtags[1] | f.dtags[2] | f.dtags[3]) != 0u);
-    for (int q = 0; q < nq; ++q) {
-        const DevHyb& h = hq[q];
-        bool keep = base;
-        if (keep && h.src_restrict) keep = (h.q.source_type_any[src >> 6] >> (src & 63)) & 1ull;
-        if (keep && h.q.n_phrases > 0) {
-            // quick reject: a phrase that only its dictionary bit can satisfy is missing, and no exemption can apply
-            const bool bits_ok = !h.impossible && (f.phrase_bits[0] & h.need[0]) == h.need[0] && (f.phrase_bits[1] & h.need[1]) == h.need[1];
-            if (!bits_ok && !maybe_exempt) keep = false;
-            else keep = hybrid_keep(h, f, hybrid_eval(h, f, jt, r, ov));
+    // Phase 1 (thread = row): the verdicts a few bit tests decide.  A (row, query) pair that needs the weighted coverage,
+    // the j-tag credit or a d-tag lookup -- every required dictionary bit present, or a row that may be exempt from the
+    // floor (~6 % of the rows) -- is only MARKED.  Phase 2 (lane = query): the warp takes its marked rows one at a time and
+    // the lanes evaluate the queries of the chunk in parallel.  (With phase 2 inline in the thread = row loop nearly every
+    // warp held an exempt row and ran the full evaluation, 2 lanes active, for each of the queries: 1.47 ms for 10M rows x
+    // 22 queries, r2y.)
+    union FeatWords { mrag_chunkfeat f; uint32_t w[10]; };
+    static_assert(sizeof(mrag_chunkfeat) == 40, "mrag_chunkfeat is broadcast as 10 words");
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int nqc = min(32, nq - q0);
+        uint32_t slow = 0u;                      // bit i: query q0 + i needs the full evaluation of this row
+        for (int i = 0; i < nqc; ++i) {
+            const DevHyb& h = hq[q0 + i];
+            bool keep = base;
+            if (keep && h.src_restrict) keep = (h.q.source_type_any[src >> 6] >> (src & 63)) & 1ull;
+            if (keep && h.q.n_phrases > 0) {
+                const bool bits_ok = !h.impossible && (f.phrase_bits[0] & h.need[0]) == h.need[0] && (f.phrase_bits[1] & h.need[1]) == h.need[1];
+                if (bits_ok || maybe_exempt) slow |= 1u << i;
+                keep = false;
+            }
+            const uint32_t word = __ballot_sync(kFull, keep);
+            if (lane == 0 && (r >> 5) < nwords) hmask[size_t(q0 + i) * nwords + (r >> 5)] = word;
         }
-        const uint32_t word = __ballot_sync(kFull, keep);
-        if (lane == 0 && (r >> 5) < nwords) hmask[size_t(q) * nwords + (r >> 5)] = word;
+        unsigned todo = __ballot_sync(kFull, slow != 0u);
+        __syncwarp();                            // the words above are in place before any bit is OR-ed into them
+        while (todo) {
+            const int L = __ffs(todo) - 1;
+            todo &= todo - 1;
+            FeatWords fw;
+            fw.f = f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) fw.w[k] = __shfl_sync(kFull, fw.w[k], L);
+            const uint32_t slowL = __shfl_sync(kFull, slow, L);
+            const long long rL = __shfl_sync(kFull, (long long)r, L);
+            const unsigned long long jtL = __shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(jt), L);
+            if (lane < nqc && ((slowL >> lane) & 1u)) {
+                const DevHyb& h = hq[q0 + lane];
+                const uint64_t* jp = reinterpret_cast<const uint64_t*>(uintptr_t(jtL));
+                if (hybrid_keep(h, fw.f, hybrid_eval(h, fw.f, jp, rL, ov)))
+                    atomicOr(&hmask[size_t(q0 + lane) * nwords + (rL >> 5)], 1u << (rL & 31));
+            }
+        }
+    }
+}
+
+// ---- pair path: when the coverage floors leave each query a small share of the rows (the usual case: required phrases),
+// the rerank is taken over the LIST of surviving (query, row) pairs instead of a scan that walks every mask word and
+// serves 4 queries per pass:  count -> (host: segment offsets) -> fill -> score (one warp per pair) -> segmented merge.
+// counts[q] += rows set in hmask[q][*].   grid = (blocks over words, nq)
+__global__ void __launch_bounds__(256) hybrid_count_kernel(const uint32_t* __restrict__ hmask, int64_t nwords, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned s_part[8];
+    const int q = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t* m = hmask + size_t(q) * nwords;
+    unsigned c = 0;
+    for (int64_t w = int64_t(blockIdx.x) * 256 + threadIdx.x; w < nwords; w += int64_t(gridDim.x) * 256) c += __popc(__ldg(m + w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if (lane == 0) s_part[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        if (t) atomicAdd(counts + q, (unsigned long long)t);
+    }
+}
+
+// rows_out[seg_off[q] + ...] = the rows set in hmask[q][*] (order within a segment is arbitrary: the keys carry the row).
+// One warp per 32 words of a query.   grid = (blocks over word groups, nq)
+__global__ void __launch_bounds__(256) hybrid_fill_kernel(const uint32_t* __restrict__ hmask, int64_t nwords, const int64_t* __restrict__ seg_off,
+                                                         unsigned long long* __restrict__ cursor, uint32_t* __restrict__ rows_out) {
+    const int q = blockIdx.y, lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t(gridDim.x) * 256) >> 5;
+    const uint32_t* m = hmask + size_t(q) * nwords;
+    for (int64_t w0 = ((int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5) * 32; w0 < nwords; w0 += warps * 32) {
+        const int64_t w = w0 + lane;
+        uint32_t word = w < nwords ? __ldg(m + w) : 0u;
+        const unsigned c = __popc(word);
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned total = __shfl_sync(kFull, incl, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor + q, (unsigned long long)total);
+        base = __shfl_sync(kFull, base, 0);
+        uint32_t* out = rows_out + seg_off[q] + int64_t(base) + (incl - c);
+        for (; word; word &= word - 1) *out++ = uint32_t(w * 32 + (__ffs(word) - 1));
+    }
+}
+
+struct PairArgs {
+    const void* rows; int ld; const float* inv_norm; const float* q; const float* qinv;
+    const uint32_t* pair_rows; const int64_t* seg_off; int nq; int64_t total;
+    const mrag_chunkfeat* feat; const DevHyb* hyb; const uint32_t* doc_idx; const uint8_t* authority;
+    const uint64_t* doc_jtags; int64_t n_jtag_docs; DtagOver ov;
+    uint64_t* keys;                 // [total] key of the pair, 0 = not eligible (NaN score)
+};
+
+// one warp per (query, row) pair: cosine of the stored row, then the rerank score (same arithmetic as the scan's epilogue)
+template <int DT>
+__global__ void __launch_bounds__(256) hybrid_pair_score_kernel(const PairArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (p >= a.total) return;
+    int lo = 0, hi = a.nq;                      // the segment that holds p: seg_off[lo] <= p < seg_off[lo + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.seg_off + mid) <= p) lo = mid; else hi = mid;
+    }
+    const int q = lo;
+    const uint32_t row = __ldg(a.pair_rows + p);
+    const float* qrow = a.q + size_t(q) * a.ld;
+    float acc = 0.0f;
+    if (DT == 1) {
+        const uint4* x = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.rows) + size_t(row) * a.ld);
+        for (int v = lane; v < a.ld / 8; v += 32) {
+            const uint4 d = ldg_stream(x + v);
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v);
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v + 1);
+            acc = fmaf(bf16lo(d.x), q0.x, acc); acc = fmaf(bf16hi(d.x), q0.y, acc);
+            acc = fmaf(bf16lo(d.y), q0.z, acc); acc = fmaf(bf16hi(d.y), q0.w, acc);
+            acc = fmaf(bf16lo(d.z), q1.x, acc); acc = fmaf(bf16hi(d.z), q1.y, acc);
+            acc = fmaf(bf16lo(d.w), q1.z, acc); acc = fmaf(bf16hi(d.w), q1.w, acc);
+        }
+    } else {
+        const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.rows) + size_t(row) * a.ld);
+        for (int v = lane; v < a.ld / 4; v += 32) {
+            const uint4 du = ldg_stream(x + v);
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + v);
+            acc = fmaf(__uint_as_float(du.x), q0.x, acc); acc = fmaf(__uint_as_float(du.y), q0.y, acc);
+            acc = fmaf(__uint_as_float(du.z), q0.z, acc); acc = fmaf(__uint_as_float(du.w), q0.w, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float inv = a.inv_norm[row];
+        const float cs = isinf(inv) ? CUDART_NAN_F : acc * inv * a.qinv[q];
+        // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
+        const float c01 = (cs == cs) ? cs : 1.0f;
+        const mrag_chunkfeat f = a.feat[row];
+        const uint32_t d = a.doc_idx[row];
+        const uint64_t* jt = (a.doc_jtags && int64_t(d) < a.n_jtag_docs) ? a.doc_jtags + size_t(d) * MRAG_JTAG_WORDS : nullptr;
+        const DevHyb& h = a.hyb[q];
+        const float s = hybrid_score(h, f, hybrid_eval(h, f, jt, int64_t(row), a.ov), c01, a.authority[row]);
+        a.keys[p] = (s == s) ? make_key(s, row) : 0ull;
     }
 }
 

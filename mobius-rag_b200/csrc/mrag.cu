@@ -120,13 +120,15 @@ struct Workspace {
     DevBuf<int> fb;                 // [0] count, [1..] query list of the exact fallback
     DevBuf<DevHyb> hyb;             // hybrid search: per-query parameters
     DevBuf<uint32_t> hmask;         // hybrid search: per-query row bitmaps
+    DevBuf<uint32_t> pair_rows;     // hybrid search, pair path: rows of the surviving (query, row) pairs, one segment per query
+    DevBuf<int64_t> segoff;         // [nq + 1] segment offsets
     DevBuf<uint16_t> codes;         // d-tag arm: the codes asked for
     DevBuf<int> flags;              // [0] need_tail
     DevBuf<unsigned long long> npass, stats;
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release(); qhl.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); gmax.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
-        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); codes.release(); flags.release(); npass.release(); stats.release();
+        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); pair_rows.release(); segoff.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -201,7 +203,8 @@ static thread_local EventSet t_last_ev;          // borrowed handles (owned by a
 static thread_local bool t_last_valid = false;
 static thread_local const char* t_last_kind = "none";
 static thread_local unsigned long long* t_stats_ptr = nullptr;
-static thread_local int* t_fb_ptr = nullptr;      // fallback counter of the last approx+rescore search
+static thread_local int* t_fb_ptr = nullptr;
+static thread_local bool t_hybrid_pairs = false;      // fallback counter of the last approx+rescore search
 static thread_local std::vector<EventSet> t_ring;
 static thread_local int t_ring_used = 0;
 static thread_local int t_ring_device = -1;
@@ -1162,11 +1165,16 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     // 2 (default) = group maxima + shared-memory candidate buffers on shards of >= sample_min_tiles tiles
     // (measured r2m, 1.25M x 768, 64 queries, k = 10: 0.378 / 0.480 / 0.349 ms per step)
     static const int gmax_mode = [] { const char* e = getenv("MRAG_GMAX"); return (e && *e) ? atoi(e) : 2; }();
-    const bool use_gmax = gmax_mode > 0 && x->has_tmap && x->dtype == MRAG_BF16 && k <= kMmaRegK;
-    if (w->gthr.reserve(size_t(nq)) || (use_gmax && w->gmax.reserve(size_t(nq) * 16))) return MRAG_ERR_OOM;
+    // MRAG_GMAX_MAXK: largest k served by the group maxima (16 slots up to k = 16, 128 beyond; default: every single-round k).
+    // Measured r2x (10M x 768, 64 queries, k = 100): 2.58-2.62 ms per step against 2.65 with the sampling launch (16);
+    // the merge phase 0.08 -> 0.03 ms.
+    static const int gmax_maxk = [] { const char* e = getenv("MRAG_GMAX_MAXK"); return (e && *e) ? std::min(128, atoi(e)) : 128; }();
+    const bool use_gmax = gmax_mode > 0 && x->has_tmap && x->dtype == MRAG_BF16 && k <= gmax_maxk;
+    const int gslots = k <= 16 ? 16 : 128;
+    if (w->gthr.reserve(size_t(nq)) || (use_gmax && w->gmax.reserve(size_t(nq) * gslots))) return MRAG_ERR_OOM;
     query_prep_kernel<<<unsigned(ceil_div(int64_t(nq) * 32, 128)), 128, 0, s>>>(d_q, nq, x->dim, ld, w->qpad.p,
                                                                                w->qinv.p, nullptr, nq, qhl, w->gthr.p,
-                                                                               use_gmax ? w->gmax.p : nullptr, k, 16, w->flags.p);
+                                                                               use_gmax ? w->gmax.p : nullptr, k, gslots, w->flags.p);
     LAUNCHED();
 
     float* d_scores = dev_io ? scores : w->scores.p;
@@ -1243,7 +1251,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
             if (r > 0) CU(cudaMemsetAsync(w->gthr.p, 0, size_t(nq) * 4, s));      // (round 0: cleared by query_prep_kernel)
             a.gthr = w->gthr.p;
             const bool gmax_on = use_gmax && rounds == 1;
-            if (gmax_on) { a.gmax = w->gmax.p; a.ngroups = kr; a.gslots = 16; }
+            if (gmax_on) { a.gmax = w->gmax.p; a.ngroups = kr; a.gslots = gslots; }
             a.tile_mul = 1;
             a.stats = nullptr;
             a.tstamps = nullptr;
@@ -1316,7 +1324,7 @@ static int search_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         m.ub_out = (rounds > 1) ? w->ub.p : nullptr;
         m.need_tail = w->flags.p;
         // the exact tensor-core scan leaves a bound that k rows of the query reach (group maxima / compactions) in gthr
-        if (n > 0 && use_mma && rounds == 1 && int64_t(grid) * kp <= kMergeSlots) m.thr_in = w->gthr.p;
+        if (n > 0 && use_mma && rounds == 1) m.thr_in = w->gthr.p;
         // the last merge of the search also appends the NaN tail of the queries that end short (no nan_tail_kernel launch)
         if (n > 0 && r == rounds - 1) {
             m.tail_mask = mask; m.tail_inv_norm = x->inv_norm; m.tail_qinv = w->qinv.p; m.tail_n = n;
@@ -1601,6 +1609,7 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     const int64_t nwords = ceil_div(n, 32);
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
     if (w->part.reserve(size_t(nq) * grid * kp)) return MRAG_ERR_OOM;
+    bool pair_path = false;
     if (n > 0) {
         const uint32_t* mask = x->cols.valid;
         if (filter && filter->flags) {
@@ -1615,13 +1624,56 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                                                                               x->n_jtag_docs, n, w->hmask.p, nwords, ov);
         LAUNCHED();
         CU(cudaEventRecord(ev.e[1], s));
+        // ---- pair path: the floors usually leave a query a small share of the rows; then the rerank runs over the list of
+        //      surviving (query, row) pairs (one warp per pair) instead of 4 queries per pass over every mask word.
+        //      Taken when EVERY query of the batch keeps <= 2^20 rows (a query without required phrases keeps them all and
+        //      sends the batch down the scan below).  MRAG_HYB_PAIRS=0: always scan.
+        static const bool pairs_ok = [] { const char* e = getenv("MRAG_HYB_PAIRS"); return !(e && e[0] == '0'); }();
+        if (pairs_ok) {
+            if (w->npass.reserve(size_t(2) * nq) || w->segoff.reserve(size_t(nq) + 1)) return MRAG_ERR_OOM;
+            CU(cudaMemsetAsync(w->npass.p, 0, size_t(2) * nq * 8, s));
+            hybrid_count_kernel<<<dim3(unsigned(std::min<int64_t>(512, ceil_div(nwords, 256))), unsigned(nq)), 256, 0, s>>>(w->hmask.p, nwords, w->npass.p);
+            LAUNCHED();
+            std::vector<unsigned long long> cnt;
+            cnt.resize(size_t(nq));
+            CU(cudaMemcpyAsync(cnt.data(), w->npass.p, size_t(nq) * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            std::vector<int64_t> seg;
+            seg.resize(size_t(nq) + 1);
+            unsigned long long maxc = 0;
+            seg[0] = 0;
+            for (int i = 0; i < nq; ++i) { seg[size_t(i) + 1] = seg[size_t(i)] + int64_t(cnt[size_t(i)]); maxc = std::max(maxc, cnt[size_t(i)]); }
+            const int64_t total = seg[size_t(nq)];
+            const char* pm_env = getenv("MRAG_HYB_PAIR_MAX");              // read per call: the tests switch between the two paths
+            const unsigned long long pair_max = (pm_env && *pm_env) ? strtoull(pm_env, nullptr, 10) : (1ull << 20);
+            if (maxc <= pair_max && pair_max > 0) {
+                if (w->pair_rows.reserve(size_t(std::max<int64_t>(total, 1))) || w->part.reserve(size_t(std::max<int64_t>(total, 1)))) return MRAG_ERR_OOM;
+                CU(cudaMemcpyAsync(w->segoff.p, seg.data(), (size_t(nq) + 1) * 8, cudaMemcpyHostToDevice, s));
+                CU(cudaStreamSynchronize(s));              // seg is a stack-lifetime host buffer
+                if (total > 0) {
+                    hybrid_fill_kernel<<<dim3(unsigned(std::min<int64_t>(512, ceil_div(nwords, 256))), unsigned(nq)), 256, 0, s>>>(
+                        w->hmask.p, nwords, w->segoff.p, w->npass.p + nq, w->pair_rows.p);
+                    LAUNCHED();
+                    PairArgs pa{};
+                    pa.rows = x->rows; pa.ld = ld; pa.inv_norm = x->inv_norm; pa.q = w->qpad.p; pa.qinv = w->qinv.p;
+                    pa.pair_rows = w->pair_rows.p; pa.seg_off = w->segoff.p; pa.nq = nq; pa.total = total;
+                    pa.feat = x->feat; pa.hyb = w->hyb.p; pa.doc_idx = x->cols.doc_idx; pa.authority = x->cols.authority;
+                    pa.doc_jtags = x->doc_jtags; pa.n_jtag_docs = x->n_jtag_docs; pa.ov = ov; pa.keys = w->part.p;
+                    const unsigned pb = unsigned(ceil_div(total * 32, 256));
+                    if (x->dtype == MRAG_BF16) hybrid_pair_score_kernel<1><<<pb, 256, 0, s>>>(pa);
+                    else hybrid_pair_score_kernel<0><<<pb, 256, 0, s>>>(pa);
+                    LAUNCHED();
+                }
+                pair_path = true;
+            }
+        }
         ScanArgs a{};
         a.rows = x->rows; a.n = n; a.ld = ld; a.mask = mask; a.q = w->qpad.p; a.qinv = w->qinv.p; a.ub = nullptr;
         a.part = w->part.p; a.k = k; a.kp = kp; a.P = grid;
         a.hmask = w->hmask.p; a.hwords = nwords; a.feat = x->feat; a.hyb = w->hyb.p; a.doc_idx = x->cols.doc_idx;
         a.dtag_over = ov;
         a.authority = x->cols.authority; a.doc_jtags = x->doc_jtags; a.n_jtag_docs = x->n_jtag_docs;
-        int q0 = 0;
+        int q0 = pair_path ? nq : 0;
         while (q0 < nq) {
             const int left = nq - q0;
             const int g = gemv_nq_for(left >= 3 ? 4 : left, ld, kp, true);
@@ -1643,6 +1695,18 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     MergeArgs m{};
     m.part = w->part.p; m.P = grid; m.kp = kp; m.nq = nq; m.k = k; m.k_total = k; m.k_off = 0;
     m.scores = w->scores.p; m.rows = w->rows.p; m.counts = w->counts.p; m.row_base = x->row_base; m.no_clamp = 1;
+    t_hybrid_pairs = pair_path;
+    if (pair_path) {
+        // two levels: 8 blocks per query each keep the best k of a slice of the query's segment, then the usual merge of 8 lists
+        // (one block per query left 126 SMs idle: 22 queries x ~34k keys took 0.85 ms)
+        const int slices = 8;
+        if (w->part2.reserve(size_t(nq) * slices * kp)) return MRAG_ERR_OOM;
+        MergeArgs m1 = m;
+        m1.seg_off = w->segoff.p; m1.P = 1; m1.kp = kp; m1.part_out = w->part2.p; m1.lk = 1;
+        merge_kernel<<<dim3(unsigned(nq), unsigned(slices)), kMergeThreads, 0, s>>>(m1);
+        LAUNCHED();
+        m.part = w->part2.p; m.P = slices; m.kp = kp;
+    }
     int rc = launch_merge(w, m, nq, s);
     if (rc != MRAG_OK) return rc;
     if (n > 0) {
@@ -1695,7 +1759,7 @@ extern "C" int mrag_search_hybrid(mrag_index* x, const float* q, int nq, int k, 
         for (size_t i = 0; i < size_t(nq) * k; ++i) cos_out[i] = NAN;
     t_last_ev = *ev;
     t_last_valid = (rc == MRAG_OK);
-    t_last_kind = "gemv_hybrid";
+    t_last_kind = t_hybrid_pairs ? "pairs_hybrid" : "gemv_hybrid";
     release_ws(x, w, nullptr);
     return rc;
 }

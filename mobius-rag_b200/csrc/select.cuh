@@ -41,6 +41,7 @@ struct MergeArgs {
     // NaN tail folded into the last merge of a search (tail_mask != nullptr): a query that ends short of k_total walks the
     // mask for NaN rows in this block instead of in a nan_tail_kernel launch; need_tail is then left alone
     const uint32_t* tail_mask; const float* tail_inv_norm; const float* tail_qinv; int64_t tail_n;
+    const int64_t* seg_off; // if set: query q's keys are the UNSORTED segment part[seg_off[q] .. seg_off[q + 1]) (P, kp ignored)
     const uint32_t* thr_in; // [nq] orderable(score) that k rows of the query are known to reach (the scan's cross-CTA bound), 0 =
                             // unknown; or nullptr.  Replaces the pass over the lists' k-th entries: one dependent round trip less.
 };
@@ -185,13 +186,23 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     const int q = a.qlist ? a.qlist[a.q_lo + blockIdx.x] : int(blockIdx.x);
     const int p_lo = a.part_out ? int(blockIdx.y) * a.Pg : 0;
     const int P = a.part_out ? min(a.Pg, a.P - p_lo) : a.P;
-    const uint64_t* base = a.part + (size_t(q) * a.P + p_lo) * a.kp;
+    // segments: a first-level block (part_out set) takes the blockIdx.y-th slice of the query's segment
+    int64_t seg_lo = 0, seg_hi = 0;
+    if (a.seg_off) {
+        seg_lo = a.seg_off[q]; seg_hi = a.seg_off[q + 1];
+        if (a.part_out) {
+            const int64_t per = (seg_hi - seg_lo + gridDim.y - 1) / gridDim.y;
+            seg_lo = min(seg_hi, seg_lo + int64_t(blockIdx.y) * per);
+            seg_hi = min(seg_hi, seg_lo + per);
+        }
+    }
+    const uint64_t* base = a.seg_off ? a.part + seg_lo : a.part + (size_t(q) * a.P + p_lo) * a.kp;
     if (tid == 0) { s_T = 0ull; s_cnt = 0; }
     __syncthreads();
     uint64_t t = 0;
     if (a.thr_in) {
         if (tid == 0) t = uint64_t(a.thr_in[q]) << 32;          // every key of a row scoring >= the bound compares >= t
-    } else if (a.lk == 0 || a.lk >= a.k) {
+    } else if (!a.seg_off && (a.lk == 0 || a.lk >= a.k)) {
         for (int p = tid; p < P; p += kMergeThreads) {
             uint64_t v = base[size_t(p) * a.kp + (a.k - 1)];
             t = v > t ? v : t;
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(const MergeArgs
     if (t) atomicMax(&s_T, (unsigned long long)t);
     __syncthreads();
     const uint64_t T = s_T;
-    const int total = P * a.kp;
+    const int total = a.seg_off ? int(seg_hi - seg_lo) : P * a.kp;
     int done = 0;
     while (done < total) {
         int kept = s_cnt;                       // uniform: read between two barriers
