@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
     // floor (~6 % of the rows) -- is only MARKED.  Phase 2 (lane = query): the warp takes its marked rows one at a time and
     // the lanes evaluate the queries of the chunk in parallel.  (With phase 2 inline in the thread = row loop nearly every
     // warp held an exempt row and ran the full evaluation, 2 lanes active, for each of the queries: 1.47 ms for 10M rows x
-    // 22 queries, r2y.)
+    // 22 queries, r2y; this version 0.96-1.0 ms, ALU bound at ~50-65 instructions per (warp, query) in phase 1.  Two
+    // variants measured and dropped: per-query constants staged in shared memory + exemptions decided in phase 1 (0.99 ms,
+    // more instructions), and phase 1 with lane = query, the rows' fields travelling by shuffle (1.15 ms: latency bound).)
     union FeatWords { mrag_chunkfeat f; uint32_t w[10]; };
     static_assert(sizeof(mrag_chunkfeat) == 40, "mrag_chunkfeat is broadcast as 10 words");
     for (int q0 = 0; q0 < nq; q0 += 32) {
@@ -257,24 +259,13 @@ struct PairArgs {
     uint64_t* keys;                 // [total] key of the pair, 0 = not eligible (NaN score)
 };
 
-// one warp per (query, row) pair: cosine of the stored row, then the rerank score (same arithmetic as the scan's epilogue)
+// dot product of one stored row with one padded fp32 query, by a whole warp (every lane returns the sum)
 template <int DT>
-__global__ void __launch_bounds__(256) hybrid_pair_score_kernel(const PairArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t p = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (p >= a.total) return;
-    int lo = 0, hi = a.nq;                      // the segment that holds p: seg_off[lo] <= p < seg_off[lo + 1]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(a.seg_off + mid) <= p) lo = mid; else hi = mid;
-    }
-    const int q = lo;
-    const uint32_t row = __ldg(a.pair_rows + p);
-    const float* qrow = a.q + size_t(q) * a.ld;
+MRAG_DEVINL float pair_dot(const void* rows, int ld, uint32_t row, const float* qrow, int lane) {
     float acc = 0.0f;
     if (DT == 1) {
-        const uint4* x = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.rows) + size_t(row) * a.ld);
-        for (int v = lane; v < a.ld / 8; v += 32) {
+        const uint4* x = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rows) + size_t(row) * ld);
+        for (int v = lane; v < ld / 8; v += 32) {
             const uint4 d = ldg_stream(x + v);
             const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v);
             const float4 q1 = __ldg(reinterpret_cast<const float4*>(qrow) + 2 * v + 1);
@@ -284,18 +275,56 @@ __global__ void __launch_bounds__(256) hybrid_pair_score_kernel(const PairArgs a
             acc = fmaf(bf16lo(d.w), q1.z, acc); acc = fmaf(bf16hi(d.w), q1.w, acc);
         }
     } else {
-        const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.rows) + size_t(row) * a.ld);
-        for (int v = lane; v < a.ld / 4; v += 32) {
+        const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + size_t(row) * ld);
+        for (int v = lane; v < ld / 4; v += 32) {
             const uint4 du = ldg_stream(x + v);
             const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow) + v);
             acc = fmaf(__uint_as_float(du.x), q0.x, acc); acc = fmaf(__uint_as_float(du.y), q0.y, acc);
             acc = fmaf(__uint_as_float(du.z), q0.z, acc); acc = fmaf(__uint_as_float(du.w), q0.w, acc);
         }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
+    return warp_sum(acc);
+}
+
+// One warp per 32 consecutive pairs.  Phase A: the warp takes the dot products of its pairs one after the other (four rows
+// in flight), lane j keeps pair j's.  Phase B: every lane turns ITS pair's cosine into the rerank score -- the same
+// arithmetic as the scan's epilogue, 32 pairs at a time instead of one lane working while 31 wait (r2z: the one-pair-per-
+// warp version issued 932 instructions per pair, ~700 of them on a single lane, and was issue bound at 0.92 ms).
+template <int DT>
+__global__ void __launch_bounds__(256) hybrid_pair_score_kernel(const PairArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p0 = ((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (p0 >= a.total) return;
+    const int np = int(min(int64_t(32), a.total - p0));
+    int q = 0;
+    uint32_t row = 0u;
+    if (lane < np) {
+        const int64_t p = p0 + lane;
+        int lo = 0, hi = a.nq;                      // the segment that holds p: seg_off[lo] <= p < seg_off[lo + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(a.seg_off + mid) <= p) lo = mid; else hi = mid;
+        }
+        q = lo;
+        row = __ldg(a.pair_rows + p);
+    }
+    float mydot = 0.0f;
+    for (int j0 = 0; j0 < np; j0 += 4) {
+        float d4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                // independent loads of up to four rows (np is warp uniform)
+            const int j = j0 + u < np ? j0 + u : j0;
+            const uint32_t rj = __shfl_sync(kFull, row, j);
+            const int qj = __shfl_sync(kFull, q, j);
+            d4[u] = pair_dot<DT>(a.rows, a.ld, rj, a.q + size_t(qj) * a.ld, lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane == j0 + u) mydot = d4[u];
+    }
+    if (lane < np) {
         const float inv = a.inv_norm[row];
-        const float cs = isinf(inv) ? CUDART_NAN_F : acc * inv * a.qinv[q];
+        const float cs = isinf(inv) ? CUDART_NAN_F : mydot * inv * a.qinv[q];
         // a NaN similarity reports 1.0 (max(0.0, min(1.0, nan)) in corpus_search.py:1569)
         const float c01 = (cs == cs) ? cs : 1.0f;
         const mrag_chunkfeat f = a.feat[row];
@@ -303,7 +332,7 @@ __global__ void __launch_bounds__(256) hybrid_pair_score_kernel(const PairArgs a
         const uint64_t* jt = (a.doc_jtags && int64_t(d) < a.n_jtag_docs) ? a.doc_jtags + size_t(d) * MRAG_JTAG_WORDS : nullptr;
         const DevHyb& h = a.hyb[q];
         const float s = hybrid_score(h, f, hybrid_eval(h, f, jt, int64_t(row), a.ov), c01, a.authority[row]);
-        a.keys[p] = (s == s) ? make_key(s, row) : 0ull;
+        a.keys[p0 + lane] = (s == s) ? make_key(s, row) : 0ull;
     }
 }
 

@@ -1659,7 +1659,7 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
                     pa.pair_rows = w->pair_rows.p; pa.seg_off = w->segoff.p; pa.nq = nq; pa.total = total;
                     pa.feat = x->feat; pa.hyb = w->hyb.p; pa.doc_idx = x->cols.doc_idx; pa.authority = x->cols.authority;
                     pa.doc_jtags = x->doc_jtags; pa.n_jtag_docs = x->n_jtag_docs; pa.ov = ov; pa.keys = w->part.p;
-                    const unsigned pb = unsigned(ceil_div(total * 32, 256));
+                    const unsigned pb = unsigned(ceil_div(ceil_div(total, 32) * 32, 256));      // one warp per 32 pairs
                     if (x->dtype == MRAG_BF16) hybrid_pair_score_kernel<1><<<pb, 256, 0, s>>>(pa);
                     else hybrid_pair_score_kernel<0><<<pb, 256, 0, s>>>(pa);
                     LAUNCHED();
