@@ -30,6 +30,18 @@ struct DevHyb {
     uint32_t src_restrict;       // source_type_any is not empty
 };
 
+// Per chunk of 32 queries: what phase 1 of hybrid_mask_kernel needs, transposed so that a thread (= row) settles all the
+// chunk's queries with a handful of word operations.  Built on the host (fill_hyb_chunks in mrag.cu).
+struct HybChunk {
+    uint32_t qneed[MRAG_PHRASE_WORDS * 64];   // bit q: query q0 + q can only see dictionary phrase p through its bit (DevHyb::need)
+    uint32_t cnt[5];                          // popcount(need) of every query, bit-sliced (slice b = bit b of the count)
+    uint32_t live, phr, imp, src, contact, dcodes, lowfloor;   // queries that: exist / have phrases / are impossible /
+                                              // restrict source_type / are contact queries / carry d: codes / have a floor < 1
+    uint32_t ncodes;                          // distinct d: codes of the chunk's queries (0xFFFFFFFF: more than 64, no table)
+    uint16_t code[64];
+    uint32_t codemask[64];                    // bit q: query q0 + q carries code[i]
+};
+
 struct HybEval {
     float cov;
     bool dtag_match;
@@ -131,9 +143,19 @@ __global__ void __launch_bounds__(128) rerank_candidates_kernel(const mrag_candi
     keep[i] = hybrid_keep(h, c.feat, e) ? 1 : 0;
 }
 
-// One thread per row, all queries in a loop (the row's features are read once).  Bit (q, r) = row r passes the
-// WHERE mask and query q's coverage floor.  hmask: [nq][nwords].
-__global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restrict__ hq, int nq, const mrag_chunkfeat* __restrict__ feat,
+// One thread per row.  Bit (q, r) = row r passes the WHERE mask and query q's coverage floor.  hmask: [nq][nwords].
+// Phase 1 (thread = row): all 32 queries of a chunk at once, on words whose bit q belongs to query q (HybChunk): which
+// queries find every dictionary bit they need in this row (bit-sliced count of the row's present bits against the
+// queries' need counts), which keep it through an exemption that does not depend on the coverage (promoted, contact
+// value of a contact query, an inline chunk d-tag that matches one of the query's d: codes) -- and which must run the
+// phrase loop (weighted coverage with j-tag credit, overflow d-tags, floors below 1): those pairs are only MARKED.
+// One ballot per query turns the per-row words into the per-query bitmap words.
+// Phase 2 (lane = query): the warp takes its marked rows one at a time; the lanes that marked a row run hybrid_eval.
+// History (10M rows x 22 queries): evaluation inline in a per-query loop 1.47 ms (nearly every warp holds a row that may
+// be exempt and ran it with 2 lanes active, once per query); per-query bit tests + phase 2: 0.96-1.0 ms, ALU bound at
+// 50-65 instructions per (warp, query); the same with lane = query in phase 1: 1.15 ms (shuffle latency).
+__global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restrict__ hq, const HybChunk* __restrict__ chunks, int nq,
+                                                         const mrag_chunkfeat* __restrict__ feat,
                                                          const uint32_t* __restrict__ base_mask, const uint32_t* __restrict__ doc_idx,
                                                          const uint8_t* __restrict__ source_type,
                                                          const uint64_t* __restrict__ doc_jtags, int64_t n_jtag_docs, int64_t n,
@@ -154,32 +176,57 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
             if (doc_jtags && int64_t(d) < n_jtag_docs) jt = doc_jtags + size_t(d) * MRAG_JTAG_WORDS;
         }
     }
-    const bool maybe_exempt = base && ((f.flags & (MRAG_CF_PROMOTED | MRAG_CF_CONTACT_VALUE)) ||
-                                       (f.dtags[0] | f.dtags[1] | f.dtags[2] | f.dtags[3]) != 0u);
-    // Phase 1 (thread = row): the verdicts a few bit tests decide.  A (row, query) pair that needs the weighted coverage,
-    // the j-tag credit or a d-tag lookup -- every required dictionary bit present, or a row that may be exempt from the
-    // floor (~6 % of the rows) -- is only MARKED.  Phase 2 (lane = query): the warp takes its marked rows one at a time and
-    // the lanes evaluate the queries of the chunk in parallel.  (With phase 2 inline in the thread = row loop nearly every
-    // warp held an exempt row and ran the full evaluation, 2 lanes active, for each of the queries: 1.47 ms for 10M rows x
-    // 22 queries, r2y; this version 0.96-1.0 ms, ALU bound at ~50-65 instructions per (warp, query) in phase 1.  Two
-    // variants measured and dropped: per-query constants staged in shared memory + exemptions decided in phase 1 (0.99 ms,
-    // more instructions), and phase 1 with lane = query, the rows' fields travelling by shuffle (1.15 ms: latency bound).)
+    const bool anydtag = base && (f.dtags[0] | f.dtags[1] | f.dtags[2] | f.dtags[3]) != 0u;
+    const bool maybe_exempt = base && ((f.flags & (MRAG_CF_PROMOTED | MRAG_CF_CONTACT_VALUE)) || anydtag);
     union FeatWords { mrag_chunkfeat f; uint32_t w[10]; };
     static_assert(sizeof(mrag_chunkfeat) == 40, "mrag_chunkfeat is broadcast as 10 words");
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int nqc = min(32, nq - q0);
-        uint32_t slow = 0u;                      // bit i: query q0 + i needs the full evaluation of this row
-        for (int i = 0; i < nqc; ++i) {
-            const DevHyb& h = hq[q0 + i];
-            bool keep = base;
-            if (keep && h.src_restrict) keep = (h.q.source_type_any[src >> 6] >> (src & 63)) & 1ull;
-            if (keep && h.q.n_phrases > 0) {
-                const bool bits_ok = !h.impossible && (f.phrase_bits[0] & h.need[0]) == h.need[0] && (f.phrase_bits[1] & h.need[1]) == h.need[1];
-                if (bits_ok || maybe_exempt) slow |= 1u << i;
-                keep = false;
+        const HybChunk& c = chunks[q0 >> 5];
+        uint32_t keepm = 0u, slow = 0u;          // bit i: query q0 + i keeps this row / needs the phrase loop for it
+        if (base) {
+            uint32_t livem = c.live;
+            if (c.src) {                          // rare: some query restricts source_type
+                for (uint32_t m = c.src; m; m &= m - 1) {
+                    const int i = __ffs(m) - 1;
+                    if (!((hq[q0 + i].q.source_type_any[src >> 6] >> (src & 63)) & 1ull)) livem &= ~(1u << i);
+                }
             }
-            const uint32_t word = __ballot_sync(kFull, keep);
-            if (lane == 0 && (r >> 5) < nwords) hmask[size_t(q0 + i) * nwords + (r >> 5)] = word;
+            // queries whose needed dictionary bits are all present: count the row's bits per query, compare with popcount(need)
+            uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u;
+#pragma unroll
+            for (int w = 0; w < MRAG_PHRASE_WORDS; ++w) {
+                for (uint64_t m = f.phrase_bits[w]; m; m &= m - 1) {
+                    uint32_t a = c.qneed[w * 64 + (__ffsll((long long)m) - 1)], t;
+                    t = s0 & a; s0 ^= a; a = t;
+                    t = s1 & a; s1 ^= a; a = t;
+                    t = s2 & a; s2 ^= a; a = t;
+                    t = s3 & a; s3 ^= a; a = t;
+                    s4 ^= a;
+                }
+            }
+            const uint32_t okm = ~((s0 ^ c.cnt[0]) | (s1 ^ c.cnt[1]) | (s2 ^ c.cnt[2]) | (s3 ^ c.cnt[3]) | (s4 ^ c.cnt[4])) & ~c.imp;
+            // exemptions that do not depend on the coverage
+            uint32_t exm = (f.flags & MRAG_CF_PROMOTED) ? c.phr : ((f.flags & MRAG_CF_CONTACT_VALUE) ? c.contact : 0u);
+            uint32_t dslow = 0u;                  // queries whose d: codes need the phrase loop (overflow table / no code table)
+            if (anydtag && c.dcodes) {
+                if (c.ncodes == 0xFFFFFFFFu || (f.flags & MRAG_CF_DTAG_OVERFLOW)) dslow = c.dcodes;
+                if (c.ncodes != 0xFFFFFFFFu) {
+                    for (uint32_t i = 0; i < c.ncodes; ++i) {
+                        const uint32_t code = c.code[i];
+                        if (f.dtags[0] == code || f.dtags[1] == code || f.dtags[2] == code || f.dtags[3] == code) exm |= c.codemask[i];
+                    }
+                }
+            }
+            exm &= c.phr;
+            keepm = livem & (~c.phr | exm);
+            slow = livem & c.phr & ~exm & (okm | dslow | (maybe_exempt ? c.lowfloor : 0u));
+        }
+        uint32_t* hm = hmask + size_t(q0) * nwords + (r >> 5);
+        const bool writer = lane == 0 && (r >> 5) < nwords;
+        for (int i = 0; i < nqc; ++i) {
+            const uint32_t word = __ballot_sync(kFull, (keepm >> i) & 1u);
+            if (writer) hm[size_t(i) * nwords] = word;
         }
         unsigned todo = __ballot_sync(kFull, slow != 0u);
         __syncwarp();                            // the words above are in place before any bit is OR-ed into them

@@ -119,6 +119,7 @@ struct Workspace {
     DevBuf<uint64_t> ckeys;
     DevBuf<int> fb;                 // [0] count, [1..] query list of the exact fallback
     DevBuf<DevHyb> hyb;             // hybrid search: per-query parameters
+    DevBuf<HybChunk> hchunks;       // hybrid search: the same, transposed per chunk of 32 queries (hybrid_mask_kernel phase 1)
     DevBuf<uint32_t> hmask;         // hybrid search: per-query row bitmaps
     DevBuf<uint32_t> pair_rows;     // hybrid search, pair path: rows of the surviving (query, row) pairs, one segment per query
     DevBuf<int64_t> segoff;         // [nq + 1] segment offsets
@@ -128,7 +129,7 @@ struct Workspace {
     void release() {
         qraw.release(); qpad.release(); qinv.release(); scores.release(); qbf.release(); qhl.release();
         mask.release(); pool.release(); pool_bits.release(); gthr.release(); gmax.release(); part.release(); part2.release(); part3.release(); ub.release(); gcand.release();
-        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hmask.release(); pair_rows.release(); segoff.release(); codes.release(); flags.release(); npass.release(); stats.release();
+        rows.release(); counts.release(); crows.release(); ccounts.release(); cscores.release(); ckeys.release(); fb.release(); hyb.release(); hchunks.release(); hmask.release(); pair_rows.release(); segoff.release(); codes.release(); flags.release(); npass.release(); stats.release();
         ev.destroy();
         if (own_stream) cudaStreamDestroy(own_stream);
         own_stream = nullptr;
@@ -1586,6 +1587,38 @@ static void derive_hyb(const mrag_hybrid_query& q, DevHyb* d) {
     for (int i = 0; i < MRAG_SMALL_WORDS; ++i) if (q.source_type_any[i]) d->src_restrict = 1;
 }
 
+// HybChunk of queries [q0, q0 + 32): the transposed per-query constants of hybrid_mask_kernel's phase 1
+static void fill_hyb_chunk(const DevHyb* dh, int q0, int nq, HybChunk* c) {
+    memset(c, 0, sizeof *c);
+    const int nqc = std::min(32, nq - q0);
+    for (int i = 0; i < nqc; ++i) {
+        const DevHyb& h = dh[q0 + i];
+        const uint32_t bit = 1u << i;
+        c->live |= bit;
+        if (h.q.n_phrases > 0) c->phr |= bit;
+        if (h.impossible) c->imp |= bit;
+        if (h.src_restrict) c->src |= bit;
+        if (h.q.contact_query) c->contact |= bit;
+        if (h.has_dcodes) c->dcodes |= bit;
+        if (h.q.floor < 1.0f) c->lowfloor |= bit;
+        int need_bits = 0;
+        for (int p = 0; p < MRAG_PHRASE_WORDS * 64; ++p)
+            if ((h.need[p >> 6] >> (p & 63)) & 1ull) { c->qneed[p] |= bit; ++need_bits; }
+        for (int b = 0; b < 5; ++b) if ((need_bits >> b) & 1) c->cnt[b] |= bit;
+        for (int j = 0; j < h.q.n_phrases; ++j) {
+            const uint16_t dc = uint16_t(h.q.phrase_dcode[j]);
+            if (dc == 0 || c->ncodes == 0xFFFFFFFFu) continue;
+            uint32_t s = 0;
+            while (s < c->ncodes && c->code[s] != dc) ++s;
+            if (s == c->ncodes) {
+                if (c->ncodes == 64) { c->ncodes = 0xFFFFFFFFu; continue; }
+                c->code[c->ncodes++] = dc;
+            }
+            c->codemask[s] |= bit;
+        }
+    }
+}
+
 static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float* q, int nq, int k, const mrag_filter* filter,
                          const mrag_hybrid_query* hq, float* scores, float* cos_out, int64_t* rows, int32_t* counts,
                          cudaStream_t s) {
@@ -1604,7 +1637,12 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
     dh.resize(size_t(nq));
     for (int i = 0; i < nq; ++i) derive_hyb(hq[i], &dh[size_t(i)]);
     CU(cudaMemcpyAsync(w->hyb.p, dh.data(), size_t(nq) * sizeof(DevHyb), cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s));                      // dh is a stack-lifetime host buffer
+    std::vector<HybChunk> hc;
+    hc.resize(size_t(ceil_div(nq, 32)));
+    for (size_t c = 0; c < hc.size(); ++c) fill_hyb_chunk(dh.data(), int(c) * 32, nq, &hc[c]);
+    if (w->hchunks.reserve(hc.size())) return MRAG_ERR_OOM;
+    CU(cudaMemcpyAsync(w->hchunks.p, hc.data(), hc.size() * sizeof(HybChunk), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));                      // dh / hc are stack-lifetime host buffers
     const int kp = std::max(8, host_next_pow2(k));
     const int64_t nwords = ceil_div(n, 32);
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(x->num_sms, ceil_div(nwords, kGemvWarps))));
@@ -1620,7 +1658,7 @@ static int hybrid_locked(mrag_index* x, Workspace* w, EventSet& ev, const float*
         }
         if (w->hmask.reserve(size_t(nq) * nwords)) return MRAG_ERR_OOM;
         const DtagOver ov{x->over_rows, x->over_codes, x->n_over};
-        hybrid_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(w->hyb.p, nq, x->feat, mask, x->cols.doc_idx, x->cols.source_type, x->doc_jtags,
+        hybrid_mask_kernel<<<unsigned(ceil_div(nwords * 32, 256)), 256, 0, s>>>(w->hyb.p, w->hchunks.p, nq, x->feat, mask, x->cols.doc_idx, x->cols.source_type, x->doc_jtags,
                                                                               x->n_jtag_docs, n, w->hmask.p, nwords, ov);
         LAUNCHED();
         CU(cudaEventRecord(ev.e[1], s));
