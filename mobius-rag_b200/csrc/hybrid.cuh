@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
         }
     }
     const bool anydtag = base && (f.dtags[0] | f.dtags[1] | f.dtags[2] | f.dtags[3]) != 0u;
-    const bool maybe_exempt = base && ((f.flags & (MRAG_CF_PROMOTED | MRAG_CF_CONTACT_VALUE)) || anydtag);
     union FeatWords { mrag_chunkfeat f; uint32_t w[10]; };
     static_assert(sizeof(mrag_chunkfeat) == 40, "mrag_chunkfeat is broadcast as 10 words");
     for (int q0 = 0; q0 < nq; q0 += 32) {
@@ -220,7 +219,9 @@ __global__ void __launch_bounds__(256) hybrid_mask_kernel(const DevHyb* __restri
             }
             exm &= c.phr;
             keepm = livem & (~c.phr | exm);
-            slow = livem & c.phr & ~exm & (okm | dslow | (maybe_exempt ? c.lowfloor : 0u));
+            // (a floor below 1 -- the reference's is the constant 1.0, corpus_search.py:614 -- can be met with a phrase
+            //  missing, so such a query takes the phrase loop for every row)
+            slow = livem & c.phr & ~exm & (okm | dslow | c.lowfloor);
         }
         uint32_t* hm = hmask + size_t(q0) * nwords + (r >> 5);
         const bool writer = lane == 0 && (r >> 5) < nwords;
