@@ -155,6 +155,11 @@ int mrag_set_doc_tags(mrag_index* idx, int64_t first_doc, const uint64_t* bits, 
  * clears the valid bit of every row whose doc_idx matches. *n_rows (may be NULL) gets the count. */
 int mrag_tombstone_doc(mrag_index* idx, uint32_t doc_idx, int64_t* n_rows);
 
+/* Of the mrag_size() slots in use: rows that still exist (inserted, not deleted) and rows that still have a vector.
+ * The shard is append-only -- a re-published document (publish.py:310-362: DELETE + INSERT) takes new slots -- so
+ * size - live is what a rebuild (snapshot the live rows, load into a fresh index) reclaims. */
+int mrag_live_rows(mrag_index* idx, int64_t* live_rows, int64_t* rows_with_vector);
+
 int64_t mrag_size(const mrag_index* idx);      /* rows appended so far (incl. tombstoned) */
 int64_t mrag_capacity(const mrag_index* idx);
 int mrag_dim(const mrag_index* idx);

@@ -31,7 +31,7 @@ EXPORTS = [
     "mrag_last_error", "mrag_version",
     "mrag_set_chunk_features", "mrag_set_doc_jtags", "mrag_search_hybrid", "mrag_dtag_mask", "mrag_exchange_merge", "mrag_save", "mrag_load",
     "mrag_set_row_ids", "mrag_set_dtag_overflow", "mrag_rerank_candidates", "mrag_pool_build", "mrag_pool_select", "mrag_pool_add_docs", "mrag_pool_docs", "mrag_pool_destroy",
-    "mrag_set_prepared_event",
+    "mrag_set_prepared_event", "mrag_live_rows",
 ]
 
 
@@ -151,6 +151,8 @@ def load(build_if_missing: bool = True):
     lib.mrag_search.argtypes = [vp, vp, i32, i32, C.POINTER(FilterStruct), vp, vp, vp, u32, vp]
     lib.mrag_set_row_base.restype = i32
     lib.mrag_set_row_base.argtypes = [vp, i64]
+    lib.mrag_live_rows.restype = i32
+    lib.mrag_live_rows.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.mrag_set_prepared_event.restype = i32
     lib.mrag_set_prepared_event.argtypes = [vp, vp]
     lib.mrag_set_row_ids.restype = i32

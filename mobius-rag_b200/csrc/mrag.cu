@@ -433,9 +433,10 @@ static int append_common(mrag_index* x, const float* rows, bool rows_on_device, 
         // order our stream after the producer of d_rows
         cudaEvent_t ev;
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CU(cudaEventRecord(ev, user_stream));
-        CU(cudaStreamWaitEvent(s, ev, 0));
-        cudaEventDestroy(ev);
+        cudaError_t e1 = cudaEventRecord(ev, user_stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(s, ev, 0);
+        cudaEventDestroy(ev);                            // (released on the error path too)
+        if (e1 != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_append_device: cannot order the write stream after the caller's: %s", cudaGetErrorString(e1));
     }
     // default metadata: every row its own document, no codes, vector present
     std::vector<mrag_rowmeta> defmeta;
@@ -549,6 +550,34 @@ extern "C" int mrag_tombstone_doc(mrag_index* x, uint32_t doc_idx, int64_t* n_ro
     cudaFree(d_hit);
     if (e != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_tombstone_doc: %s", cudaGetErrorString(e));
     if (n_rows) *n_rows = int64_t(hit);
+    return MRAG_OK;
+}
+
+// Rows that still exist / that still have a vector, of the mrag_size() slots in use: the shard is append-only (a
+// re-published document gets new slots, publish.py:310-362), so size - live is what a rebuild would reclaim.
+extern "C" int mrag_live_rows(mrag_index* x, int64_t* live_rows, int64_t* rows_with_vector) {
+    if (!x) return fail(MRAG_ERR_ARG, "mrag_live_rows: null index");
+    if (live_rows) *live_rows = 0;
+    if (rows_with_vector) *rows_with_vector = 0;
+    std::shared_lock<std::shared_mutex> rl(x->lock);
+    if (x->size == 0) return MRAG_OK;
+    DeviceGuard g(x->device);
+    if (!g.ok) return fail(MRAG_ERR_CUDA, "mrag_live_rows: cudaSetDevice failed (no CPU path)");
+    unsigned long long* d_out = nullptr;
+    CU(cudaMalloc(&d_out, 16));
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemsetAsync(d_out, 0, 16, x->wstream);
+    if (e == cudaSuccess) {
+        const int64_t nwords = ceil_div(x->size, 32);
+        count_bits_kernel<<<unsigned(std::min<int64_t>(1024, ceil_div(nwords, 256))), 256, 0, x->wstream>>>(x->cols.live, x->cols.valid, x->size, d_out);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, x->wstream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(x->wstream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(MRAG_ERR_CUDA, "mrag_live_rows: %s", cudaGetErrorString(e));
+    if (live_rows) *live_rows = int64_t(h[0]);
+    if (rows_with_vector) *rows_with_vector = int64_t(h[1]);
     return MRAG_OK;
 }
 

@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(256) scatter_meta_kernel(const mrag_rowmeta* _
     const int64_t r = first_row + i;
     c.doc_idx[r] = x.doc_idx; c.payer[r] = x.payer; c.state[r] = x.state; c.program[r] = x.program;
     c.authority[r] = x.authority; c.source_type[r] = x.source_type;
-    if (x.valid) atomicOr(&c.valid[r >> 5], 1u << (r & 31));
-    atomicOr(&c.live[r >> 5], 1u << (r & 31));
+    // the row's bits are WRITTEN, not only set: a slot past `size` may carry bits of an append that failed half way
+    const uint32_t bit = 1u << (r & 31);
+    if (x.valid) atomicOr(&c.valid[r >> 5], bit); else atomicAnd(&c.valid[r >> 5], ~bit);
+    atomicOr(&c.live[r >> 5], bit);
 }
 
 // device copy of mrag_filter without the host pointer
@@ -225,6 +227,24 @@ __global__ void tombstone_kernel(const uint32_t* __restrict__ doc_idx, int64_t n
         uint32_t old = atomicAnd(&valid[r >> 5], ~(1u << (r & 31)));
         atomicAnd(&live[r >> 5], ~(1u << (r & 31)));
         if ((old >> (r & 31)) & 1u) atomicAdd(n_hit, 1ull);
+    }
+}
+
+// out[0] += rows of [0, n) whose `live` bit is set, out[1] += rows whose `valid` bit is set (mrag_live_rows)
+__global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t* __restrict__ live, const uint32_t* __restrict__ valid, int64_t n,
+                                                        unsigned long long* __restrict__ out) {
+    const int64_t nwords = (n + 31) >> 5;
+    unsigned a = 0, b = 0;
+    for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < nwords; w += int64_t(gridDim.x) * blockDim.x) {
+        const uint32_t tail = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
+        a += __popc(live[w] & tail);
+        b += __popc(valid[w] & tail);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(out, (unsigned long long)a);
+        if (b) atomicAdd(out + 1, (unsigned long long)b);
     }
 }
 

@@ -294,6 +294,12 @@ class Index:
         N.check(self._lib.mrag_tombstone_doc(self._h, int(doc_idx), C.byref(n)))
         return int(n.value)
 
+    def live_rows(self) -> tuple[int, int]:
+        """(rows that still exist, rows that still have a vector) of the len(self) slots in use."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        N.check(self._lib.mrag_live_rows(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_row_base(self, base: int) -> None:
         N.check(self._lib.mrag_set_row_base(self._h, int(base)))
 

@@ -215,8 +215,10 @@ def test_tombstone_document(oracle):
     idx.append(X, meta)
     d = int(meta["doc_idx"][2500])
     want_gone = (meta["doc_idx"] == d) & valid.astype(bool)
+    assert idx.live_rows() == (n, int(valid.sum()))
     assert idx.tombstone_doc(d) == int(want_gone.sum())
     assert idx.tombstone_doc(d) == 0
+    assert idx.live_rows() == (n - int((meta["doc_idx"] == d).sum()), int(valid.sum()) - int(want_gone.sum()))
     mask = valid.astype(bool) & ~want_gone
     s, r, c = idx.search(Q, 30)
     check_all(oracle, X, Q, mask, 30, s, r, c, "f32")
