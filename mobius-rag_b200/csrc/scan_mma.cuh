@@ -407,7 +407,8 @@ MRAG_DEVINL void walk_group64(const float (&sc)[64], float& thr, SelState& st, u
 
 // ----------------------------------------------------------------------------------------------
 // KREG = 0: candidates go to per-query shared-memory buffers of k + 64 keys, compacted when full
-//           (k up to 128; large shards get their admission bound from a sampling pass first).
+//           (k up to 128; on large shards the admission bound comes from the cross-CTA group maxima -- GroupBound above --
+//            or, with MRAG_GMAX=0 and in the rounds of k > 128, from a sampling pass first).
 // KREG > 0: k <= KREG; every thread keeps the sorted top-KREG keys of its query in REGISTERS
 //           (branch-free insertion), so its threshold is always the exact k-th best so far:
 //           ~k ln(n/k) insertions per query and CTA, no buffers, no compaction, no sampling pass.
